@@ -1,0 +1,98 @@
+"""Self-checks of the (unpinned) network oracle: SAME-padding conv vs a naive loop restatement of
+lax.conv_general_dilated, autograd gradients vs fp64 finite differences, fp32 vs fp64 agreement,
+optax-Adam arithmetic, shift/sync semantics (idqn.py:13-24) and the schedule trace of SURVEY App. B."""
+import numpy as np
+import torch
+
+from oracle import networks as O
+
+
+def small_batch(rng, B, obs, A, u8=True):
+    if u8:
+        s = rng.integers(0, 256, (B,) + obs).astype(np.uint8)
+        s2 = rng.integers(0, 256, (B,) + obs).astype(np.uint8)
+    else:
+        s = rng.standard_normal((B,) + obs).astype(np.float32)
+        s2 = rng.standard_normal((B,) + obs).astype(np.float32)
+    return dict(state=s, next_state=s2, action=rng.integers(0, A, B).astype(np.int32),
+                reward=rng.integers(-1, 2, B).astype(np.float32), is_terminal=(rng.random(B) < 0.2))
+
+
+def test_same_pad_values():
+    # conv0 (2,2), conv1 (1,2), conv2 (1,1); 84 -> 21 -> 11 -> 11
+    assert O.same_pad(84, 8, 4) == (21, 2, 2)
+    assert O.same_pad(21, 4, 2) == (11, 1, 2)
+    assert O.same_pad(11, 3, 1) == (11, 1, 1)
+    shapes = O.layer_shapes((84, 84, 4), [32, 64, 64, 512], "cnn", 6)
+    assert shapes[3][1] == (7744, 512)
+    assert sum(int(np.prod(k)) + int(np.prod(b)) for _, k, b in shapes) == 4_046_502
+
+
+def test_conv_same_vs_naive():
+    rng = np.random.default_rng(0)
+    for (H, W, C, O_, k, s) in [(21, 21, 3, 5, 4, 2), (13, 10, 2, 3, 8, 4), (11, 11, 4, 4, 3, 1)]:
+        x = rng.standard_normal((2, H, W, C))
+        w = rng.standard_normal((k, k, C, O_))
+        b = rng.standard_normal(O_)
+        y = O._conv_same(torch.as_tensor(x), torch.as_tensor(w), torch.as_tensor(b), s).numpy()
+        np.testing.assert_allclose(y, O.conv_same_naive(x, w, b, s), rtol=1e-12, atol=1e-12)
+
+
+def test_grad_finite_differences_fp64():
+    rng = np.random.default_rng(1)
+    obs, feats, A = (20, 20, 2), [3, 4, 4, 6], 3
+    p = O.init_params(rng, obs, feats, "cnn", A, bias_scale=0.1)
+    pt = O.init_params(rng, obs, feats, "cnn", A, bias_scale=0.1)
+    batch = small_batch(rng, 4, obs, A)
+    loss, g = O.loss_and_grad(p, pt, batch, "cnn", 0.99, 1, torch.float64)
+    eps = 1e-6
+    for name in p["params"]:
+        for leaf in ("kernel", "bias"):
+            arr = p["params"][name][leaf].astype(np.float64)
+            flat_idx = rng.integers(0, arr.size, 3)
+            for fi in flat_idx:
+                pp = {"params": {n: {l: v.astype(np.float64).copy() for l, v in d.items()} for n, d in p["params"].items()}}
+                pm = {"params": {n: {l: v.astype(np.float64).copy() for l, v in d.items()} for n, d in p["params"].items()}}
+                pp["params"][name][leaf].flat[fi] += eps
+                pm["params"][name][leaf].flat[fi] -= eps
+                fd = (O.loss_on_batch(pp, pt, batch, "cnn", 0.99, 1, torch.float64)
+                      - O.loss_on_batch(pm, pt, batch, "cnn", 0.99, 1, torch.float64)) / (2 * eps)
+                assert abs(fd - g["params"][name][leaf].flat[fi]) <= 1e-5 * max(1.0, abs(fd)), (name, leaf, fi)
+
+
+def test_fp32_vs_fp64_and_adam():
+    rng = np.random.default_rng(2)
+    obs, feats, A, K = (8,), [16, 16], 4, 3
+    params = O.init_params(rng, obs, feats, "fc", A, n_networks=K)
+    target = O.init_params(rng, obs, feats, "fc", A, n_networks=K)
+    batch = small_batch(rng, 32, obs + (1,), A, u8=False)
+    st = O.init_optimizer_state(params)
+    p32, s32, l32 = O.learn_on_batch(params, target, st, batch, "fc", 0.99, 1, 3e-4, 1e-8, torch.float32)
+    p64, s64, l64 = O.learn_on_batch(params, target, st, batch, "fc", 0.99, 1, 3e-4, 1e-8, torch.float64)
+    np.testing.assert_allclose(l32, l64, rtol=1e-5)
+    assert (s32["count"] == 1).all()
+    # first Adam step moves every weight with a non-negligible gradient by ~lr (|m_hat|/sqrt(v_hat) == 1)
+    _, g = O.loss_and_grad(O.tree_index(params, 0), O.tree_index(target, 0), batch, "fc", 0.99, 1, torch.float64)
+    gk = g["params"]["Dense_0"]["kernel"]
+    d = p64["params"]["Dense_0"]["kernel"][0] - params["params"]["Dense_0"]["kernel"][0]
+    mask = np.abs(gk) > 1e-4
+    np.testing.assert_allclose(d[mask], -3e-4 * np.sign(gk[mask]), rtol=1e-3)
+
+
+def test_shift_and_sync():
+    K = 4
+    p = {"params": {"Dense_0": {"kernel": np.arange(K * 6, dtype=np.float32).reshape(K, 2, 3), "bias": np.arange(K, dtype=np.float32)[:, None]}}}
+    t = O.tree_map(lambda a: -a, p)
+    s = O.shift_params(p)
+    np.testing.assert_array_equal(s["params"]["Dense_0"]["bias"][:, 0], [1, 2, 3, 3])
+    y = O.sync_target_params(p, t)
+    np.testing.assert_array_equal(y["params"]["Dense_0"]["bias"][:, 0], [-0.0, 0, 1, 2])
+
+
+def test_schedule_trace_appendix_b():
+    sch = O.ScheduleOracle(1, 8, 4)
+    got = {s: sch.events(s) for s in range(1, 17)}
+    assert got[3] == ["grad"] and got[4] == ["grad", "D"] and got[8] == ["grad", "T"]
+    assert got[12] == ["grad", "D"] and got[16] == ["grad", "T"]
+    sch = O.ScheduleOracle(2.0, 8, 4)  # update_to_data is a float flag in the reference
+    assert sch.events(3) == [] and sch.events(4) == ["grad", "D"]
