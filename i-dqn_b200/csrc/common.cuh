@@ -1,0 +1,139 @@
+// Shared declarations of libidqn_b200 (internal; the public surface is include/idqn_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/idqn_b200.h"
+
+void idqn_set_error(const char* fmt, ...);
+
+#define CK(expr)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      idqn_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_));    \
+      return IDQN_ECUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+#define REQUIRE(cond, ...)                                                                     \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      idqn_set_error(__VA_ARGS__);                                                             \
+      return IDQN_EINVAL;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// division by a runtime constant with one mul.hi + shift (valid for 0 <= n < 2^31)
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __host__ __device__ FastDiv() : d(1), mul(0), shr(0) {}
+  __host__ explicit FastDiv(uint32_t div) : d(div), mul(0), shr(0) {
+    if (div > 1) {
+      uint32_t lg = 0;
+      while ((1ull << lg) < div) ++lg;
+      uint32_t p = 31 + lg;
+      mul = (uint32_t)(((1ull << p) + div - 1) / div);
+      shr = p - 32;
+    }
+  }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return d == 1 ? n : (__umulhi(n, mul) >> shr);
+#else
+    return d == 1 ? n : (uint32_t)((((uint64_t)n * mul) >> 32) >> shr);
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// One layer of DQNNet seen as a convolution (Dense == 1x1 conv on a 1x1 image with IC = fan-in).
+struct ConvGeom {
+  int B;                // samples in the batch
+  int IH, IW, IC;       // input  (NHWC)
+  int OH, OW, OC;       // output (NHWC)
+  int KH, KW, S;        // kernel, stride
+  int PH, PW;           // low-side SAME padding (XLA: total//2)
+  int Kd;               // KH*KW*IC  (rows of the flax kernel seen as a [Kd, OC] matrix)
+  FastDiv d_ohow, d_ow, d_kwic, d_ic, d_oc;
+};
+
+struct Layer {
+  ConvGeom g;           // with g.B == cfg.batch_size
+  int is_conv;
+  int64_t w_off, b_off; // float offsets inside a head's arena (b_off == w_off + Kd*OC)
+  int64_t act_off;      // float offset of this layer's output inside one net's activation block (per sample count B)
+  int64_t act_size;     // B*OH*OW*OC
+  char name[16];
+};
+
+#define IDQN_MAX_LAYERS (IDQN_MAX_FEATURES + 1)
+#define IDQN_PROF_MAX 64
+
+struct idqn_handle {
+  idqn_config cfg;
+  int n_layers;
+  Layer layers[IDQN_MAX_LAYERS];
+  int64_t stride;       // floats per head in every arena
+  int64_t in_elems;     // elements of one input sample
+  int K, B, A;
+  cudaStream_t stream;
+  // arenas [K][stride]
+  float *online, *target, *mu, *nu, *grad;
+  int32_t* count;       // [K]
+  float* loss;          // [K] last step
+  double* loss_sum;     // [K] cumulated (idqn.py:72)
+  // batch staging (device)
+  void *s, *s2;         // [B][in_elems] u8 or f32 (allocated for f32)
+  int32_t* action;
+  float* reward;
+  uint8_t* terminal;
+  // activations: nets g in [0,2K): g<K online on s, g>=K target on s'
+  float* act;           // [2K][act_stride]
+  int64_t act_stride;
+  float* dact;          // [K][act_stride]   gradients w.r.t. layer outputs
+  float* q;             // [2K][B][A] final-layer outputs (debug / apply)
+  // split-K workspace
+  float* part;
+  int64_t part_floats;
+  int* tickets;
+  int n_tickets;
+  // pinned host scratch
+  float* h_loss;
+  int32_t* h_i32;
+  // CUDA graph of one learn step, per input dtype (0: f32, 1: u8)
+  cudaGraphExec_t graph[2];
+  int sm_count;
+  // launch accounting / live per-kernel timing (idqn_profile_step)
+  int n_launch;          // kernels enqueued by the last enqueue_learn_step
+  int prof_on, prof_n;
+  cudaEvent_t prof_ev[IDQN_PROF_MAX + 1];
+  char prof_name[IDQN_PROF_MAX][32];
+};
+
+// replay store (replay.cu)
+struct idqn_replay {
+  int device;
+  int64_t n_slots, state_bytes;
+  uint8_t *state, *next_state;
+  int32_t* action;
+  double* reward;
+  uint8_t *terminal, *episode_end;
+  cudaStream_t stream;
+  int64_t* d_slots;  // device copy of gather indices
+  int64_t cap_slots; // capacity of d_slots
+  // pinned staging for gather_host
+  void* h_stage;
+  size_t h_stage_bytes;
+};
+
+int idqn_learn_step_resident(idqn_handle* h, int state_is_u8, float* losses_host);

@@ -1,0 +1,366 @@
+// fp32 CUDA-core implicit GEMM used (a) as the exact-fp32 path for every layer shape the tensor-core
+// path does not cover and (b) as the on-device cross-check of the tcgen05 kernels.
+//
+// C[z][m][n] = sum_k A_z(m,k) * B_z(k,n), with A/B produced on the fly by a "problem" object:
+//   FwdProb    y = relu(conv_SAME(x) * scale + bias)          (architectures/dqn.py:42-52,68)
+//   WgradProb  dW[(ky,kx,c),o] = sum_{b,oy,ox} im2col(x) * dY  (+ bias row), flax kernel layout
+//   DgradProb  dX = conv_transpose(dY, W) masked by relu'(x)   (one stride-parity class per grid.z slice)
+// Split-K partials are combined by the last-arriving CTA in a fixed order (deterministic results).
+#pragma once
+#include "common.cuh"
+
+struct NetPtr {  // per-net pointer selection: nets [0,zsplit) use p0, the rest p1
+  const void* p0;
+  const void* p1;
+  int64_t stride0, stride1;  // in elements of the pointee
+  int zsplit;
+  template <class T>
+  __device__ __forceinline__ const T* get(int z) const {
+    return z < zsplit ? (const T*)p0 + (int64_t)z * stride0 : (const T*)p1 + (int64_t)(z - zsplit) * stride1;
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+struct FwdProb {
+  ConvGeom g;
+  NetPtr x;  // input activations (u8 or f32)
+  NetPtr w;  // head arena base
+  int x_u8;
+  int64_t w_off, b_off;
+  float* y;
+  int64_t ystride;
+  float scale;
+  int relu;
+  int nz, S;  // nets, split-K factor
+  int M, N, K, kchunk;
+
+  struct Ctx {
+    const FwdProb* p;
+    const uint8_t* xu;
+    const float* xf;
+    const float* wk;
+    const float* bias;
+    float* y;
+    int M, kbeg, kend, z;
+    __device__ __forceinline__ float loadA(int m, int k) const {
+      if (m >= M || k >= kend) return 0.f;
+      const ConvGeom& g = p->g;
+      uint32_t b, r, oy, ox, ky, r2, kx, c;
+      g.d_ohow.divmod(m, b, r);
+      g.d_ow.divmod(r, oy, ox);
+      g.d_kwic.divmod(k, ky, r2);
+      g.d_ic.divmod(r2, kx, c);
+      int iy = (int)(oy * g.S + ky) - g.PH, ix = (int)(ox * g.S + kx) - g.PW;
+      if ((unsigned)iy >= (unsigned)g.IH || (unsigned)ix >= (unsigned)g.IW) return 0.f;
+      int64_t idx = (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + c;
+      return xu ? (float)__ldg(xu + idx) : __ldg(xf + idx);
+    }
+    __device__ __forceinline__ float loadB(int k, int n) const {
+      if (k >= kend || n >= p->N) return 0.f;
+      return __ldg(wk + (int64_t)k * p->N + n);
+    }
+    __device__ __forceinline__ void store(int m, int n, float acc) const {
+      if (m >= M || n >= p->N) return;
+      float v = acc * p->scale + __ldg(bias + n);
+      if (p->relu) v = fmaxf(v, 0.f);
+      y[(int64_t)m * p->N + n] = v;
+    }
+  };
+  __device__ __forceinline__ Ctx ctx(int zz) const {
+    Ctx c;
+    int z = zz / S, sp = zz - z * S;
+    c.p = this;
+    c.z = z;
+    const float* base = w.get<float>(z);
+    c.wk = base + w_off;
+    c.bias = base + b_off;
+    c.xu = x_u8 ? x.get<uint8_t>(z) : nullptr;
+    c.xf = x_u8 ? nullptr : x.get<float>(z);
+    c.y = y + (int64_t)z * ystride;
+    c.M = M;
+    c.kbeg = sp * kchunk;
+    c.kend = min(K, c.kbeg + kchunk);
+    return c;
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+struct WgradProb {
+  ConvGeom g;
+  NetPtr x;   // layer input (u8 / f32)
+  int x_u8;
+  const float* dy;  // [nz][B*OH*OW][OC]
+  int64_t dystride;
+  float* gout;      // grad arena base; row m of the [Kd+1, OC] result goes to gout[z*gstride + w_off + m*OC + n]
+  int64_t gstride, w_off;
+  float scale;      // 1/255 for the u8/255 first layer (applied to kernel rows only)
+  int nz, S;
+  int M, N, K, kchunk;
+
+  struct Ctx {
+    const WgradProb* p;
+    const uint8_t* xu;
+    const float* xf;
+    const float* dy;
+    float* out;
+    int M, kbeg, kend, z;
+    __device__ __forceinline__ float loadA(int m, int k) const {  // = im2col(x)[row k][col m]; row Kd = ones
+      if (m >= M || k >= kend) return 0.f;
+      const ConvGeom& g = p->g;
+      if (m == g.Kd) return 1.f;
+      uint32_t b, r, oy, ox, ky, r2, kx, c;
+      g.d_ohow.divmod(k, b, r);
+      g.d_ow.divmod(r, oy, ox);
+      g.d_kwic.divmod(m, ky, r2);
+      g.d_ic.divmod(r2, kx, c);
+      int iy = (int)(oy * g.S + ky) - g.PH, ix = (int)(ox * g.S + kx) - g.PW;
+      if ((unsigned)iy >= (unsigned)g.IH || (unsigned)ix >= (unsigned)g.IW) return 0.f;
+      int64_t idx = (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + c;
+      return xu ? (float)__ldg(xu + idx) : __ldg(xf + idx);
+    }
+    __device__ __forceinline__ float loadB(int k, int n) const {
+      if (k >= kend || n >= p->N) return 0.f;
+      return __ldg(dy + (int64_t)k * p->N + n);
+    }
+    __device__ __forceinline__ void store(int m, int n, float acc) const {
+      if (m >= M || n >= p->N) return;
+      out[(int64_t)m * p->N + n] = (m < p->g.Kd) ? acc * p->scale : acc;
+    }
+  };
+  __device__ __forceinline__ Ctx ctx(int zz) const {
+    Ctx c;
+    int z = zz / S, sp = zz - z * S;
+    c.p = this;
+    c.z = z;
+    c.xu = x_u8 ? x.get<uint8_t>(z) : nullptr;
+    c.xf = x_u8 ? nullptr : x.get<float>(z);
+    c.dy = dy + (int64_t)z * dystride;
+    c.out = gout + (int64_t)z * gstride + w_off;
+    c.M = M;
+    c.kbeg = sp * kchunk;
+    c.kend = min(K, c.kbeg + kchunk);
+    return c;
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+#define IDQN_MAX_CLASSES 16
+struct DgradProb {
+  ConvGeom g;
+  const float* dy;  // [nz][B*OH*OW][OC]
+  int64_t dystride;
+  NetPtr w;         // head arena base (online)
+  int64_t w_off;
+  const float* xact;  // layer input activations (relu outputs) [nz][B*IH*IW*IC] for the mask
+  float* dx;          // same shape
+  int64_t xstride;
+  int nz, S;          // S: split-K (always 1 here)
+  int ncls;           // S_conv^2 stride-parity classes
+  int JH, JW;         // taps per class per axis: ceil(KH/S), ceil(KW/S)
+  int N, K, kchunk, M;  // M = max rows over classes (grid sizing)
+  FastDiv d_jwoc;       // JW*OC
+  int cls_niy[IDQN_MAX_CLASSES], cls_nix[IDQN_MAX_CLASSES];
+  FastDiv cls_d_n[IDQN_MAX_CLASSES], cls_d_nix[IDQN_MAX_CLASSES];  // niy*nix, nix
+
+  struct Ctx {
+    const DgradProb* p;
+    const float* dy;
+    const float* wk;
+    const float* xact;
+    float* dx;
+    int M, kbeg, kend, z;
+    int py, px, ky0, kx0;
+    FastDiv d_n, d_nix;
+    __device__ __forceinline__ void rowdec(int m, uint32_t& b, int& iy, int& ix) const {
+      uint32_t r, iyp, ixp;
+      d_n.divmod(m, b, r);
+      d_nix.divmod(r, iyp, ixp);
+      iy = iyp * p->g.S + py;
+      ix = ixp * p->g.S + px;
+    }
+    __device__ __forceinline__ float loadA(int m, int k) const {
+      if (m >= M || k >= kend) return 0.f;
+      const ConvGeom& g = p->g;
+      uint32_t b, jy, r2, jx, co;
+      int iy, ix;
+      rowdec(m, b, iy, ix);
+      p->d_jwoc.divmod(k, jy, r2);
+      g.d_oc.divmod(r2, jx, co);
+      int ky = ky0 + jy * g.S, kx = kx0 + jx * g.S;
+      if (ky >= g.KH || kx >= g.KW) return 0.f;
+      int ny = iy + g.PH - ky, nx = ix + g.PW - kx;
+      if (ny < 0 || nx < 0) return 0.f;
+      int oy = ny / g.S, ox = nx / g.S;  // exact by construction of the class
+      if (oy >= g.OH || ox >= g.OW) return 0.f;
+      return __ldg(dy + (((int64_t)b * g.OH + oy) * g.OW + ox) * g.OC + co);
+    }
+    __device__ __forceinline__ float loadB(int k, int n) const {
+      if (k >= kend || n >= p->N) return 0.f;
+      const ConvGeom& g = p->g;
+      uint32_t jy, r2, jx, co;
+      p->d_jwoc.divmod(k, jy, r2);
+      g.d_oc.divmod(r2, jx, co);
+      int ky = ky0 + jy * g.S, kx = kx0 + jx * g.S;
+      if (ky >= g.KH || kx >= g.KW) return 0.f;
+      return __ldg(wk + ((int64_t)(ky * g.KW + kx) * g.IC + n) * g.OC + co);
+    }
+    __device__ __forceinline__ void store(int m, int n, float acc) const {
+      if (m >= M || n >= p->N) return;
+      const ConvGeom& g = p->g;
+      uint32_t b;
+      int iy, ix;
+      rowdec(m, b, iy, ix);
+      int64_t idx = (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + n;
+      dx[idx] = xact[idx] > 0.f ? acc : 0.f;  // relu'(0) = 0 as in jax
+    }
+  };
+  __device__ __forceinline__ Ctx ctx(int zz) const {
+    Ctx c;
+    int z = zz / ncls, cl = zz - z * ncls;
+    c.p = this;
+    c.z = z;
+    c.py = cl / g.S;
+    c.px = cl - c.py * g.S;
+    c.ky0 = (c.py + g.PH) % g.S;
+    c.kx0 = (c.px + g.PW) % g.S;
+    c.d_n = cls_d_n[cl];
+    c.d_nix = cls_d_nix[cl];
+    c.M = g.B * cls_niy[cl] * cls_nix[cl];
+    c.dy = dy + (int64_t)z * dystride;
+    c.wk = w.get<float>(z) + w_off;
+    c.xact = xact + (int64_t)z * xstride;
+    c.dx = dx + (int64_t)z * xstride;
+    c.kbeg = 0;
+    c.kend = K;
+    return c;
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+// The kernel: BMxBN tile, BK=16, 4x4 register tile per thread, register-prefetched single smem stage.
+template <int BM, int BN, bool A_KFAST, bool B_KFAST, class P>
+__global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_simt_kernel(const P p, float* __restrict__ part,
+                                                                       int* __restrict__ tickets) {
+  constexpr int BK = 16;
+  constexpr int NT = (BM / 4) * (BN / 4);
+  constexpr int EA = BM * BK / NT;
+  constexpr int EB = BK * BN / NT;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x;
+  const typename P::Ctx c = p.ctx(blockIdx.z);
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (m0 >= c.M) return;  // dgrad classes have fewer rows than the grid was sized for (uniform per CTA)
+
+  const int ty = tid / (BN / 4), tx = tid % (BN / 4);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float ra[EA], rb[EB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < EA; ++i) {
+      int e = tid + i * NT;
+      int ak = A_KFAST ? e % BK : e / BM;
+      int am = A_KFAST ? e / BK : e % BM;
+      ra[i] = c.loadA(m0 + am, k0 + ak);
+    }
+#pragma unroll
+    for (int i = 0; i < EB; ++i) {
+      int e = tid + i * NT;
+      int bk = B_KFAST ? e % BK : e / BN;
+      int bn = B_KFAST ? e / BK : e % BN;
+      rb[i] = c.loadB(k0 + bk, n0 + bn);
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < EA; ++i) {
+      int e = tid + i * NT;
+      int ak = A_KFAST ? e % BK : e / BM;
+      int am = A_KFAST ? e / BK : e % BM;
+      As[ak][am] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < EB; ++i) {
+      int e = tid + i * NT;
+      int bk = B_KFAST ? e % BK : e / BN;
+      int bn = B_KFAST ? e / BK : e % BN;
+      Bs[bk][bn] = rb[i];
+    }
+  };
+
+  if (c.kbeg < c.kend) {
+    fetch(c.kbeg);
+    for (int k0 = c.kbeg; k0 < c.kend; k0 += BK) {
+      stash();
+      __syncthreads();
+      if (k0 + BK < c.kend) fetch(k0 + BK);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float a4[4] = {av.x, av.y, av.z, av.w};
+        const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  if (p.S > 1) {
+    // deterministic split-K: publish the partial, the last CTA of this (net, tile) adds all S of them in order
+    const int z = blockIdx.z / p.S, sp = blockIdx.z - z * p.S;
+    const int tiles = gridDim.x * gridDim.y;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    float* mine = part + ((int64_t)(z * tiles + tile) * p.S + sp) * (16 * NT);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) __stcg(mine + (i * 4 + j) * NT + tid, acc[i][j]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      int t = atomicAdd(&tickets[z * tiles + tile], 1);
+      s_last = (t == p.S - 1);
+      if (s_last) tickets[z * tiles + tile] = 0;  // self-reset for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* base = part + (int64_t)(z * tiles + tile) * p.S * (16 * NT);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+        for (int q = 0; q < p.S; ++q) s += __ldcg(base + (int64_t)q * (16 * NT) + (i * 4 + j) * NT + tid);
+        acc[i][j] = s;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c.store(m0 + ty * 4 + i, n0 + tx * 4 + j, acc[i][j]);
+}
+
+// host-side launcher: picks the tile shape from N and returns the launch geometry it used
+template <bool A_KFAST, bool B_KFAST, class P>
+static inline cudaError_t launch_gemm_simt(const P& p, int gridz, float* part, int* tickets, cudaStream_t st) {
+  if (p.N <= 32) {
+    dim3 grid((p.M + 63) / 64, (p.N + 31) / 32, gridz);
+    gemm_simt_kernel<64, 32, A_KFAST, B_KFAST, P><<<grid, 128, 0, st>>>(p, part, tickets);
+  } else {
+    dim3 grid((p.M + 63) / 64, (p.N + 63) / 64, gridz);
+    gemm_simt_kernel<64, 64, A_KFAST, B_KFAST, P><<<grid, 256, 0, st>>>(p, part, tickets);
+  }
+  return cudaGetLastError();
+}

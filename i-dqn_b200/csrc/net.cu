@@ -1,0 +1,790 @@
+// libidqn_b200 — the i-DQN learning step (idqn.py:96-124 of the reference) on one B200.
+//
+// One step = forward of 2K nets (K online heads on s, K target heads on s'), the fused
+// final-layer + Bellman-target + TD-loss kernel, backward of the K online heads, Adam.
+// The sequence is captured once into a CUDA graph and replayed.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void idqn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* idqn_last_error(void) { return g_err; }
+extern "C" int idqn_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------
+// geometry
+static void same_pad(int in, int k, int s, int* out, int* lo) {
+  *out = (in + s - 1) / s;
+  int total = std::max((*out - 1) * s + k - in, 0);
+  *lo = total / 2;  // XLA: pad_lo = total // 2
+}
+
+static void finish_geom(ConvGeom& g) {
+  g.Kd = g.KH * g.KW * g.IC;
+  g.d_ohow = FastDiv(g.OH * g.OW);
+  g.d_ow = FastDiv(g.OW);
+  g.d_kwic = FastDiv(g.KW * g.IC);
+  g.d_ic = FastDiv(g.IC);
+  g.d_oc = FastDiv(g.OC);
+}
+
+static int build_layers(idqn_handle* h) {
+  const idqn_config& c = h->cfg;
+  int L = 0;
+  int ih, iw, ic, start = 0;
+  if (c.arch == IDQN_ARCH_CNN) {
+    REQUIRE(c.n_features >= 3, "cnn needs >= 3 features (architectures/dqn.py:43-51)");
+    static const int ks[3][2] = {{8, 4}, {4, 2}, {3, 1}};
+    ih = c.obs[0], iw = c.obs[1], ic = c.obs[2];
+    for (int i = 0; i < 3; ++i) {
+      Layer& l = h->layers[L++];
+      memset(&l, 0, sizeof(l));
+      l.is_conv = 1;
+      ConvGeom& g = l.g;
+      g.B = c.batch_size;
+      g.IH = ih, g.IW = iw, g.IC = ic;
+      g.KH = g.KW = ks[i][0];
+      g.S = ks[i][1];
+      g.OC = c.features[i];
+      same_pad(ih, g.KH, g.S, &g.OH, &g.PH);
+      same_pad(iw, g.KW, g.S, &g.OW, &g.PW);
+      finish_geom(g);
+      snprintf(l.name, sizeof(l.name), "Conv_%d", i);
+      ih = g.OH, iw = g.OW, ic = g.OC;
+    }
+    start = 3;
+    h->in_elems = (int64_t)c.obs[0] * c.obs[1] * c.obs[2];
+  } else if (c.arch == IDQN_ARCH_FC) {
+    ih = iw = 1;
+    ic = c.obs[0] * std::max(c.obs[1], 1) * std::max(c.obs[2], 1);
+    h->in_elems = ic;
+  } else {
+    REQUIRE(false, "unknown architecture %d", c.arch);
+  }
+  int fan_in = ih * iw * ic;
+  for (int i = start; i <= c.n_features; ++i) {
+    REQUIRE(L < IDQN_MAX_LAYERS, "too many layers");
+    Layer& l = h->layers[L++];
+    memset(&l, 0, sizeof(l));
+    ConvGeom& g = l.g;
+    g.B = c.batch_size;
+    g.IH = g.IW = g.OH = g.OW = 1;
+    g.KH = g.KW = g.S = 1;
+    g.IC = fan_in;
+    g.OC = (i == c.n_features) ? c.n_actions : c.features[i];
+    finish_geom(g);
+    snprintf(l.name, sizeof(l.name), "Dense_%d", i - start);
+    fan_in = g.OC;
+  }
+  h->n_layers = L;
+  int64_t off = 0, aoff = 0;
+  for (int i = 0; i < L; ++i) {
+    Layer& l = h->layers[i];
+    REQUIRE(l.g.OC > 0 && l.g.Kd > 0, "layer %d has an empty dimension", i);
+    off = (off + 31) / 32 * 32;  // 128-byte aligned layer start
+    l.w_off = off;
+    l.b_off = off + (int64_t)l.g.Kd * l.g.OC;  // bias directly after the kernel: [Kd+1, OC] block
+    off = l.b_off + l.g.OC;
+    l.act_off = aoff;
+    l.act_size = (int64_t)c.batch_size * l.g.OH * l.g.OW * l.g.OC;
+    aoff += (l.act_size + 31) / 32 * 32;
+  }
+  h->stride = (off + 127) / 128 * 128;
+  h->act_stride = aoff;
+  return IDQN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch planning (tile shape, split-K) — shared by workspace sizing and launching
+struct GemmPlan {
+  int bn, gx, gy, S, kchunk;
+  int64_t part_floats;
+  int tickets;
+};
+static GemmPlan plan_gemm(int M, int N, int K, int nz, int sms, bool allow_split) {
+  GemmPlan p;
+  p.bn = N <= 32 ? 32 : 64;
+  p.gx = (M + 63) / 64;
+  p.gy = (N + p.bn - 1) / p.bn;
+  int tiles = p.gx * p.gy * nz;
+  int kiters = (K + 15) / 16;
+  int S = 1;
+  if (allow_split && tiles < 2 * sms) {
+    S = (2 * sms + tiles - 1) / tiles;
+    S = std::min(S, std::max(1, kiters / 4));
+    S = std::min(S, 64);
+  }
+  int it_per = (kiters + S - 1) / S;
+  p.kchunk = it_per * 16;
+  S = (K + p.kchunk - 1) / p.kchunk;
+  p.S = S;
+  p.part_floats = S > 1 ? (int64_t)nz * p.gx * p.gy * S * 64 * p.bn : 0;
+  p.tickets = S > 1 ? nz * p.gx * p.gy : 0;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused final Dense layer (fwd + bwd) + Bellman target + TD loss     (idqn.py:111-124; dqn.py:77-87)
+struct HeadArgs {
+  NetPtr hid;  // last hidden activations, nets [0,K) online / [K,2K) target, [B][H] each
+  int H, A, B, K;
+  const float* online;
+  const float* target;
+  int64_t stride, w_off, b_off;
+  const int32_t* action;
+  const float* reward;
+  const uint8_t* terminal;
+  float gamma_n;
+  float* grad;   // arena
+  float* dhid;   // [K][dstride] gradient w.r.t. the hidden activations (masked by relu'), may be null
+  int64_t dstride;
+  int relu_mask;
+  float* loss;
+  double* loss_sum;
+  int32_t* count;
+  float* q;      // [2K][B][A]
+};
+
+__global__ void __launch_bounds__(256) head_loss_kernel(const HeadArgs a) {
+  extern __shared__ float sm[];
+  const int k = blockIdx.x;
+  const int B = a.B, A = a.A, H = a.H;
+  float* qs = sm;               // [2][B][A]
+  float* coef = sm + 2 * B * A; // [B]
+  float* lterm = coef + B;      // [B]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const float* W[2] = {a.online + (int64_t)k * a.stride + a.w_off, a.target + (int64_t)k * a.stride + a.w_off};
+  const float* bias[2] = {a.online + (int64_t)k * a.stride + a.b_off, a.target + (int64_t)k * a.stride + a.b_off};
+  const float* hid[2] = {a.hid.get<float>(k), a.hid.get<float>(a.K + k)};
+
+  // 1. Q(theta_k, s_b)[.] and Q(theta_bar_k, s'_b)[.]
+  for (int pair = warp; pair < 2 * B; pair += nwarp) {
+    const int net = pair / B, b = pair - net * B;
+    const float* hv = hid[net] + (int64_t)b * H;
+    for (int act = 0; act < A; ++act) {
+      float s = 0.f;
+      for (int j = lane; j < H; j += 32) s = fmaf(hv[j], __ldg(W[net] + (int64_t)j * A + act), s);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) {
+        float v = s + __ldg(bias[net] + act);
+        qs[(net * B + b) * A + act] = v;
+        a.q[((int64_t)(net * a.K + k) * B + b) * A + act] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // 2. y = r + (1-done) * gamma^n * max_a' Q_target ; delta = Q(s,a) - y
+  for (int b = tid; b < B; b += blockDim.x) {
+    float mx = qs[(B + b) * A];
+    for (int act = 1; act < A; ++act) mx = fmaxf(mx, qs[(B + b) * A + act]);
+    float notdone = a.terminal[b] ? 0.f : 1.f;
+    float y = a.reward[b] + (notdone * a.gamma_n) * mx;
+    float d = qs[b * A + a.action[b]] - y;
+    lterm[b] = d * d;
+    coef[b] = 2.f * d / (float)B;  // d mean_b(delta^2) / d Q(s_b, a_b)
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += lterm[b];
+    s /= (float)B;
+    a.loss[k] = s;
+    a.loss_sum[k] += (double)s;
+    a.count[k] += 1;  // ScaleByAdamState.count, read by the Adam kernel that follows
+  }
+  // 3. dW[j][act] = sum_b [a_b == act] coef_b h[b][j];  db[act] = sum_b [a_b == act] coef_b
+  float* gW = a.grad + (int64_t)k * a.stride + a.w_off;
+  for (int idx = tid; idx < H * A; idx += blockDim.x) {
+    const int j = idx / A, act = idx - j * A;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b)
+      if (a.action[b] == act) s = fmaf(coef[b], hid[0][(int64_t)b * H + j], s);
+    gW[idx] = s;
+  }
+  float* gb = a.grad + (int64_t)k * a.stride + a.b_off;
+  for (int act = tid; act < A; act += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b)
+      if (a.action[b] == act) s += coef[b];
+    gb[act] = s;
+  }
+  // 4. dh[b][j] = relu'(h) * coef_b * W[j][a_b]
+  if (a.dhid) {
+    float* dh = a.dhid + (int64_t)k * a.dstride;
+    for (int idx = tid; idx < B * H; idx += blockDim.x) {
+      const int b = idx / H, j = idx - b * H;
+      float v = coef[b] * __ldg(W[0] + (int64_t)j * A + a.action[b]);
+      if (a.relu_mask && !(hid[0][idx] > 0.f)) v = 0.f;
+      dh[idx] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// optax.adam (scale_by_adam b1=.9 b2=.999 eps, eps_root=0; scale(-lr); apply_updates)  idqn.py:52,106-107
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                   float4* __restrict__ m, float4* __restrict__ v,
+                                                   const int32_t* __restrict__ count, int64_t n4_per_head, float lr,
+                                                   float b1, float b2, float eps) {
+  const int k = blockIdx.y;
+  const float t = (float)count[k];  // already incremented for this step
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+  const int64_t base = (int64_t)k * n4_per_head;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4_per_head;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 P = p[base + i], G = __ldcs(g + base + i), M = m[base + i], V = v[base + i];
+    float* pp = &P.x;
+    const float* gg = &G.x;
+    float* mm = &M.x;
+    float* vv = &V.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float mn = omb1 * gg[e] + b1 * mm[e];
+      float vn = omb2 * (gg[e] * gg[e]) + b2 * vv[e];
+      float upd = (mn / bc1) / (sqrtf(vn / bc2) + eps);
+      pp[e] = pp[e] + (-lr) * upd;
+      mm[e] = mn;
+      vv[e] = vn;
+    }
+    p[base + i] = P;
+    m[base + i] = M;
+    v[base + i] = V;
+  }
+}
+
+__global__ void argmax_kernel(const float* __restrict__ q, int A, int32_t* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int best = 0;
+    float bv = q[0];
+    for (int i = 1; i < A; ++i)
+      if (q[i] > bv) bv = q[i], best = i;  // first maximum, like jnp.argmax
+    *out = best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// every kernel launch of the step goes through mark(): counts launches and, when profiling, drops an event
+static void mark(idqn_handle* h, const char* fmt, int li) {
+  h->n_launch++;
+  if (h->prof_on && h->prof_n < IDQN_PROF_MAX) {
+    snprintf(h->prof_name[h->prof_n], 32, fmt, li);
+    cudaEventRecord(h->prof_ev[h->prof_n + 1], h->stream);
+    h->prof_n++;
+  }
+}
+
+static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nsamples, NetPtr x, int x_u8, NetPtr w, float* y,
+                            int64_t ystride, int relu) {
+  const Layer& l = h->layers[li];
+  FwdProb p;
+  p.g = l.g;
+  p.g.B = nsamples;
+  p.x = x;
+  p.x_u8 = x_u8;
+  p.w = w;
+  p.w_off = l.w_off;
+  p.b_off = l.b_off;
+  p.y = y;
+  p.ystride = ystride;
+  p.scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;  // architectures/dqn.py:44
+  p.relu = relu;
+  p.nz = nz;
+  p.M = nsamples * l.g.OH * l.g.OW;
+  p.N = l.g.OC;
+  p.K = l.g.Kd;
+  GemmPlan gp = plan_gemm(p.M, p.N, p.K, nz, h->sm_count, true);
+  p.S = gp.S;
+  p.kchunk = gp.kchunk;
+  if (gp.part_floats > h->part_floats || gp.tickets > h->n_tickets) {
+    idqn_set_error("internal: split-K workspace too small (fwd layer %d)", li);
+    return IDQN_EINVAL;
+  }
+  CK((launch_gemm_simt<true, false>(p, nz * p.S, h->part, h->tickets, h->stream)));
+  mark(h, "fwd_L%d", li);
+  return IDQN_OK;
+}
+
+static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8) {
+  const Layer& l = h->layers[li];
+  const int K = h->K;
+  WgradProb p;
+  p.g = l.g;
+  if (li == 0) {
+    p.x = NetPtr{h->s, h->s, 0, 0, K};
+  } else {
+    const float* xin = h->act + h->layers[li - 1].act_off;
+    p.x = NetPtr{xin, xin, h->act_stride, h->act_stride, K};
+  }
+  p.x_u8 = (li == 0) ? x_u8 : 0;
+  p.dy = h->dact + l.act_off;
+  p.dystride = h->act_stride;
+  p.gout = h->grad;
+  p.gstride = h->stride;
+  p.w_off = l.w_off;
+  p.scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;
+  p.nz = K;
+  p.M = l.g.Kd + 1;
+  p.N = l.g.OC;
+  p.K = h->B * l.g.OH * l.g.OW;
+  GemmPlan gp = plan_gemm(p.M, p.N, p.K, K, h->sm_count, true);
+  p.S = gp.S;
+  p.kchunk = gp.kchunk;
+  if (gp.part_floats > h->part_floats || gp.tickets > h->n_tickets) {
+    idqn_set_error("internal: split-K workspace too small (wgrad layer %d)", li);
+    return IDQN_EINVAL;
+  }
+  CK((launch_gemm_simt<false, false>(p, K * p.S, h->part, h->tickets, h->stream)));
+  mark(h, "wgrad_L%d", li);
+  return IDQN_OK;
+}
+
+static int launch_dgrad_layer(idqn_handle* h, int li) {  // writes dact of layer li-1
+  const Layer& l = h->layers[li];
+  const Layer& prev = h->layers[li - 1];
+  const int K = h->K;
+  DgradProb p;
+  p.g = l.g;
+  p.dy = h->dact + l.act_off;
+  p.dystride = h->act_stride;
+  p.w = NetPtr{h->online, h->online, h->stride, h->stride, K};
+  p.w_off = l.w_off;
+  p.xact = h->act + prev.act_off;
+  p.dx = h->dact + prev.act_off;
+  p.xstride = h->act_stride;
+  p.nz = K;
+  p.S = 1;
+  const int S = l.g.S;
+  p.ncls = S * S;
+  if (p.ncls > IDQN_MAX_CLASSES) {
+    idqn_set_error("stride %d not supported in dgrad", S);
+    return IDQN_EINVAL;
+  }
+  p.JH = (l.g.KH + S - 1) / S;
+  p.JW = (l.g.KW + S - 1) / S;
+  p.d_jwoc = FastDiv(p.JW * l.g.OC);
+  p.N = l.g.IC;
+  p.K = p.JH * p.JW * l.g.OC;
+  p.kchunk = p.K;
+  int maxM = 0;
+  for (int cl = 0; cl < p.ncls; ++cl) {
+    int py = cl / S, px = cl % S;
+    int niy = (l.g.IH - py + S - 1) / S, nix = (l.g.IW - px + S - 1) / S;
+    niy = std::max(niy, 0), nix = std::max(nix, 0);
+    p.cls_niy[cl] = niy;
+    p.cls_nix[cl] = nix;
+    p.cls_d_n[cl] = FastDiv(std::max(niy * nix, 1));
+    p.cls_d_nix[cl] = FastDiv(std::max(nix, 1));
+    maxM = std::max(maxM, h->B * niy * nix);
+  }
+  p.M = maxM;
+  CK((launch_gemm_simt<true, true>(p, K * p.ncls, h->part, h->tickets, h->stream)));
+  mark(h, "dgrad_L%d", li);
+  return IDQN_OK;
+}
+
+// enqueue one whole learning step on h->stream (batch already staged in h->s/s2/action/reward/terminal)
+static int enqueue_learn_step(idqn_handle* h, int x_u8) {
+  const int K = h->K, L = h->n_layers, B = h->B;
+  h->n_launch = 0;
+  // forward of 2K nets through all hidden layers
+  for (int li = 0; li < L - 1; ++li) {
+    NetPtr x;
+    if (li == 0) {
+      x = NetPtr{h->s, h->s2, 0, 0, K};
+    } else {
+      const float* xin = h->act + h->layers[li - 1].act_off;
+      x = NetPtr{xin, xin, h->act_stride, h->act_stride, 2 * K};
+    }
+    NetPtr w{h->online, h->target, h->stride, h->stride, K};
+    int rc = launch_fwd_layer(h, li, 2 * K, B, x, li == 0 ? x_u8 : 0, w, h->act + h->layers[li].act_off,
+                              h->act_stride, 1);
+    if (rc) return rc;
+  }
+  // final layer + loss + its backward
+  {
+    const Layer& l = h->layers[L - 1];
+    HeadArgs a;
+    if (L >= 2) {
+      const float* hid = h->act + h->layers[L - 2].act_off;
+      a.hid = NetPtr{hid, hid, h->act_stride, h->act_stride, 2 * K};
+      a.dhid = h->dact + h->layers[L - 2].act_off;
+      a.relu_mask = 1;
+    } else {
+      REQUIRE(!x_u8, "a network without hidden layers needs float32 inputs");
+      a.hid = NetPtr{h->s, h->s2, 0, 0, K};
+      a.dhid = nullptr;
+      a.relu_mask = 0;
+    }
+    a.H = l.g.Kd, a.A = h->A, a.B = B, a.K = K;
+    a.online = h->online, a.target = h->target;
+    a.stride = h->stride, a.w_off = l.w_off, a.b_off = l.b_off;
+    a.action = h->action, a.reward = h->reward, a.terminal = h->terminal;
+    a.gamma_n = h->cfg.gamma_n;
+    a.grad = h->grad;
+    a.dstride = h->act_stride;
+    a.loss = h->loss, a.loss_sum = h->loss_sum, a.count = h->count;
+    a.q = h->q;
+    size_t smem = (size_t)(2 * B * h->A + 2 * B) * sizeof(float);
+    head_loss_kernel<<<K, 256, smem, h->stream>>>(a);
+    CK(cudaGetLastError());
+    mark(h, "head_loss_L%d", L - 1);
+  }
+  // backward through the hidden layers
+  for (int li = L - 2; li >= 0; --li) {
+    int rc = launch_wgrad_layer(h, li, x_u8);
+    if (rc) return rc;
+    if (li > 0) {
+      rc = launch_dgrad_layer(h, li);
+      if (rc) return rc;
+    }
+  }
+  // Adam over the whole arena of every head
+  {
+    int64_t n4 = h->stride / 4;
+    int bx = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)h->sm_count * 8);
+    dim3 grid(bx, K);
+    adam_kernel<<<grid, 256, 0, h->stream>>>((float4*)h->online, (const float4*)h->grad, (float4*)h->mu,
+                                             (float4*)h->nu, h->count, n4, h->cfg.learning_rate, 0.9f, 0.999f,
+                                             h->cfg.adam_eps);
+    CK(cudaGetLastError());
+    mark(h, "adam", 0);
+  }
+  return IDQN_OK;
+}
+
+int idqn_learn_step_resident(idqn_handle* h, int x_u8, float* losses_host) {
+  x_u8 = x_u8 ? 1 : 0;
+  if (h->cfg.flags & IDQN_F_NO_GRAPH) {
+    int rc = enqueue_learn_step(h, x_u8);
+    if (rc) return rc;
+  } else {
+    if (!h->graph[x_u8]) {
+      cudaGraph_t g;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_learn_step(h, x_u8);
+      cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+      if (rc) return rc;
+      CK(e);
+      CK(cudaGraphInstantiate(&h->graph[x_u8], g, 0));
+      CK(cudaGraphDestroy(g));
+    }
+    CK(cudaGraphLaunch(h->graph[x_u8], h->stream));
+  }
+  if (losses_host) {
+    CK(cudaMemcpyAsync(h->h_loss, h->loss, sizeof(float) * h->K, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(losses_host, h->h_loss, sizeof(float) * h->K);
+  }
+  return IDQN_OK;
+}
+
+extern "C" int idqn_kernels_per_step(idqn_handle* h) {
+  if (!h) return 0;
+  if (!h->n_launch) {  // dry count without touching state: replicate the launch plan
+    int n = (h->n_layers - 1) + 1 + (h->n_layers - 1) + std::max(h->n_layers - 2, 0) + 1;
+    return n;
+  }
+  return h->n_launch;
+}
+
+extern "C" int idqn_profile_step(idqn_handle* h, int x_u8, int max_entries, float* ms, char* names, int* n_out) {
+  REQUIRE(h && ms && names && n_out, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  for (int i = 0; i <= IDQN_PROF_MAX; ++i)
+    if (!h->prof_ev[i]) CK(cudaEventCreate(&h->prof_ev[i]));
+  h->prof_on = 1, h->prof_n = 0;
+  CK(cudaEventRecord(h->prof_ev[0], h->stream));
+  int rc = enqueue_learn_step(h, x_u8 ? 1 : 0);
+  h->prof_on = 0;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  int n = std::min(h->prof_n, max_entries);
+  for (int i = 0; i < n; ++i) {
+    CK(cudaEventElapsedTime(&ms[i], h->prof_ev[i], h->prof_ev[i + 1]));
+    memcpy(names + 32 * i, h->prof_name[i], 32);
+  }
+  *n_out = n;
+  return IDQN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
+  REQUIRE(cfg && out, "null argument");
+  REQUIRE(cfg->n_heads >= 1 && cfg->batch_size >= 1 && cfg->n_actions >= 1, "bad sizes");
+  REQUIRE(cfg->n_features >= 0 && cfg->n_features <= IDQN_MAX_FEATURES, "bad n_features");
+  idqn_handle* h = new idqn_handle();
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->K = cfg->n_heads, h->B = cfg->batch_size, h->A = cfg->n_actions;
+  int rc = build_layers(h);
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  REQUIRE(prop.major == 10, "libidqn_b200 is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
+  h->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const int K = h->K, B = h->B;
+  const size_t arena = sizeof(float) * h->stride * K;
+  float** arenas[5] = {&h->online, &h->target, &h->mu, &h->nu, &h->grad};
+  for (auto a : arenas) {
+    CK(cudaMalloc(a, arena));
+    CK(cudaMemsetAsync(*a, 0, arena, h->stream));
+  }
+  CK(cudaMalloc(&h->count, sizeof(int32_t) * K));
+  CK(cudaMemsetAsync(h->count, 0, sizeof(int32_t) * K, h->stream));
+  CK(cudaMalloc(&h->loss, sizeof(float) * K));
+  CK(cudaMemsetAsync(h->loss, 0, sizeof(float) * K, h->stream));
+  CK(cudaMalloc(&h->loss_sum, sizeof(double) * K));
+  CK(cudaMemsetAsync(h->loss_sum, 0, sizeof(double) * K, h->stream));
+  CK(cudaMalloc(&h->s, sizeof(float) * h->in_elems * B));
+  CK(cudaMalloc(&h->s2, sizeof(float) * h->in_elems * B));
+  CK(cudaMalloc(&h->action, sizeof(int32_t) * B));
+  CK(cudaMalloc(&h->reward, sizeof(float) * B));
+  CK(cudaMalloc(&h->terminal, B));
+  CK(cudaMalloc(&h->act, sizeof(float) * h->act_stride * 2 * K));
+  CK(cudaMalloc(&h->dact, sizeof(float) * h->act_stride * K));
+  CK(cudaMemsetAsync(h->dact, 0, sizeof(float) * h->act_stride * K, h->stream));
+  CK(cudaMalloc(&h->q, sizeof(float) * 2 * K * B * h->A));
+  // split-K workspace: maximum over every launch the step will make
+  int64_t part = 0;
+  int tickets = 0;
+  for (int li = 0; li < h->n_layers; ++li) {
+    const ConvGeom& g = h->layers[li].g;
+    GemmPlan f = plan_gemm(B * g.OH * g.OW, g.OC, g.Kd, 2 * K, h->sm_count, true);
+    GemmPlan w = plan_gemm(g.Kd + 1, g.OC, B * g.OH * g.OW, K, h->sm_count, true);
+    part = std::max(part, std::max(f.part_floats, w.part_floats));
+    tickets = std::max(tickets, std::max(f.tickets, w.tickets));
+  }
+  h->part_floats = std::max<int64_t>(part, 1);
+  h->n_tickets = std::max(tickets, 1);
+  CK(cudaMalloc(&h->part, sizeof(float) * h->part_floats));
+  CK(cudaMalloc(&h->tickets, sizeof(int) * h->n_tickets));
+  CK(cudaMemsetAsync(h->tickets, 0, sizeof(int) * h->n_tickets, h->stream));
+  CK(cudaMallocHost(&h->h_loss, sizeof(float) * std::max(K, B * h->A)));
+  CK(cudaMallocHost(&h->h_i32, sizeof(int32_t) * std::max(K, 4)));
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return IDQN_OK;
+}
+
+extern "C" int idqn_destroy(idqn_handle* h) {
+  if (!h) return IDQN_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < 2; ++i)
+    if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
+  for (int i = 0; i <= IDQN_PROF_MAX; ++i)
+    if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
+  void* ptrs[] = {h->online, h->target, h->mu,     h->nu,  h->grad, h->count, h->loss, h->loss_sum, h->s,
+                  h->s2,     h->action, h->reward, h->terminal, h->act,  h->dact,  h->q,    h->part,     h->tickets};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->h_loss) cudaFreeHost(h->h_loss);
+  if (h->h_i32) cudaFreeHost(h->h_i32);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return IDQN_OK;
+}
+
+extern "C" int64_t idqn_arena_stride(const idqn_handle* h) { return h ? h->stride : 0; }
+extern "C" int idqn_leaf_count(const idqn_handle* h) { return h ? 2 * h->n_layers : 0; }
+extern "C" int idqn_leaf_info(const idqn_handle* h, int leaf, int64_t* offset, int64_t* size, int32_t shape[4],
+                              int32_t* ndim, char name[16]) {
+  REQUIRE(h && leaf >= 0 && leaf < 2 * h->n_layers, "bad leaf index");
+  const Layer& l = h->layers[leaf / 2];
+  if (leaf % 2 == 0) {
+    *offset = l.w_off;
+    *size = (int64_t)l.g.Kd * l.g.OC;
+    if (l.is_conv) {
+      shape[0] = l.g.KH, shape[1] = l.g.KW, shape[2] = l.g.IC, shape[3] = l.g.OC;
+      *ndim = 4;
+    } else {
+      shape[0] = l.g.Kd, shape[1] = l.g.OC, shape[2] = shape[3] = 0;
+      *ndim = 2;
+    }
+  } else {
+    *offset = l.b_off;
+    *size = l.g.OC;
+    shape[0] = l.g.OC, shape[1] = shape[2] = shape[3] = 0;
+    *ndim = 1;
+  }
+  memcpy(name, l.name, 16);
+  return IDQN_OK;
+}
+
+static float* arena_of(idqn_handle* h, int which) {
+  switch (which) {
+    case IDQN_ONLINE: return h->online;
+    case IDQN_TARGET: return h->target;
+    case IDQN_MU: return h->mu;
+    case IDQN_NU: return h->nu;
+    case IDQN_GRAD: return h->grad;
+  }
+  return nullptr;
+}
+
+extern "C" void* idqn_arena_ptr(idqn_handle* h, int which) { return h ? arena_of(h, which) : nullptr; }
+extern "C" void* idqn_stream(idqn_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+extern "C" int idqn_upload(idqn_handle* h, int which, int head, int64_t offset, const float* src, int64_t n) {
+  float* a = h ? arena_of(h, which) : nullptr;
+  REQUIRE(a && which != IDQN_GRAD, "bad arena");
+  REQUIRE(head >= 0 && head < h->K && offset >= 0 && n >= 0 && offset + n <= h->stride, "range outside the arena");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(a + (int64_t)head * h->stride + offset, src, sizeof(float) * n, cudaMemcpyHostToDevice,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return IDQN_OK;
+}
+extern "C" int idqn_download(idqn_handle* h, int which, int head, int64_t offset, float* dst, int64_t n) {
+  float* a = h ? arena_of(h, which) : nullptr;
+  REQUIRE(a, "bad arena");
+  REQUIRE(head >= 0 && head < h->K && offset >= 0 && n >= 0 && offset + n <= h->stride, "range outside the arena");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(dst, a + (int64_t)head * h->stride + offset, sizeof(float) * n, cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return IDQN_OK;
+}
+extern "C" int idqn_set_count(idqn_handle* h, const int32_t* c) {
+  REQUIRE(h && c, "null argument");
+  CK(cudaMemcpyAsync(h->count, c, sizeof(int32_t) * h->K, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return IDQN_OK;
+}
+extern "C" int idqn_get_count(idqn_handle* h, int32_t* c) {
+  REQUIRE(h && c, "null argument");
+  CK(cudaMemcpyAsync(c, h->count, sizeof(int32_t) * h->K, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return IDQN_OK;
+}
+
+static int stage_batch(idqn_handle* h, const void* s, const void* s2, int u8, const int32_t* a, const float* r,
+                       const uint8_t* d, cudaMemcpyKind kind) {
+  REQUIRE(h && s && s2 && a && r && d, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t sb = (size_t)h->in_elems * h->B * (u8 ? 1 : 4);
+  CK(cudaMemcpyAsync(h->s, s, sb, kind, h->stream));
+  CK(cudaMemcpyAsync(h->s2, s2, sb, kind, h->stream));
+  CK(cudaMemcpyAsync(h->action, a, sizeof(int32_t) * h->B, kind, h->stream));
+  CK(cudaMemcpyAsync(h->reward, r, sizeof(float) * h->B, kind, h->stream));
+  CK(cudaMemcpyAsync(h->terminal, d, h->B, kind, h->stream));
+  return IDQN_OK;
+}
+
+extern "C" int idqn_learn_on_batch_host(idqn_handle* h, const void* s, const void* s2, int u8, const int32_t* a,
+                                        const float* r, const uint8_t* d, float* losses) {
+  int rc = stage_batch(h, s, s2, u8, a, r, d, cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  return idqn_learn_step_resident(h, u8, losses);
+}
+extern "C" int idqn_learn_on_batch_dev(idqn_handle* h, const void* s, const void* s2, int u8, const int32_t* a,
+                                       const float* r, const uint8_t* d, float* losses) {
+  int rc = stage_batch(h, s, s2, u8, a, r, d, cudaMemcpyDeviceToDevice);
+  if (rc) return rc;
+  return idqn_learn_step_resident(h, u8, losses);
+}
+
+extern "C" int idqn_read_cumulated_losses(idqn_handle* h, double* sums, int reset) {
+  REQUIRE(h && sums, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(sums, h->loss_sum, sizeof(double) * h->K, cudaMemcpyDeviceToHost, h->stream));
+  if (reset) CK(cudaMemsetAsync(h->loss_sum, 0, sizeof(double) * h->K, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return IDQN_OK;
+}
+
+extern "C" int idqn_shift_params(idqn_handle* h) {  // idqn.py:13-17
+  REQUIRE(h, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  for (int k = 0; k + 1 < h->K; ++k)
+    CK(cudaMemcpyAsync(h->online + (int64_t)k * h->stride, h->online + (int64_t)(k + 1) * h->stride,
+                       sizeof(float) * h->stride, cudaMemcpyDeviceToDevice, h->stream));
+  return IDQN_OK;
+}
+extern "C" int idqn_sync_target(idqn_handle* h) {  // idqn.py:20-24
+  REQUIRE(h, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->K > 1)
+    CK(cudaMemcpyAsync(h->target + h->stride, h->online, sizeof(float) * h->stride * (h->K - 1),
+                       cudaMemcpyDeviceToDevice, h->stream));
+  return IDQN_OK;
+}
+extern "C" int idqn_copy_online_to_target(idqn_handle* h) {  // idqn.py:78, dqn.py:52
+  REQUIRE(h, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->target, h->online, sizeof(float) * h->stride * h->K, cudaMemcpyDeviceToDevice, h->stream));
+  return IDQN_OK;
+}
+
+// network.apply of one head on n <= B inputs (already staged in h->s), result in h->q[0..n*A)
+static int enqueue_apply(idqn_handle* h, int which, int head, int u8, int n) {
+  const float* base = arena_of(h, which) + (int64_t)head * h->stride;
+  NetPtr w{base, base, 0, 0, 1};
+  for (int li = 0; li < h->n_layers; ++li) {
+    NetPtr x;
+    if (li == 0) {
+      x = NetPtr{h->s, h->s, 0, 0, 1};
+    } else {
+      const float* xin = h->act + h->layers[li - 1].act_off;
+      x = NetPtr{xin, xin, 0, 0, 1};
+    }
+    const bool last = li == h->n_layers - 1;
+    float* y = last ? h->q : h->act + h->layers[li].act_off;
+    int rc = launch_fwd_layer(h, li, 1, n, x, li == 0 ? u8 : 0, w, y, 0, last ? 0 : 1);
+    if (rc) return rc;
+  }
+  return IDQN_OK;
+}
+
+extern "C" int idqn_apply_host(idqn_handle* h, int which, int head, const void* x, int u8, int n, float* q) {
+  REQUIRE(h && x && q && n >= 0, "bad argument");
+  REQUIRE(which == IDQN_ONLINE || which == IDQN_TARGET, "apply needs the online or target arena");
+  REQUIRE(head >= 0 && head < h->K, "bad head");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t esz = u8 ? 1 : 4;
+  for (int done = 0; done < n; done += h->B) {
+    const int m = std::min(h->B, n - done);
+    CK(cudaMemcpyAsync(h->s, (const char*)x + (size_t)done * h->in_elems * esz, (size_t)m * h->in_elems * esz,
+                       cudaMemcpyHostToDevice, h->stream));
+    int rc = enqueue_apply(h, which, head, u8, m);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(q + (size_t)done * h->A, h->q, sizeof(float) * m * h->A, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return IDQN_OK;
+}
+
+extern "C" int idqn_best_action(idqn_handle* h, int which, int head, const void* state, int u8, int32_t* action) {
+  REQUIRE(h && state && action, "bad argument");
+  REQUIRE(which == IDQN_ONLINE || which == IDQN_TARGET, "best_action needs the online or target arena");
+  REQUIRE(head >= 0 && head < h->K, "bad head");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->s, state, (size_t)h->in_elems * (u8 ? 1 : 4), cudaMemcpyHostToDevice, h->stream));
+  int rc = enqueue_apply(h, which, head, u8, 1);
+  if (rc) return rc;
+  int32_t* d_out = (int32_t*)h->loss;  // scratch would alias the loss; use the tail of q instead
+  d_out = (int32_t*)(h->q + h->A);     // q[0..A) holds the values, the next word receives the index
+  argmax_kernel<<<1, 32, 0, h->stream>>>(h->q, h->A, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_i32, d_out, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *action = h->h_i32[0];
+  return IDQN_OK;
+}

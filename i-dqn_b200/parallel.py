@@ -1,0 +1,161 @@
+"""Head sharding of one i-DQN chain over several B200s — one process per GPU.
+
+The K heads share no parameters and see the same batch, so rank r simply owns a contiguous block of heads and
+runs the ordinary single-GPU step on it: there is NO per-step collective.  The only cross-GPU traffic is the
+neighbour exchange of one head's parameters (16.2 MB for NatureCNN) at the target events of idqn.py:74-94:
+
+* D-sync  target[k] <- online[k-1]:  rank r receives the LAST online head of rank r-1 into its target[0];
+* T-shift online[k] <- online[k+1]:  rank r receives the FIRST online head of rank r+1 (its value before that
+  rank's own shift — the read-before-overwrite hazard is avoided by staging the send first) into its last slot.
+
+Transfers are NCCL send/recv pairs over NVLink issued on the learner's own CUDA stream, so they are ordered
+with the step's kernels without host synchronisation.  The functions below work on any torch tensors, which is
+how the protocol is tested on CPU with the gloo backend (tests/test_parallel_gloo.py).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+def head_partition(n_heads_total: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous (start, count) block of heads per rank; the first ``K % world`` ranks hold one more."""
+    base, extra = divmod(n_heads_total, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        cnt = base + (1 if r < extra else 0)
+        out.append((start, cnt))
+        start += cnt
+    return out
+
+
+def _neighbours(rank: int, parts: List[Tuple[int, int]]):
+    """Previous / next rank that actually owns heads (ranks with an empty block are skipped)."""
+    prev = next((r for r in range(rank - 1, -1, -1) if parts[r][1] > 0), None)
+    nxt = next((r for r in range(rank + 1, len(parts)) if parts[r][1] > 0), None)
+    return prev, nxt
+
+
+def exchange_for_sync(online, target, rank: int, parts, dist, group=None) -> None:
+    """sync_target_params (idqn.py:20-24) across shards.  ``online``/``target``: [K_local, stride] tensors."""
+    import torch
+
+    k_local = parts[rank][1]
+    if k_local == 0:
+        return
+    prev, nxt = _neighbours(rank, parts)
+    ops = []
+    if nxt is not None:
+        ops.append(dist.P2POp(dist.isend, online[k_local - 1], nxt, group))
+    recv = None
+    if prev is not None:
+        recv = torch.empty_like(target[0])
+        ops.append(dist.P2POp(dist.irecv, recv, prev, group))
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    if k_local > 1:
+        target[1:].copy_(online[:-1])
+    for r in reqs:
+        r.wait()
+    if recv is not None:
+        target[0].copy_(recv)
+
+
+def exchange_for_shift(online, rank: int, parts, dist, group=None) -> None:
+    """shift_params (idqn.py:13-17) across shards: online[k] <- online[k+1] over the GLOBAL head index."""
+    import torch
+
+    k_local = parts[rank][1]
+    if k_local == 0:
+        return
+    prev, nxt = _neighbours(rank, parts)
+    ops = []
+    send_buf = None
+    if prev is not None:
+        send_buf = online[0].clone()  # stage the pre-shift value: the slot is overwritten below
+        ops.append(dist.P2POp(dist.isend, send_buf, prev, group))
+    recv = None
+    if nxt is not None:
+        recv = torch.empty_like(online[0])
+        ops.append(dist.P2POp(dist.irecv, recv, nxt, group))
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    for k in range(k_local - 1):
+        online[k].copy_(online[k + 1])
+    for r in reqs:
+        r.wait()
+    if recv is not None:
+        online[k_local - 1].copy_(recv)
+
+
+class _CudaView:
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def arena_tensor(engine, which: int):
+    """Zero-copy torch view [K_local, stride] of one of the engine's arenas (for NCCL / peer copies)."""
+    import torch
+
+    return torch.as_tensor(_CudaView(engine.arena_ptr(which), (engine.K, engine.stride)),
+                           device=f"cuda:{engine.device}")
+
+
+def engine_stream(engine):
+    import torch
+
+    return torch.cuda.ExternalStream(int(engine.lib.idqn_stream(engine.h)), device=f"cuda:{engine.device}")
+
+
+def make_sharded_idqn(key, observation_dim, n_actions, n_networks_total: int, features, architecture_type,
+                      learning_rate, gamma, update_horizon, update_to_data, target_update_frequency,
+                      target_sync_frequency, adam_eps=1e-8, *, rank: int, world_size: int, device: int,
+                      batch_size: int = 32, flags: int = 0, group=None):
+    """This rank's shard of a ``n_networks_total``-head i-DQN as an ``iDQN`` whose target events exchange the
+    boundary heads with the neighbouring ranks.  Requires an initialised NCCL process group."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib as L
+    from . import _prng
+    from .networks.idqn import iDQN
+
+    parts = head_partition(n_networks_total, world_size)
+    start, k_local = parts[rank]
+    if k_local == 0:
+        raise ValueError(f"rank {rank} owns no head: use world_size <= n_networks ({n_networks_total})")
+
+    class ShardediDQN(iDQN):
+        def update_target_params(self, step: int):
+            eng = self._engine
+            if step % self.target_update_frequency == 0:
+                eng.copy_online_to_target()
+                with torch.cuda.stream(self._stream):
+                    exchange_for_shift(self._online, rank, parts, dist, group)
+                cumulated = eng.cumulated_losses(reset=True)
+                denom = self.target_update_frequency / self.update_to_data
+                logs = {"loss": np.mean(cumulated) / denom}
+                for i in range(self.n_networks):
+                    logs[f"networks/{start + i}_loss"] = cumulated[i] / denom
+                return True, logs
+            if step % self.target_sync_frequency == 0:
+                with torch.cuda.stream(self._stream):
+                    exchange_for_sync(self._online, self._target, rank, parts, dist, group)
+            return False, {}
+
+    torch.cuda.set_device(device)
+    # every rank derives the same K_total head keys and keeps its own block
+    keys = _prng.split(key, n_networks_total)
+    agent = ShardediDQN(0, observation_dim, n_actions, k_local, features, architecture_type, learning_rate, gamma,
+                        update_horizon, update_to_data, target_update_frequency, target_sync_frequency, adam_eps,
+                        batch_size=batch_size, device=device, flags=flags)
+    obs = tuple(int(d) for d in np.atleast_1d(observation_dim))
+    heads = [agent.network.init(k, np.zeros(obs, np.float32)) for k in keys[start:start + k_local]]
+    from .networks.idqn import _map_stack
+    agent._engine.upload_tree(L.ONLINE, _map_stack(heads))
+    agent._engine.copy_online_to_target()
+    agent._online = arena_tensor(agent._engine, L.ONLINE)
+    agent._target = arena_tensor(agent._engine, L.TARGET)
+    agent._stream = engine_stream(agent._engine)
+    agent.head_offset, agent.n_networks_total = start, n_networks_total
+    return agent

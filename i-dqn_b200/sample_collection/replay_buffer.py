@@ -1,0 +1,238 @@
+"""``ReplayBuffer`` — drop-in for slimdqn/sample_collection/replay_buffer.py with the element store resident
+in HBM (csrc/replay.cu) instead of a host ``OrderedDict`` of snappy blobs.
+
+What stays on the host (env-rate, a few hundred bytes per step): the n-step/frame-stack accumulator
+(:103-200) and the sampler's key bookkeeping.  What moves to the device: element storage (``add`` uploads
+the two stacks once, :207-210) and the batch assembly of ``sample`` (:222-230), which becomes one coalesced
+gather kernel writing straight into the learner's batch staging (``learn_step_on``), so the per-step
+dict-lookup + decompress + np.stack + H2D path of the reference disappears.
+
+FIFO semantics are the reference's: keys are the cumulative ``add_count`` (:207), the oldest key is evicted
+once ``add_count > max_capacity`` (:211-213); key ``k`` lives in slot ``k % max_capacity``."""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+import dataclasses
+import typing
+import weakref
+import zlib
+from typing import Any, Iterable, Iterator, Optional
+
+import numpy as np
+
+from .. import _lib as L
+from . import ReplayItemID
+
+
+class TransitionElement(typing.NamedTuple):  # replay_buffer.py:18-23
+    observation: Any
+    action: int
+    reward: float
+    is_terminal: bool
+    episode_end: bool = False
+
+
+@dataclasses.dataclass(frozen=True)
+class ReplayElement:  # replay_buffer.py:26-69
+    state: Any
+    action: Any
+    reward: Any
+    next_state: Any
+    is_terminal: Any
+    episode_end: Any
+
+    def replace(self, **changes) -> "ReplayElement":
+        return dataclasses.replace(self, **changes)
+
+    # The reference packs with snappy (:36-57), which is a host-storage detail; the device store keeps raw
+    # bytes.  pack/unpack are kept for API parity (round trip pinned by tests/test_replay_buffer.py:21-49 of the
+    # reference) on top of zlib from the standard library.
+    @staticmethod
+    def compress(buffer: np.ndarray):
+        buffer = np.ascontiguousarray(buffer)
+        return (zlib.compress(buffer.tobytes(), 1), buffer.shape, buffer.dtype.str)
+
+    @staticmethod
+    def uncompress(packed) -> np.ndarray:
+        blob, shape, dtype = packed
+        return np.frombuffer(zlib.decompress(blob), dtype=dtype).reshape(shape).copy()
+
+    def pack(self) -> "ReplayElement":
+        return self.replace(state=self.compress(self.state), next_state=self.compress(self.next_state))
+
+    def unpack(self) -> "ReplayElement":
+        return self.replace(state=self.uncompress(self.state), next_state=self.uncompress(self.next_state))
+
+
+class _DeviceStore:
+    """Fixed-slot element store in HBM."""
+
+    def __init__(self, n_slots: int, obs_shape, obs_dtype, device: int):
+        self.lib = L.lib()
+        self.shape, self.dtype = tuple(obs_shape), np.dtype(obs_dtype)
+        self.state_bytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.n_slots, self.device = int(n_slots), int(device)
+        h = C.c_void_p()
+        L.check(self.lib.idqn_replay_create(self.n_slots, self.state_bytes, self.device, C.byref(h)))
+        self.h = h
+        self._finalizer = weakref.finalize(self, self.lib.idqn_replay_destroy, h)
+
+    def put(self, slot: int, el: ReplayElement) -> None:
+        s = np.ascontiguousarray(el.state, dtype=self.dtype)
+        s2 = np.ascontiguousarray(el.next_state, dtype=self.dtype)
+        if s.shape != self.shape or s2.shape != self.shape:
+            raise ValueError(f"element shape {s.shape} differs from the store's {self.shape}")
+        L.check(self.lib.idqn_replay_put(self.h, int(slot), L.ptr(s), L.ptr(s2), int(el.action), float(el.reward),
+                                         int(bool(el.is_terminal)), int(bool(el.episode_end))))
+
+    def gather(self, slots: np.ndarray):
+        n = len(slots)
+        slots = np.ascontiguousarray(slots, dtype=np.int64)
+        s = np.empty((n,) + self.shape, self.dtype)
+        s2 = np.empty((n,) + self.shape, self.dtype)
+        a, r = np.empty(n, np.int32), np.empty(n, np.float64)
+        d, e = np.empty(n, np.uint8), np.empty(n, np.uint8)
+        L.check(self.lib.idqn_replay_gather_host(self.h, L.ptr(slots), n, L.ptr(s), L.ptr(s2), L.ptr(a), L.ptr(r),
+                                                 L.ptr(d), L.ptr(e)))
+        return s, s2, a.astype(np.int64), r, d.astype(bool), e.astype(bool)
+
+
+class _MemoryView(collections.abc.Mapping):
+    """``rb._memory`` of the reference (an OrderedDict key -> ReplayElement) as a read-only view of the
+    device store: live keys in insertion order, elements fetched on access."""
+
+    def __init__(self, rb: "ReplayBuffer"):
+        self._rb = rb
+
+    def _range(self) -> range:
+        rb = self._rb
+        return range(max(0, rb.add_count - rb._max_capacity), rb.add_count)
+
+    def __len__(self) -> int:
+        return len(self._range())
+
+    def __iter__(self) -> Iterator[int]:
+        return iter(self._range())
+
+    def __contains__(self, key) -> bool:
+        return isinstance(key, (int, np.integer)) and int(key) in self._range()
+
+    def __getitem__(self, key) -> ReplayElement:
+        if key not in self:
+            raise KeyError(key)
+        s, s2, a, r, d, e = self._rb._store.gather(np.asarray([int(key) % self._rb._max_capacity]))
+        return ReplayElement(s[0], int(a[0]), float(r[0]), s2[0], bool(d[0]), bool(e[0]))
+
+
+class ReplayBuffer:
+    def __init__(
+        self,
+        sampling_distribution,
+        batch_size: int,
+        max_capacity: int,
+        stack_size: int = 4,
+        update_horizon: int = 1,
+        gamma: float = 0.99,
+        checkpoint_duration: int = 4,
+        compress: bool = True,
+        clipping: callable = None,
+        *,
+        device: int = 0,
+    ):
+        self.add_count = 0
+        self._max_capacity = max_capacity
+        self._compress = compress  # accepted for signature parity; HBM slots hold raw bytes
+        self._sampling_distribution = sampling_distribution
+        self._checkpoint_duration = checkpoint_duration
+        self._batch_size = batch_size
+        self._stack_size = stack_size
+        self._update_horizon = update_horizon
+        self._gamma = gamma
+        self._clipping = clipping
+        self._device = device
+        self._store: Optional[_DeviceStore] = None
+        self._memory = _MemoryView(self)
+        self._trajectory: "collections.deque[TransitionElement]" = collections.deque(
+            maxlen=self._update_horizon + self._stack_size)
+
+    # ---- n-step / frame-stack accumulator (replay_buffer.py:103-200) ---------------------------------
+    def _make_replay_element(self) -> Optional[ReplayElement]:
+        traj, n, stack = self._trajectory, self._update_horizon, self._stack_size
+        length = len(traj)
+        newest = traj[-1]
+        if not (length > n or (length > 1 and newest.is_terminal)):
+            return None
+        # a terminal cuts the n-step window short when the trajectory is still shorter than n (:116-118)
+        horizon = length - 1 if (newest.is_terminal and length <= n) else n
+        pivot = length - horizon - 1  # newest frame of the state stack; its action is the element's action
+        frame = np.asarray(newest.observation)
+        state = np.zeros(frame.shape + (stack,), frame.dtype)  # missing history stays zero (:125,136)
+        next_state = np.zeros(frame.shape + (stack,), frame.dtype)
+        for pos in range(stack):
+            t_state, t_next = pivot - (stack - 1) + pos, length - stack + pos
+            if t_state >= 0:
+                state[..., pos] = traj[t_state].observation
+            if t_next >= 0:
+                next_state[..., pos] = traj[t_next].observation
+        ret = 0.0
+        for t in range(pivot, min(pivot + n, length)):  # discounted n-step return (:153-165)
+            ret += traj[t].reward * (self._gamma ** (t - pivot))
+        return ReplayElement(state=state, action=traj[pivot].action, reward=ret, next_state=next_state,
+                             is_terminal=newest.is_terminal, episode_end=newest.is_terminal)
+
+    def accumulate(self, transition: TransitionElement) -> Iterable[ReplayElement]:
+        self._trajectory.append(transition)
+        if transition.is_terminal:  # drain: one element per remaining start frame (:189-194)
+            while (element := self._make_replay_element()) is not None:
+                yield element
+                self._trajectory.popleft()
+            self._trajectory.clear()
+        else:
+            if (element := self._make_replay_element()) is not None:
+                yield element
+            if transition.episode_end:  # truncation (:199-200)
+                self._trajectory.clear()
+
+    # ---- add / sample / update (replay_buffer.py:202-237) -----------------------------------------------
+    def add(self, transition: TransitionElement, **kwargs: Any) -> None:
+        for element in self.accumulate(transition):
+            if self._store is None:
+                self._store = _DeviceStore(self._max_capacity, np.shape(element.state),
+                                           np.asarray(element.state).dtype, self._device)
+            key = ReplayItemID(self.add_count)
+            self._store.put(key % self._max_capacity, element)
+            self._sampling_distribution.add(key, **kwargs)
+            self.add_count += 1
+            if self.add_count > self._max_capacity:
+                self._sampling_distribution.remove(ReplayItemID(self.add_count - self._max_capacity - 1))
+
+    def sample(self, size=None) -> ReplayElement:
+        assert self.add_count, ValueError("No samples in replay buffer!")
+        if size is None:
+            size = self._batch_size
+        keys = self._sampling_distribution.sample(size)
+        s, s2, a, r, d, e = self._store.gather(np.asarray(keys, np.int64) % self._max_capacity)
+        return ReplayElement(state=s, action=a, reward=r, next_state=s2, is_terminal=d, episode_end=e)
+
+    def learn_step_on(self, engine, want_losses: bool = False):
+        """``update_online_params`` fast path (idqn.py:65-72): sample keys, gather on the device into the
+        learner's staging and run the step — no batch ever visits the host.  Returns False when this buffer
+        cannot feed ``engine`` directly (different device / element layout)."""
+        st = self._store
+        assert self.add_count, ValueError("No samples in replay buffer!")
+        if st is None or st.device != engine.device or self._batch_size != engine.B:
+            return False
+        u8 = st.dtype == np.uint8
+        if not (u8 or st.dtype == np.float32) or int(np.prod(st.shape)) != engine.in_elems:
+            return False
+        keys = self._sampling_distribution.sample(self._batch_size)
+        slots = np.ascontiguousarray(np.asarray(keys, np.int64) % self._max_capacity)
+        losses = np.zeros(engine.K, np.float32) if want_losses else None
+        L.check(st.lib.idqn_learn_from_replay(engine.h, st.h, L.ptr(slots), len(slots), int(u8),
+                                              L.ptr(losses) if want_losses else None))
+        self.last_keys = keys
+        return losses if want_losses else True
+
+    def update(self, keys, **kwargs: Any) -> None:
+        self._sampling_distribution.update(keys, **kwargs)

@@ -1,0 +1,80 @@
+"""Sampling distributions — drop-in for slimdqn/sample_collection/samplers.py.
+
+The key<->index bookkeeping (O(1) swap-remove) and the PCG64 draws stay on the host, as SURVEY App. A
+recommends (32 numbers per step; numpy *is* the reference's generator, so the stream is bit-identical); the
+SumTree arithmetic of the prioritised sampler runs on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import ReplayItemID
+from .sum_tree import SumTree
+
+
+class UniformSamplingDistribution:
+    """samplers.py:13-49."""
+
+    def __init__(self, seed: int) -> None:
+        self._rng_key = np.random.default_rng(seed)
+        self._key_to_index = {}
+        self._index_to_key = []
+
+    def add(self, key: ReplayItemID) -> None:
+        self._key_to_index[key] = len(self._index_to_key)
+        self._index_to_key.append(key)
+
+    def remove(self, key: ReplayItemID) -> None:
+        assert key in self._key_to_index, ValueError(f"Key {key} not found.")
+        hole = self._key_to_index.pop(key)
+        tail = self._index_to_key.pop()
+        if tail != key:  # the last key moves into the hole (samplers.py:31-37)
+            self._index_to_key[hole] = tail
+            self._key_to_index[tail] = hole
+
+    def sample(self, size: int):
+        assert self._index_to_key, ValueError("No keys to sample from.")
+        picks = self._rng_key.integers(len(self._index_to_key), size=size)
+        table = self._index_to_key
+        return np.fromiter((table[i] for i in picks), dtype=np.int32, count=size)
+
+
+class PrioritizedSamplingDistribution(UniformSamplingDistribution):
+    """samplers.py:52-116 with the sum tree on the device."""
+
+    def __init__(self, seed: int, max_capacity: int, priority_exponent: float = 1.0, device: int = 0) -> None:
+        self._max_capacity = max_capacity
+        self._priority_exponent = priority_exponent
+        self._sum_tree = SumTree(self._max_capacity, device=device)
+        super().__init__(seed=seed)
+
+    def _shape(self, priorities):
+        p = np.asarray(priorities, dtype=np.float64)
+        return np.where(p == 0.0, 0.0, p ** self._priority_exponent)
+
+    def add(self, key: ReplayItemID, priority: float) -> None:
+        super().add(key)
+        self._sum_tree.set(self._key_to_index[key], float(self._shape(0.0 if priority is None else priority)))
+
+    def update(self, keys, priorities) -> None:
+        if not isinstance(keys, np.ndarray):
+            keys = np.asarray([keys], dtype=np.int32)
+        leaves = np.fromiter((self._key_to_index[int(k)] for k in keys), dtype=np.int32, count=len(keys))
+        self._sum_tree.set(leaves, np.atleast_1d(self._shape(priorities)))
+
+    def remove(self, key: ReplayItemID) -> None:
+        hole = self._key_to_index[key]
+        tail = len(self._index_to_key) - 1
+        if hole == tail:
+            self._sum_tree.set(hole, 0.0)
+        else:  # mirror the swap-remove inside the tree (samplers.py:96-102)
+            self._sum_tree.set(np.asarray([hole, tail], dtype=np.int32),
+                               np.asarray([self._sum_tree.get(tail), 0.0], dtype=np.float64))
+        super().remove(key)
+
+    def sample(self, size: int):
+        # rng.uniform(0.0, root) == 0.0 + root * rng.random(): the product is formed on the device (__dmul_rn),
+        # so the root never has to come back to the host on the step path.
+        units = self._rng_key.random(size)
+        leaves = self._sum_tree.sample_unit(units)
+        table = self._index_to_key
+        return np.fromiter((table[i] for i in leaves), dtype=np.int32, count=size)

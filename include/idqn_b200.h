@@ -1,0 +1,162 @@
+/*
+ * idqn_b200.h — C ABI of libidqn_b200.so, the B200 (sm_100a) implementation of the i-DQN
+ * iterated-Bellman learning step and its data feed.
+ *
+ * The reference (theovincent/i-DQN) has no FFI layer: its boundary is the Python class API of
+ * slimdqn/networks and slimdqn/sample_collection.  Each entry point below names the reference
+ * interface (file:line under the reference tree) it replaces; the Python package `idqn_b200`
+ * binds them with ctypes and re-exposes the reference's class API.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative IDQN_E* code on failure and never throws;
+ *     idqn_last_error() returns a thread-local message for the last failure;
+ *   - pointers named *_host are host memory, *_dev are device memory of the handle's device;
+ *     the caller keeps them alive for the duration of the call;
+ *   - a handle owns all its device memory and one CUDA stream; one host thread drives one handle;
+ *   - parameters cross the boundary as flat float32 arrays per head in the "arena" layout
+ *     described by idqn_leaf_info(): layers in flax creation order, kernel then bias, kernel
+ *     stored exactly as flax stores it ([kh,kw,in,out] / [in,out], row-major).
+ */
+#ifndef IDQN_B200_H
+#define IDQN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDQN_OK 0
+#define IDQN_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define IDQN_ECUDA (-2)    /* a CUDA runtime call or kernel failed */
+#define IDQN_ERANGE (-3)   /* sum-tree query target outside [0, root)  (sum_tree.py:73-74 ValueError) */
+#define IDQN_EASSERT (-4)  /* reference assertion would fire (sum_tree.py:30-31,81) */
+#define IDQN_ENOMEM (-5)
+
+#define IDQN_ARCH_FC 0     /* architectures/dqn.py:61-63 */
+#define IDQN_ARCH_CNN 1    /* architectures/dqn.py:39-53 */
+#define IDQN_MAX_FEATURES 8
+
+/* which per-head arena a transfer addresses */
+#define IDQN_ONLINE 0      /* iDQN.params          idqn.py:48 */
+#define IDQN_TARGET 1      /* iDQN.target_params   idqn.py:56 */
+#define IDQN_MU 2          /* ScaleByAdamState.mu  idqn.py:53 */
+#define IDQN_NU 3          /* ScaleByAdamState.nu  idqn.py:53 */
+#define IDQN_GRAD 4        /* d loss_k / d params[k] of the last step (read-only; debug/parity) */
+
+typedef struct idqn_config {
+  int32_t arch;                         /* IDQN_ARCH_* */
+  int32_t obs[3];                       /* cnn: H,W,C (stack last); fc: {dim,1,1} */
+  int32_t n_actions;
+  int32_t n_heads;                      /* K heads held by THIS handle (idqn.py:44) */
+  int32_t n_features;
+  int32_t features[IDQN_MAX_FEATURES];  /* DQNNet.features (architectures/dqn.py:32) */
+  int32_t batch_size;                   /* B of learn_on_batch (samples per step) */
+  float learning_rate;                  /* optax.adam(lr, eps) idqn.py:52 */
+  float adam_eps;
+  float gamma_n;                        /* gamma ** update_horizon (idqn.py:122) rounded to f32 */
+  int32_t device;                       /* CUDA device ordinal */
+  int32_t flags;                        /* IDQN_F_* */
+} idqn_config;
+
+#define IDQN_F_NO_GRAPH 1   /* launch kernels directly instead of replaying the captured CUDA graph */
+#define IDQN_F_SIMT_ONLY 2  /* force the fp32 CUDA-core GEMM path for every layer (cross-check mode) */
+#define IDQN_F_KEEP_GRADS 4 /* materialise every gradient in the IDQN_GRAD arena (disables fused wgrad+Adam) */
+
+typedef struct idqn_handle idqn_handle;
+
+const char* idqn_last_error(void);
+int idqn_version(void);
+
+/* iDQN.__init__ / DQN.__init__ (idqn.py:28-63, dqn.py:14-39): allocates K online + K target arenas,
+ * Adam state (count=0, mu=nu=0) and all workspaces.  Parameters start at zero; the host uploads them. */
+int idqn_create(const idqn_config* cfg, idqn_handle** out);
+int idqn_destroy(idqn_handle* h);
+
+/* arena description: floats per head (padded), number of leaves, and per leaf its offset/shape.
+ * Leaf 2*l is layer l's kernel, leaf 2*l+1 its bias; name is "Conv_i"/"Dense_i" (flax auto-naming). */
+int64_t idqn_arena_stride(const idqn_handle* h);
+int idqn_leaf_count(const idqn_handle* h);
+int idqn_leaf_info(const idqn_handle* h, int leaf, int64_t* offset, int64_t* size, int32_t shape[4],
+                   int32_t* ndim, char name[16]);
+
+/* host <-> device transfer of n floats at `offset` of head `head` of arena `which` */
+int idqn_upload(idqn_handle* h, int which, int head, int64_t offset, const float* src_host, int64_t n);
+int idqn_download(idqn_handle* h, int which, int head, int64_t offset, float* dst_host, int64_t n);
+int idqn_set_count(idqn_handle* h, const int32_t* count_host);  /* ScaleByAdamState.count[K] */
+int idqn_get_count(idqn_handle* h, int32_t* count_host);
+/* raw device pointer of an arena ([K][stride] floats) for zero-copy interop (NCCL / peer copies) */
+void* idqn_arena_ptr(idqn_handle* h, int which);
+void* idqn_stream(idqn_handle* h);
+
+/* iDQN.learn_on_batch (idqn.py:96-109) / DQN.learn_on_batch (dqn.py:60-72) on the handle's resident state:
+ * one gradient step of all K heads on one shared batch; per-head MSE TD loss written to losses_host[K]
+ * (may be NULL: losses stay on the device and are accumulated, see idqn_read_cumulated_losses).
+ * state/next_state: [B, obs...] uint8 (state_is_u8=1) or float32; action int32[B]; reward float32[B];
+ * is_terminal uint8[B].  The *_host variant includes the H2D copies (end-to-end path). */
+int idqn_learn_on_batch_host(idqn_handle* h, const void* state_host, const void* next_state_host,
+                             int state_is_u8, const int32_t* action_host, const float* reward_host,
+                             const uint8_t* is_terminal_host, float* losses_host);
+int idqn_learn_on_batch_dev(idqn_handle* h, const void* state_dev, const void* next_state_dev, int state_is_u8,
+                            const int32_t* action_dev, const float* reward_dev, const uint8_t* is_terminal_dev,
+                            float* losses_host);
+/* idqn.py:72,82-87: device-side sum of the per-head losses since the last reset */
+int idqn_read_cumulated_losses(idqn_handle* h, double* sums_host, int reset);
+
+/* measurement aids (no reference counterpart): kernels one step launches, and one un-graphed step with a CUDA
+ * event after every launch -> ms[i] / names[32*i..] per kernel, in launch order (uses the staged batch) */
+int idqn_kernels_per_step(idqn_handle* h);
+int idqn_profile_step(idqn_handle* h, int state_is_u8, int max_entries, float* ms, char* names, int* n_out);
+
+/* shift_params (idqn.py:13-17), sync_target_params (idqn.py:20-24), target_params = params.copy() (idqn.py:78) */
+int idqn_shift_params(idqn_handle* h);
+int idqn_sync_target(idqn_handle* h);
+int idqn_copy_online_to_target(idqn_handle* h);
+
+/* network.apply (architectures/dqn.py:37-70) of head `head` of arena `which` on n inputs -> q_host[n, A] */
+int idqn_apply_host(idqn_handle* h, int which, int head, const void* x_host, int x_is_u8, int n, float* q_host);
+/* iDQN.best_action (idqn.py:126-131) / DQN.best_action (dqn.py:89-92) with the head index made explicit:
+ * argmax_a Q(params[head], state) for ONE state (float32 holding 0..255 for Atari, atari.py:43-45, or uint8) */
+int idqn_best_action(idqn_handle* h, int which, int head, const void* state_host, int state_is_u8, int32_t* action);
+
+/* ------------------------------------------------------------------------------------------------
+ * SumTree (slimdqn/sample_collection/sum_tree.py:8-102): float64 nodes resident on the device.
+ * set/query reproduce the reference's arithmetic bit for bit (ordered per-ancestor adds, strict <). */
+typedef struct idqn_sumtree idqn_sumtree;
+int idqn_sumtree_create(int64_t capacity, int device, idqn_sumtree** out);     /* sum_tree.py:11-18 */
+int idqn_sumtree_destroy(idqn_sumtree* t);
+int idqn_sumtree_depth(const idqn_sumtree* t);
+int64_t idqn_sumtree_num_nodes(const idqn_sumtree* t);
+/* sum_tree.py:20-47; indices need not be unique (first occurrence wins) nor sorted */
+int idqn_sumtree_set(idqn_sumtree* t, const int32_t* indices_host, const double* values_host, int64_t n);
+int idqn_sumtree_get(idqn_sumtree* t, const int32_t* indices_host, double* values_host, int64_t n); /* :49-51 */
+int idqn_sumtree_root(idqn_sumtree* t, double* root_host);                                          /* :53-56 */
+/* sum_tree.py:58-102; IDQN_ERANGE if any target is outside [0, root) */
+int idqn_sumtree_query(idqn_sumtree* t, const double* targets_host, int32_t* indices_host, int64_t n);
+/* samplers.py:110-111: targets = root * unit_uniforms (Generator.uniform(0, root)), then query */
+int idqn_sumtree_sample(idqn_sumtree* t, const double* unit_uniforms_host, int32_t* indices_host, int64_t n);
+int idqn_sumtree_read_nodes(idqn_sumtree* t, double* nodes_host);  /* whole _nodes array (tests) */
+void* idqn_sumtree_nodes_ptr(idqn_sumtree* t);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident replay store (slimdqn/sample_collection/replay_buffer.py:89,202-230): fixed slots of
+ * raw (uncompressed) ReplayElements; `gather` is the np.stack of ReplayBuffer.sample (:222-230). */
+typedef struct idqn_replay idqn_replay;
+int idqn_replay_create(int64_t n_slots, int64_t state_bytes, int device, idqn_replay** out);
+int idqn_replay_destroy(idqn_replay* r);
+/* ReplayBuffer.add (:207-210): store one element into `slot` */
+int idqn_replay_put(idqn_replay* r, int64_t slot, const void* state_host, const void* next_state_host,
+                    int32_t action, double reward, uint8_t is_terminal, uint8_t episode_end);
+/* ReplayBuffer.sample (:222-230) into caller buffers (host) ... */
+int idqn_replay_gather_host(idqn_replay* r, const int64_t* slots_host, int n, void* state_host, void* next_state_host,
+                            int32_t* action_host, double* reward_host, uint8_t* is_terminal_host,
+                            uint8_t* episode_end_host);
+/* ... or straight into the learner's batch staging followed by one learn step (update_online_params, idqn.py:65-72) */
+int idqn_learn_from_replay(idqn_handle* h, idqn_replay* r, const int64_t* slots_host, int n, int state_is_u8,
+                           float* losses_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDQN_B200_H */

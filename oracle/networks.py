@@ -364,3 +364,48 @@ def conv_same_naive(x_nhwc: np.ndarray, kernel_hwio: np.ndarray, bias: np.ndarra
                     acc += x_nhwc[:, iy, ix, :].astype(np.float64) @ kernel_hwio[ky, kx].astype(np.float64)
             out[:, oy, ox, :] = acc + bias
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# tensor-resident CPU learner: same arithmetic as learn_on_batch above, without the per-step
+# numpy<->torch conversions — this is the variant bench.py times as the CPU baseline.
+# ---------------------------------------------------------------------------------------
+
+class CpuLearner:
+    def __init__(self, params, params_target, arch, gamma, n, lr, eps, dtype=torch.float32):
+        self.arch, self.gamma, self.n, self.lr, self.eps, self.dtype = arch, gamma, n, lr, eps, dtype
+        self.K = tree_leaves(params)[0].shape[0]
+        clone = lambda tree: tree_map(lambda x: x.clone(), tree)  # never alias the caller's numpy arrays
+        self.p = [clone(_to_torch(tree_index(params, k)["params"], dtype)) for k in range(self.K)]
+        self.t = [clone(_to_torch(tree_index(params_target, k)["params"], dtype)) for k in range(self.K)]
+        for p in self.p:
+            for leaf in tree_leaves(p):
+                leaf.requires_grad_(True)
+        self.mu = [[torch.zeros_like(l) for l in tree_leaves(p)] for p in self.p]
+        self.nu = [[torch.zeros_like(l) for l in tree_leaves(p)] for p in self.p]
+        self.count = 0
+
+    def step(self, batch):
+        b = _batch_t(batch, self.dtype)
+        self.count += 1
+        bc1 = 1 - 0.9 ** self.count
+        bc2 = 1 - 0.999 ** self.count
+        losses = []
+        for k in range(self.K):
+            leaves = tree_leaves(self.p[k])
+            loss = loss_on_batch_t(self.p[k], self.t[k], b, self.arch, self.gamma, self.n)
+            grads = torch.autograd.grad(loss, leaves)
+            with torch.no_grad():
+                torch._foreach_mul_(self.mu[k], 0.9)
+                torch._foreach_add_(self.mu[k], grads, alpha=0.1)
+                torch._foreach_mul_(self.nu[k], 0.999)
+                torch._foreach_addcmul_(self.nu[k], grads, grads, value=0.001)
+                denom = torch._foreach_div(self.nu[k], bc2)
+                torch._foreach_sqrt_(denom)
+                torch._foreach_add_(denom, self.eps)
+                torch._foreach_addcdiv_(leaves, self.mu[k], denom, value=-self.lr / bc1)
+            losses.append(float(loss.detach()))
+        return np.asarray(losses)
+
+    def params_host(self):
+        return tree_stack([{"params": tree_map(lambda t: t.detach().numpy().copy(), p)} for p in self.p])
