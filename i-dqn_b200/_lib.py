@@ -39,6 +39,7 @@ SYMBOLS = {
     "idqn_leaf_info": (_I, [_P, _I, C.POINTER(_I64), C.POINTER(_I64), _P, C.POINTER(C.c_int32), _P]),
     "idqn_upload": (_I, [_P, _I, _I, _I64, _P, _I64]),
     "idqn_download": (_I, [_P, _I, _I, _I64, _P, _I64]),
+    "idqn_download_activation": (_I, [_P, _I, _I, _P, _I64]),
     "idqn_set_count": (_I, [_P, _P]),
     "idqn_get_count": (_I, [_P, _P]),
     "idqn_arena_ptr": (_P, [_P, _I]),

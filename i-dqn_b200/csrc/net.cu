@@ -662,6 +662,16 @@ extern "C" int idqn_download(idqn_handle* h, int which, int head, int64_t offset
   CK(cudaStreamSynchronize(h->stream));
   return IDQN_OK;
 }
+extern "C" int idqn_download_activation(idqn_handle* h, int net, int layer, float* dst, int64_t n) {
+  REQUIRE(h && dst, "null argument");
+  REQUIRE(net >= 0 && net < 2 * h->K && layer >= 0 && layer < h->n_layers - 1, "bad net/layer");
+  REQUIRE(n >= 0 && n <= h->layers[layer].act_size, "too many elements");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(dst, h->act + (int64_t)net * h->act_stride + h->layers[layer].act_off, sizeof(float) * n,
+                     cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return IDQN_OK;
+}
 extern "C" int idqn_set_count(idqn_handle* h, const int32_t* c) {
   REQUIRE(h && c, "null argument");
   CK(cudaMemcpyAsync(h->count, c, sizeof(int32_t) * h->K, cudaMemcpyHostToDevice, h->stream));

@@ -183,6 +183,28 @@ class Engine:
             L.check(self.lib.idqn_download(self.h, which, k, 0, L.ptr(row), self.stride))
         return out
 
+    def layer_output_shapes(self):
+        """[(B, OH, OW, OC)] of every hidden layer (the final Dense is fused into the loss kernel)."""
+        from .architectures._shapes import CNN_SPECS, same_out
+        shapes = []
+        if self.architecture_type == "cnn":
+            h, w, _ = self.obs_shape
+            for i, (_, s) in enumerate(CNN_SPECS):
+                h, w = same_out(h, s), same_out(w, s)
+                shapes.append((self.B, h, w, int(self.cfg.features[i])))
+            start = 3
+        else:
+            start = 0
+        for i in range(start, int(self.cfg.n_features)):
+            shapes.append((self.B, 1, 1, int(self.cfg.features[i])))
+        return shapes
+
+    def download_activation(self, net: int, layer: int) -> np.ndarray:
+        shape = self.layer_output_shapes()[layer]
+        out = np.empty(shape, np.float32)
+        L.check(self.lib.idqn_download_activation(self.h, net, layer, L.ptr(out), out.size))
+        return out
+
     def get_count(self) -> np.ndarray:
         c = np.zeros(self.K, np.int32)
         L.check(self.lib.idqn_get_count(self.h, L.ptr(c)))

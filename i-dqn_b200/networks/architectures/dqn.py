@@ -61,7 +61,7 @@ class DQNNet:
         eng = self._engine_for(obs, device)
         eng.upload_tree(L.ONLINE, _host_tree(params), squeezed=True)
         q = eng.apply(L.ONLINE, 0, x)
-        return q[0] if q.shape[0] == 1 and x.size == eng.in_elems and x.ndim <= len(obs) else q
+        return q[0] if x.size == eng.in_elems else q  # unbatched input -> [A] (the squeeze of :65)
 
 
 def _truncated_normal(rng: np.random.Generator, shape) -> np.ndarray:

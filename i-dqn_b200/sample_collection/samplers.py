@@ -47,19 +47,19 @@ class PrioritizedSamplingDistribution(UniformSamplingDistribution):
         self._sum_tree = SumTree(self._max_capacity, device=device)
         super().__init__(seed=seed)
 
-    def _shape(self, priorities):
-        p = np.asarray(priorities, dtype=np.float64)
-        return np.where(p == 0.0, 0.0, p ** self._priority_exponent)
-
     def add(self, key: ReplayItemID, priority: float) -> None:
         super().add(key)
-        self._sum_tree.set(self._key_to_index[key], float(self._shape(0.0 if priority is None else priority)))
+        if priority is None:
+            priority = 0.0
+        # scalar power, exactly as samplers.py:72 (numpy's vectorised pow can differ from the scalar one by 1 ulp)
+        self._sum_tree.set(self._key_to_index[key], 0.0 if priority == 0.0 else priority ** self._priority_exponent)
 
     def update(self, keys, priorities) -> None:
         if not isinstance(keys, np.ndarray):
             keys = np.asarray([keys], dtype=np.int32)
+        priorities = np.where(priorities == 0.0, 0.0, priorities ** self._priority_exponent)  # array power, :81
         leaves = np.fromiter((self._key_to_index[int(k)] for k in keys), dtype=np.int32, count=len(keys))
-        self._sum_tree.set(leaves, np.atleast_1d(self._shape(priorities)))
+        self._sum_tree.set(leaves, np.atleast_1d(priorities))
 
     def remove(self, key: ReplayItemID) -> None:
         hole = self._key_to_index[key]

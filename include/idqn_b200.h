@@ -84,6 +84,9 @@ int idqn_leaf_info(const idqn_handle* h, int leaf, int64_t* offset, int64_t* siz
 /* host <-> device transfer of n floats at `offset` of head `head` of arena `which` */
 int idqn_upload(idqn_handle* h, int which, int head, int64_t offset, const float* src_host, int64_t n);
 int idqn_download(idqn_handle* h, int which, int head, int64_t offset, float* dst_host, int64_t n);
+/* debug/parity: hidden activations (relu outputs) of the last step; net in [0,K) = online head on `state`,
+ * [K,2K) = target head on `next_state`; layer in [0, n_layers-1); n floats (<= B*OH*OW*OC) */
+int idqn_download_activation(idqn_handle* h, int net, int layer, float* dst_host, int64_t n);
 int idqn_set_count(idqn_handle* h, const int32_t* count_host);  /* ScaleByAdamState.count[K] */
 int idqn_get_count(idqn_handle* h, int32_t* count_host);
 /* raw device pointer of an arena ([K][stride] floats) for zero-copy interop (NCCL / peer copies) */

@@ -139,17 +139,28 @@ def _to_torch(tree, dtype):
 
 
 def apply_t(p: Dict[str, Dict[str, torch.Tensor]], x: torch.Tensor, architecture_type: str,
-            collect: list | None = None) -> torch.Tensor:
+            collect: list | None = None, gates: list | None = None) -> torch.Tensor:
     """Torch forward of one head on a batch ``x`` ([N,H,W,C] for cnn, [N,obs] for fc).
-    ``p`` is the inner ``params`` dict.  ``collect`` receives the pre-activations (for gate margins)."""
+    ``p`` is the inner ``params`` dict.  ``collect`` receives the pre-activations (for gate margins).
+    ``gates`` (one 0/1 tensor per hidden layer) replaces relu(z) by z*gate: used by the parity tests to give the
+    oracle the gate decisions of the implementation under test where a pre-activation is numerically zero."""
     d = 0
+    gi = 0
+
+    def act(z):
+        nonlocal gi
+        if collect is not None:
+            collect.append(z)
+        if gates is None:
+            return torch.relu(z)
+        g = gates[gi].reshape(z.shape).to(z.dtype)
+        gi += 1
+        return z * g
+
     if architecture_type == "cnn":
         x = x / 255.0  # architectures/dqn.py:44
         for i, (_, s) in enumerate(CNN_SPECS):
-            z = _conv_same(x, p[f"Conv_{i}"]["kernel"], p[f"Conv_{i}"]["bias"], s)
-            if collect is not None:
-                collect.append(z)
-            x = torch.relu(z)
+            x = act(_conv_same(x, p[f"Conv_{i}"]["kernel"], p[f"Conv_{i}"]["bias"], s))
         x = x.reshape(x.shape[0], -1)  # (h,w,c) order, architectures/dqn.py:53
     elif architecture_type == "fc":
         x = x.reshape(x.shape[0], -1)  # jnp.squeeze of the trailing stack axis, :65
@@ -157,10 +168,7 @@ def apply_t(p: Dict[str, Dict[str, torch.Tensor]], x: torch.Tensor, architecture
         raise ValueError(architecture_type)
     n_dense = sum(1 for k in p if k.startswith("Dense_"))
     for d in range(n_dense - 1):
-        z = x @ p[f"Dense_{d}"]["kernel"] + p[f"Dense_{d}"]["bias"]
-        if collect is not None:
-            collect.append(z)
-        x = torch.relu(z)
+        x = act(x @ p[f"Dense_{d}"]["kernel"] + p[f"Dense_{d}"]["bias"])
     last = p[f"Dense_{n_dense - 1}"]
     return x @ last["kernel"] + last["bias"]
 
@@ -194,10 +202,10 @@ def compute_target_t(pt, b, arch, gamma, n):
     return b["reward"] + coef * q_next.max(dim=1).values
 
 
-def loss_on_batch_t(p, pt, b, arch, gamma, n, collect=None):
+def loss_on_batch_t(p, pt, b, arch, gamma, n, collect=None, gates=None):
     with torch.no_grad():
         y = compute_target_t(pt, b, arch, gamma, n)  # value_and_grad is w.r.t. arg 0 only (idqn.py:105)
-    q = apply_t(p, b["state"], arch, collect)
+    q = apply_t(p, b["state"], arch, collect, gates)
     q_sa = q.gather(1, b["action"][:, None])[:, 0]  # idqn.py:117
     return torch.square(q_sa - y).mean()  # idqn.py:118,112
 
@@ -215,17 +223,21 @@ def loss_on_batch(params, params_target, batch, arch, gamma, n, dtype=torch.floa
                                      b, arch, gamma, n))
 
 
-def loss_and_grad(params, params_target, batch, arch, gamma, n, dtype=torch.float32, margins=False):
+def loss_and_grad(params, params_target, batch, arch, gamma, n, dtype=torch.float32, margins=False, gates=None,
+                  preacts=False):
     """(loss, grads pytree[, min |pre-activation| per relu layer]) for ONE head (no K axis)."""
     p = _to_torch(params["params"], dtype)
     for leaf in tree_leaves(p):
         leaf.requires_grad_(True)
     pt = _to_torch(params_target["params"], dtype)
     b = _batch_t(batch, dtype)
-    collect = [] if margins else None
-    loss = loss_on_batch_t(p, pt, b, arch, gamma, n, collect)
+    collect = [] if (margins or preacts) else None
+    gates_t = None if gates is None else [torch.as_tensor(np.asarray(g, dtype=np.float32)) for g in gates]
+    loss = loss_on_batch_t(p, pt, b, arch, gamma, n, collect, gates_t)
     loss.backward()
     grads = {"params": tree_map(lambda t: t.grad.detach().numpy().copy(), p)}
+    if preacts:
+        return float(loss.detach()), grads, [z.detach().numpy() for z in collect]
     if margins:
         return float(loss.detach()), grads, [float(z.detach().abs().min()) for z in collect]
     return float(loss.detach()), grads
@@ -266,7 +278,7 @@ def tree_map_tuple(tree, i):
 
 
 def learn_on_batch(params, params_target, opt_state, batch, arch, gamma, n, lr, eps, dtype=torch.float32,
-                   return_grads=False):
+                   return_grads=False, gates=None):
     """idqn.py:96-109 — vmap over K heads of value_and_grad + adam + apply_updates on a shared batch.
 
     ``opt_state = {"count": int32[K], "mu": tree[K,...], "nu": tree[K,...]}``.
@@ -276,7 +288,7 @@ def learn_on_batch(params, params_target, opt_state, batch, arch, gamma, n, lr, 
     counts = np.asarray(opt_state["count"]).copy()
     for k in range(K):
         pk, tk = tree_index(params, k), tree_index(params_target, k)
-        loss, g = loss_and_grad(pk, tk, batch, arch, gamma, n, dtype)
+        loss, g = loss_and_grad(pk, tk, batch, arch, gamma, n, dtype, gates=None if gates is None else gates[k])
         p2, m2, v2, c2 = adam_step(pk, g, tree_index(opt_state["mu"], k), tree_index(opt_state["nu"], k),
                                    int(counts[k]), lr, eps, dtype)
         counts[k] = c2

@@ -39,19 +39,15 @@ class PrioritizedSamplerOracle(UniformSamplerOracle):
         self.tree = SumTreeOracle(max_capacity)  # :62
         super().__init__(seed)
 
-    def _transform(self, priority):
-        p = np.asarray(priority, dtype=np.float64)
-        return np.where(p == 0.0, 0.0, p ** self.exponent)  # :72,81
-
     def add(self, key, priority=None) -> None:  # :66-73
         super().add(key)
-        pr = 0.0 if priority is None else float(priority)
-        self.tree.set(self.key_to_index[key], 0.0 if pr == 0.0 else pr ** self.exponent)
+        pr = 0.0 if priority is None else priority
+        self.tree.set(self.key_to_index[key], 0.0 if pr == 0.0 else pr ** self.exponent)  # scalar power (:72)
 
     def update(self, keys, priorities) -> None:  # :75-87
         keys = np.atleast_1d(np.asarray(keys))
-        self.tree.set(np.asarray([self.key_to_index[int(k)] for k in keys], np.int32),
-                      np.atleast_1d(self._transform(priorities)))
+        priorities = np.where(priorities == 0.0, 0.0, priorities ** self.exponent)  # array power (:81)
+        self.tree.set(np.asarray([self.key_to_index[int(k)] for k in keys], np.int32), np.atleast_1d(priorities))
 
     def remove(self, key) -> None:  # :89-103 — mirror the swap-remove in the tree
         pos = self.key_to_index[key]

@@ -111,38 +111,46 @@ def golden_sum_tree(sum_tree):
 
 def golden_samplers(samplers):
     out = {}
-    # prioritised: adds, updates, removes (incl. last-index remove) interleaved with sampling
-    rng = np.random.default_rng(7)
-    s = samplers.PrioritizedSamplingDistribution(seed=3, max_capacity=50, priority_exponent=0.6)
-    ops, samples = [], []
-    next_key, live = 0, []
-    for it in range(300):
-        r = rng.random()
-        if not live or (r < 0.45 and len(live) < 50):
-            p = float(rng.uniform(0, 2)) if rng.random() > 0.1 else 0.0
-            s.add(next_key, priority=p)
-            ops.append((0, next_key, p))
-            live.append(next_key)
-            next_key += 1
-        elif r < 0.65:
-            k = live[int(rng.integers(len(live)))]
-            p = float(rng.uniform(0, 2))
-            s.update(np.asarray([k]), np.asarray([p]))
-            ops.append((1, k, p))
-        elif r < 0.8 and len(live) > 1:
-            k = live.pop(int(rng.integers(len(live))))
-            s.remove(k)
-            ops.append((2, k, 0.0))
-        else:
-            ops.append((3, -1, 0.0))
-        if s._sum_tree.root > 0:
-            samples.append(s.sample(8))
-        else:
-            samples.append(np.full(8, -1, np.int32))
-    out["prio_ops"] = np.asarray(ops, dtype=np.float64)
-    out["prio_samples"] = np.stack(samples)
-    out["prio_nodes"] = s._sum_tree._nodes.copy()
-    out["prio_index_to_key"] = np.asarray(s._index_to_key, np.int64)
+    # prioritised: adds, updates, removes (incl. last-index remove) interleaved with sampling.
+    # exponent 1.0 -> p**1.0 == p exactly: portable across hosts.  exponent 0.6 -> numpy's vectorised pow is
+    # CPU-dispatch dependent (AVX512 vs AVX2 vs libm differ by 1 ulp), so a probe of this host's pow is stored and
+    # the bit-exact check of that sequence only runs where the probe reproduces.
+    for tag, exponent in (("prio1_", 1.0), ("prio_", 0.6)):
+        rng = np.random.default_rng(7)
+        s = samplers.PrioritizedSamplingDistribution(seed=3, max_capacity=50, priority_exponent=exponent)
+        ops, samples = [], []
+        next_key, live = 0, []
+        for it in range(300):
+            r = rng.random()
+            if not live or (r < 0.45 and len(live) < 50):
+                p = float(rng.uniform(0, 2)) if rng.random() > 0.1 else 0.0
+                s.add(next_key, priority=p)
+                ops.append((0, next_key, p))
+                live.append(next_key)
+                next_key += 1
+            elif r < 0.65:
+                k = live[int(rng.integers(len(live)))]
+                p = float(rng.uniform(0, 2))
+                s.update(np.asarray([k]), np.asarray([p]))
+                ops.append((1, k, p))
+            elif r < 0.8 and len(live) > 1:
+                k = live.pop(int(rng.integers(len(live))))
+                s.remove(k)
+                ops.append((2, k, 0.0))
+            else:
+                ops.append((3, -1, 0.0))
+            if s._sum_tree.root > 0:
+                samples.append(s.sample(8))
+            else:
+                samples.append(np.full(8, -1, np.int32))
+        out[tag + "ops"] = np.asarray(ops, dtype=np.float64)
+        out[tag + "samples"] = np.stack(samples)
+        out[tag + "nodes"] = s._sum_tree._nodes.copy()
+        out[tag + "index_to_key"] = np.asarray(s._index_to_key, np.int64)
+    probe = np.random.default_rng(99).uniform(0, 2, 4096)
+    out["pow_probe_in"] = probe
+    out["pow_probe_array"] = probe ** 0.6
+    out["pow_probe_scalar"] = np.asarray([float(v) ** 0.6 for v in probe])
     # uniform: FIFO evictions through swap-remove
     u = samplers.UniformSamplingDistribution(seed=11)
     usamples = []

@@ -123,22 +123,36 @@ def test_ref_sum_tree_query_kats():
 
 # ---- samplers ------------------------------------------------------------------------------------------
 
-def test_samplers_golden(golden_dir):
+@pytest.mark.parametrize("tag,exponent", [("prio1_", 1.0), ("prio_", 0.6)])
+def test_prioritized_sampler_golden_and_oracle(golden_dir, tag, exponent):
+    """Bit-exact against the reference-generated golden (exponent 1.0 always; 0.6 where this host's numpy pow
+    reproduces the generating host's) and, on every host, against the CPU oracle fed the same operations."""
     from idqn_b200.sample_collection import samplers
+    from oracle.samplers import PrioritizedSamplerOracle
     g = np.load(os.path.join(golden_dir, "samplers.npz"))
-    s = samplers.PrioritizedSamplingDistribution(seed=3, max_capacity=50, priority_exponent=0.6)
-    for it, (op, key, p) in enumerate(g["prio_ops"]):
-        op, key = int(op), int(key)
-        if op == 0:
-            s.add(key, priority=p)
-        elif op == 1:
-            s.update(np.asarray([key]), np.asarray([p]))
-        elif op == 2:
-            s.remove(key)
-        if s._sum_tree.root > 0:
-            np.testing.assert_array_equal(s.sample(8), g["prio_samples"][it])
-    assert s._sum_tree._nodes.tobytes() == g["prio_nodes"].tobytes()
-    np.testing.assert_array_equal(np.asarray(s._index_to_key), g["prio_index_to_key"])
+    x = g["pow_probe_in"]
+    golden_ok = exponent == 1.0 or ((x ** 0.6).tobytes() == g["pow_probe_array"].tobytes() and
+                                    np.asarray([float(v) ** 0.6 for v in x]).tobytes() == g["pow_probe_scalar"].tobytes())
+    s = samplers.PrioritizedSamplingDistribution(seed=3, max_capacity=50, priority_exponent=exponent)
+    o = PrioritizedSamplerOracle(seed=3, max_capacity=50, priority_exponent=exponent)
+    for it, (op, key, p) in enumerate(g[tag + "ops"]):
+        op, key, p = int(op), int(key), float(p)
+        for t in (s, o):
+            if op == 0:
+                t.add(key, priority=p)
+            elif op == 1:
+                t.update(np.asarray([key]), np.asarray([p]))
+            elif op == 2:
+                t.remove(key)
+        if o.tree.root > 0:
+            got = s.sample(8)
+            np.testing.assert_array_equal(got, o.sample(8))
+            if golden_ok:
+                np.testing.assert_array_equal(got, g[tag + "samples"][it])
+        assert s._sum_tree._nodes.tobytes() == o.tree.nodes.tobytes(), f"op {it}"
+    if golden_ok:
+        assert s._sum_tree._nodes.tobytes() == g[tag + "nodes"].tobytes()
+        np.testing.assert_array_equal(np.asarray(s._index_to_key), g[tag + "index_to_key"])
 
 
 def test_ref_prioritized_sampler_kat():
