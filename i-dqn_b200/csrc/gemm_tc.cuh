@@ -1,0 +1,769 @@
+// tcgen05 implicit-GEMM kernels for the i-DQN step (sm_100a).
+//
+// One CTA (128 threads) owns a 128 x NT accumulator tile in TMEM.  Its threads gather the operands from global
+// memory (im2col / transposed / weight reads, u8 dequant), split fp32 into bf16 hi+lo planes and store them in
+// the UMMA canonical no-swizzle layouts of tc_core.cuh; one thread issues hi*hi + hi*lo + lo*hi tcgen05.mma per
+// 16-wide K slice (fp32-faithful "bf16x3"); a 3-stage smem ring with tcgen05.commit -> mbarrier
+// lets the gather of k-block i+1.. overlap the MMAs of block i.  The epilogue reads TMEM with tcgen05.ld and is
+// fused per problem: bias+relu, relu' mask, deterministic split-K fix-up, or Adam.
+//
+// Problems (all dims runtime):                         A operand             B operand
+//   TcFwdConv    y = relu(conv(x)*s + b)               im2col, K-major       weights [k][n], MN-major  (heads concat on N)
+//   TcDgradConv  dx = convT(dy, W) * relu'(x)          dy gather, K-major    weights, K-major          (per stride class)
+//   TcWgradConv  dW = im2col(x)^T dy                   im2col^T, MN-major    dy [k][n], MN-major       (split-K)
+//   TcFwdDenseT  y^T[o][b] = W^T x^T                   W [k][o], MN-major    x [b][k], K-major         (split-K, batch on N)
+//   TcDgradDenseT dx^T[i][b] = W dy^T * relu'(x)       W [i][o], K-major     dy [b][o], K-major
+//   TcWgradDenseAdam dW[i][o] = x^T dy, then Adam      x [b][i], MN-major    dy [b][o], MN-major       (K = batch)
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"  // NetPtr
+#include "tc_core.cuh"
+
+namespace tcg {
+using namespace tc;
+
+constexpr int NS = 3;  // smem ring depth
+
+__device__ __forceinline__ void ld8(const float* __restrict__ p, float* x) {  // 32-byte aligned
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+}
+__device__ __forceinline__ void zero8(float* x) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 0.f;
+}
+
+// ==================================================================================================
+// problem definitions.  Every problem provides
+//   Ctx ctx(bx, by, bz)                      per-CTA constants (m0, n0, k range, pointers)
+//   RowA / rowA(ctx, r)                      per-thread decode of the operand row/group the thread owns
+//   loadA(ctx, rowctx, kk, x[8]) ...         one 8-element unit
+//   epi(ctx, m, n0, v[16], ncols)            16 consecutive accumulator columns of row m
+// The kernel template below fixes who loads what.
+// ==================================================================================================
+
+struct TcFwdConv {
+  ConvGeom g;
+  NetPtr x, w;
+  int x_u8;
+  int64_t w_off, b_off;
+  float* y;
+  int64_t ystride;
+  float scale;
+  int relu;
+  int nh;         // heads concatenated along N inside one group (they share the input)
+  int hpt;        // heads per N tile
+  int M, K, NT;   // NT = UMMA N (multiple of 16)
+  int nstage;     // smem ring depth (<= NS)
+  int vec;        // 8-wide vector loads are legal (IC % 8 == 0 && OC % 8 == 0) or the u8/IC==4 fast path
+
+  struct Ctx {
+    const TcFwdConv* p;
+    int m0, kbeg, kend, group, head0, nheads;
+    const uint8_t* xu;
+    const float* xf;
+  };
+  __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
+    Ctx c;
+    c.p = this;
+    c.m0 = bx * 128;
+    c.kbeg = 0, c.kend = K;
+    c.group = bz;
+    c.head0 = by * hpt;
+    c.nheads = min(hpt, nh - c.head0);
+    const int net0 = bz * nh;
+    c.xu = x_u8 ? x.get<uint8_t>(net0) : nullptr;
+    c.xf = x_u8 ? nullptr : x.get<float>(net0);
+    return c;
+  }
+  struct Row {
+    int iy0, ix0, valid;
+    int64_t base;  // element offset of sample b
+  };
+  __device__ __forceinline__ Row rowA(const Ctx& c, int m) const {
+    Row r;
+    r.valid = m < M;
+    uint32_t b, rem, oy, ox;
+    g.d_ohow.divmod(r.valid ? m : 0, b, rem);
+    g.d_ow.divmod(rem, oy, ox);
+    r.iy0 = (int)oy * g.S - g.PH;
+    r.ix0 = (int)ox * g.S - g.PW;
+    r.base = (int64_t)b * g.IH * g.IW * g.IC;
+    return r;
+  }
+  // A unit: row = output pixel, 8 consecutive k = (ky, kx, c..c+7)
+  __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* x) const {
+    zero8(x);
+    if (!r.valid || k >= c.kend) return;
+    uint32_t ky, rem, kx, ch;
+    g.d_kwic.divmod(k, ky, rem);
+    g.d_ic.divmod(rem, kx, ch);
+    const int iy = r.iy0 + (int)ky;
+    if ((unsigned)iy >= (unsigned)g.IH) {
+      if (vec) return;
+    }
+    if (vec && g.IC >= 8) {
+      const int ix = r.ix0 + (int)kx;
+      if ((unsigned)ix >= (unsigned)g.IW) return;
+      const int64_t idx = r.base + ((int64_t)iy * g.IW + ix) * g.IC + ch;
+      if (c.xu) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(c.xu + idx));
+        const uint32_t wds[2] = {raw.x, raw.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (float)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu);
+      } else {
+        ld8(c.xf + idx, x);
+      }
+      return;
+    }
+    if (vec && g.IC == 4) {  // two pixels x four stacked frames (the Atari first layer)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ix = r.ix0 + (int)kx + h;
+        if ((int)kx + h >= g.KW || (unsigned)ix >= (unsigned)g.IW) continue;
+        const int64_t idx = r.base + ((int64_t)iy * g.IW + ix) * 4;
+        if (c.xu) {
+          const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(c.xu + idx));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[4 * h + i] = (float)((raw >> (8 * i)) & 0xffu);
+        } else {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(c.xf + idx));
+          x[4 * h] = v.x, x[4 * h + 1] = v.y, x[4 * h + 2] = v.z, x[4 * h + 3] = v.w;
+        }
+      }
+      return;
+    }
+    // generic scalar path
+    for (int i = 0; i < 8; ++i) {
+      const int kk = k + i;
+      if (kk >= c.kend) break;
+      g.d_kwic.divmod(kk, ky, rem);
+      g.d_ic.divmod(rem, kx, ch);
+      const int yy = r.iy0 + (int)ky, xx = r.ix0 + (int)kx;
+      if ((unsigned)yy >= (unsigned)g.IH || (unsigned)xx >= (unsigned)g.IW) continue;
+      const int64_t idx = r.base + ((int64_t)yy * g.IW + xx) * g.IC + ch;
+      x[i] = c.xu ? (float)__ldg(c.xu + idx) : __ldg(c.xf + idx);
+    }
+  }
+  // B unit (MN-major): one k, 8 consecutive n = head*OC + oc..oc+7
+  __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* x) const {
+    zero8(x);
+    if (k >= c.kend) return;
+    const int hl = n / g.OC, oc = n - hl * g.OC;
+    if (hl >= c.nheads) return;
+    const float* wk = w.get<float>(c.group * nh + c.head0 + hl) + w_off + (int64_t)k * g.OC + oc;
+    if (vec) {
+      ld8(wk, x);
+    } else {
+      for (int i = 0; i < 8 && oc + i < g.OC; ++i) x[i] = __ldg(wk + i);
+    }
+  }
+  __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
+    if (m >= M) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + i;
+      const int hl = n / g.OC, oc = n - hl * g.OC;
+      if (hl >= c.nheads) break;
+      const int net = c.group * nh + c.head0 + hl;
+      float r = v[i] * scale + __ldg(w.get<float>(net) + b_off + oc);
+      if (relu) r = fmaxf(r, 0.f);
+      y[(int64_t)net * ystride + (int64_t)m * g.OC + oc] = r;
+    }
+  }
+};
+
+// --------------------------------------------------------------------------------------------------
+struct TcDgradConv {
+  ConvGeom g;
+  const float* dy;
+  int64_t dystride;
+  NetPtr w;
+  int64_t w_off;
+  const float* xact;
+  float* dx;
+  int64_t xstride;
+  int ncls, JH, JW, K, NT, vec, nstage;
+  FastDiv d_jwoc;
+  int cls_niy[IDQN_MAX_CLASSES], cls_nix[IDQN_MAX_CLASSES];
+  FastDiv cls_d_n[IDQN_MAX_CLASSES], cls_d_nix[IDQN_MAX_CLASSES];
+
+  struct Ctx {
+    const TcDgradConv* p;
+    int m0, M, kbeg, kend, z, py, px, ky0, kx0;
+    FastDiv d_n, d_nix;
+    const float *dy, *wk, *xact;
+    float* dx;
+  };
+  __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
+    Ctx c;
+    c.p = this;
+    const int z = bz / ncls, cl = bz - z * ncls;
+    c.z = z;
+    c.m0 = bx * 128;
+    c.py = cl / g.S, c.px = cl - c.py * g.S;
+    c.ky0 = (c.py + g.PH) % g.S, c.kx0 = (c.px + g.PW) % g.S;
+    c.d_n = cls_d_n[cl], c.d_nix = cls_d_nix[cl];
+    c.M = g.B * cls_niy[cl] * cls_nix[cl];
+    c.kbeg = 0, c.kend = K;
+    c.dy = dy + (int64_t)z * dystride;
+    c.wk = w.get<float>(z) + w_off;
+    c.xact = xact + (int64_t)z * xstride;
+    c.dx = dx + (int64_t)z * xstride;
+    return c;
+  }
+  struct Row {
+    int b, iy, ix, valid;
+  };
+  __device__ __forceinline__ Row rowA(const Ctx& c, int m) const {
+    Row r;
+    r.valid = m < c.M;
+    uint32_t b, rem, iyp, ixp;
+    c.d_n.divmod(r.valid ? m : 0, b, rem);
+    c.d_nix.divmod(rem, iyp, ixp);
+    r.b = b, r.iy = iyp * g.S + c.py, r.ix = ixp * g.S + c.px;
+    return r;
+  }
+  // A unit: row = input pixel, k = (jy, jx, co..co+7) -> dy[b, oy, ox, co..]
+  __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* x) const {
+    zero8(x);
+    if (!r.valid || k >= c.kend) return;
+    uint32_t jy, rem, jx, co;
+    d_jwoc.divmod(k, jy, rem);
+    g.d_oc.divmod(rem, jx, co);
+    const int ky = c.ky0 + jy * g.S, kx = c.kx0 + jx * g.S;
+    if (ky >= g.KH || kx >= g.KW) return;
+    const int ny = r.iy + g.PH - ky, nx = r.ix + g.PW - kx;
+    if (ny < 0 || nx < 0) return;
+    const int oy = ny / g.S, ox = nx / g.S;
+    if (oy >= g.OH || ox >= g.OW) return;
+    ld8(c.dy + (((int64_t)r.b * g.OH + oy) * g.OW + ox) * g.OC + co, x);
+  }
+  // B unit (K-major): row n = input channel c, k = (jy, jx, co..co+7) -> W[ky,kx,c,co..]
+  __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* x) const {
+    zero8(x);
+    if (n >= g.IC || k >= c.kend) return;
+    uint32_t jy, rem, jx, co;
+    d_jwoc.divmod(k, jy, rem);
+    g.d_oc.divmod(rem, jx, co);
+    const int ky = c.ky0 + jy * g.S, kx = c.kx0 + jx * g.S;
+    if (ky >= g.KH || kx >= g.KW) return;
+    ld8(c.wk + ((int64_t)(ky * g.KW + kx) * g.IC + n) * g.OC + co, x);
+  }
+  __device__ __forceinline__ void epi(const Ctx& c, const Row& r, int n0, const float* v) const {
+    if (!r.valid) return;
+    const int64_t base = (((int64_t)r.b * g.IH + r.iy) * g.IW + r.ix) * g.IC;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + i;
+      if (n >= g.IC) break;
+      c.dx[base + n] = c.xact[base + n] > 0.f ? v[i] : 0.f;
+    }
+  }
+};
+
+// --------------------------------------------------------------------------------------------------
+struct TcWgradConv {
+  ConvGeom g;
+  NetPtr x;
+  int x_u8;
+  const float* dy;
+  int64_t dystride;
+  float* gout;
+  int64_t gstride, w_off;
+  float scale;
+  int S, kchunk;  // split-K
+  int M, K, NT, vec, nstage;
+
+  struct Ctx {
+    const TcWgradConv* p;
+    int m0, kbeg, kend, z, sp;
+    const uint8_t* xu;
+    const float* xf;
+    const float* dy;
+    float* out;
+  };
+  __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
+    Ctx c;
+    c.p = this;
+    c.z = bz / S, c.sp = bz - c.z * S;
+    c.m0 = bx * 128;
+    c.kbeg = c.sp * kchunk;
+    c.kend = min(K, c.kbeg + kchunk);
+    c.xu = x_u8 ? x.get<uint8_t>(c.z) : nullptr;
+    c.xf = x_u8 ? nullptr : x.get<float>(c.z);
+    c.dy = dy + (int64_t)c.z * dystride;
+    c.out = gout + (int64_t)c.z * gstride + w_off;
+    return c;
+  }
+  struct Row {};
+  __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
+  // A unit (MN-major): one k = output pixel, 8 consecutive m = (ky, kx, c..c+7); row Kd is the ones row whose
+  // product with dy is the bias gradient (it lands on the bias slot right behind the kernel in the arena)
+  __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
+    zero8(xx);
+    if (k >= c.kend || m >= M) return;
+    if (m == g.Kd) {
+      xx[0] = 1.f;
+      return;
+    }
+    uint32_t b, rem, oy, ox, ky, rem2, kx, ch;
+    g.d_ohow.divmod(k, b, rem);
+    g.d_ow.divmod(rem, oy, ox);
+    g.d_kwic.divmod(m, ky, rem2);
+    g.d_ic.divmod(rem2, kx, ch);
+    const int iy = (int)(oy * g.S + ky) - g.PH;
+    if ((unsigned)iy >= (unsigned)g.IH) return;
+    const int64_t sbase = (int64_t)b * g.IH * g.IW * g.IC + (int64_t)iy * g.IW * g.IC;
+    if (g.IC >= 8) {
+      const int ix = (int)(ox * g.S + kx) - g.PW;
+      if ((unsigned)ix >= (unsigned)g.IW) return;
+      const int64_t idx = sbase + (int64_t)ix * g.IC + ch;
+      if (c.xu) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(c.xu + idx));
+        const uint32_t wds[2] = {raw.x, raw.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xx[i] = (float)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu);
+      } else {
+        ld8(c.xf + idx, xx);
+      }
+    } else {  // IC == 4: two pixels
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ix = (int)(ox * g.S + kx) + h - g.PW;
+        if ((int)kx + h >= g.KW || (unsigned)ix >= (unsigned)g.IW) continue;
+        const int64_t idx = sbase + (int64_t)ix * 4;
+        if (c.xu) {
+          const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(c.xu + idx));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xx[4 * h + i] = (float)((raw >> (8 * i)) & 0xffu);
+        } else {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(c.xf + idx));
+          xx[4 * h] = v.x, xx[4 * h + 1] = v.y, xx[4 * h + 2] = v.z, xx[4 * h + 3] = v.w;
+        }
+      }
+    }
+  }
+  // B unit (MN-major): one k = output pixel, 8 consecutive n = oc
+  __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* xx) const {
+    zero8(xx);
+    if (k >= c.kend || n >= g.OC) return;
+    ld8(c.dy + (int64_t)k * g.OC + n, xx);
+  }
+  __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
+    if (m >= M) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + i;
+      if (n >= g.OC) break;
+      c.out[(int64_t)m * g.OC + n] = m < g.Kd ? v[i] * scale : v[i];
+    }
+  }
+};
+
+// --------------------------------------------------------------------------------------------------
+// Dense layers with the batch on the N side ("weights are the M operand"): no padding of B=32 to 128 rows.
+struct TcFwdDenseT {  // y[net][b][o] = relu(sum_i x[b][i] W[i][o] + bias[o]);  M = O, N = B, K = I
+  NetPtr x, w;        // x: [nets][B][I] floats
+  int64_t w_off, b_off;
+  float* y;
+  int64_t ystride;
+  int relu;
+  int I, O, B;        // K, M, N
+  int S, kchunk, NT, nstage;
+
+  struct Ctx {
+    const TcFwdDenseT* p;
+    int m0, kbeg, kend, z, sp;
+    const float *xin, *wk, *bias;
+    float* y;
+  };
+  __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
+    Ctx c;
+    c.p = this;
+    c.z = bz / S, c.sp = bz - c.z * S;
+    c.m0 = bx * 128;
+    c.kbeg = c.sp * kchunk;
+    c.kend = min(I, c.kbeg + kchunk);
+    c.xin = x.get<float>(c.z);
+    const float* base = w.get<float>(c.z);
+    c.wk = base + w_off, c.bias = base + b_off;
+    c.y = y + (int64_t)c.z * ystride;
+    return c;
+  }
+  struct Row {};
+  __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
+  // A unit (MN-major): one k = input feature i, 8 consecutive m = o
+  __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
+    zero8(xx);
+    if (k >= c.kend || m >= O) return;
+    ld8(c.wk + (int64_t)k * O + m, xx);
+  }
+  // B unit (K-major): row n = sample b, 8 consecutive k = i
+  __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* xx) const {
+    zero8(xx);
+    if (n >= B || k >= c.kend) return;
+    ld8(c.xin + (int64_t)n * I + k, xx);
+  }
+  __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
+    if (m >= O) return;
+    const float bb = __ldg(c.bias + m);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + i;
+      if (n >= B) break;
+      float r = v[i] + bb;
+      if (relu) r = fmaxf(r, 0.f);
+      c.y[(int64_t)n * O + m] = r;
+    }
+  }
+};
+
+struct TcDgradDenseT {  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o];  M = I, N = B, K = O
+  const float* dy;      // [z][B][O]
+  int64_t dystride;
+  NetPtr w;
+  int64_t w_off;
+  const float* xact;    // [z][B][I]
+  float* dx;
+  int64_t xstride;
+  int I, O, B, NT, nstage;
+
+  struct Ctx {
+    const TcDgradDenseT* p;
+    int m0, kbeg, kend, z;
+    const float *dy, *wk, *xact;
+    float* dx;
+  };
+  __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
+    Ctx c;
+    c.p = this;
+    c.z = bz;
+    c.m0 = bx * 128;
+    c.kbeg = 0, c.kend = O;
+    c.dy = dy + (int64_t)bz * dystride;
+    c.wk = w.get<float>(bz) + w_off;
+    c.xact = xact + (int64_t)bz * xstride;
+    c.dx = dx + (int64_t)bz * xstride;
+    return c;
+  }
+  struct Row {
+    int m, valid;
+  };
+  __device__ __forceinline__ Row rowA(const Ctx& c, int m) const { return Row{m, m < I}; }
+  // A unit (K-major): row m = input feature i, 8 consecutive k = o
+  __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* xx) const {
+    zero8(xx);
+    if (!r.valid || k >= c.kend) return;
+    ld8(c.wk + (int64_t)r.m * O + k, xx);
+  }
+  // B unit (K-major): row n = sample b, 8 consecutive k = o
+  __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* xx) const {
+    zero8(xx);
+    if (n >= B || k >= c.kend) return;
+    ld8(c.dy + (int64_t)n * O + k, xx);
+  }
+  __device__ __forceinline__ void epi(const Ctx& c, const Row& r, int n0, const float* v) const {
+    if (!r.valid) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + i;
+      if (n >= B) break;
+      const int64_t idx = (int64_t)n * I + r.m;
+      c.dx[idx] = c.xact[idx] > 0.f ? v[i] : 0.f;
+    }
+  }
+};
+
+struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused optax.adam on W, mu, nu
+  NetPtr x;                // [z][B][I]
+  const float* dy;         // [z][B][O]
+  int64_t dystride;
+  float *W, *mu, *nu, *grad;  // arenas (grad may be null: gradient never materialised)
+  int64_t stride, w_off;
+  const int32_t* count;
+  float lr, b1, b2, eps;
+  int I, O, B, NT, nstage;
+  int adam;                // 0: only write the gradient
+
+  struct Ctx {
+    const TcWgradDenseAdam* p;
+    int m0, n0, kbeg, kend, z;
+    const float *xin, *dy;
+    float bc1, bc2;
+  };
+  __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
+    Ctx c;
+    c.p = this;
+    c.z = bz;
+    c.m0 = bx * 128;
+    c.n0 = by * NT;
+    c.kbeg = 0, c.kend = B;
+    c.xin = x.get<float>(bz);
+    c.dy = dy + (int64_t)bz * dystride;
+    const float t = (float)count[bz];
+    c.bc1 = 1.f - powf(b1, t), c.bc2 = 1.f - powf(b2, t);
+    return c;
+  }
+  struct Row {};
+  __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
+  // A unit (MN-major): one k = sample b, 8 consecutive m = i; row I is the ones row (bias gradient)
+  __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
+    zero8(xx);
+    if (k >= c.kend || m > I) return;
+    if (m == I) {
+      xx[0] = 1.f;
+      return;
+    }
+    ld8(c.xin + (int64_t)k * I + m, xx);
+  }
+  // B unit (MN-major): one k = sample b, 8 consecutive n = o (tile-relative n + n0)
+  __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* xx) const {
+    zero8(xx);
+    if (k >= c.kend || c.n0 + n >= O) return;
+    ld8(c.dy + (int64_t)k * O + c.n0 + n, xx);
+  }
+  __device__ __forceinline__ void epi(const Ctx& c, int m, int nrel, const float* v) const {
+    if (m > I) return;  // row I = bias (arena slot b_off = w_off + I*O)
+    const int n = c.n0 + nrel;
+    if (n >= O) return;
+    const int64_t off = (int64_t)c.z * stride + w_off + (int64_t)m * O + n;
+    if (grad) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<float4*>(grad + off)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (!adam) return;
+    const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 Pv = reinterpret_cast<const float4*>(W + off)[q];
+      float4 Mv = reinterpret_cast<const float4*>(mu + off)[q];
+      float4 Vv = reinterpret_cast<const float4*>(nu + off)[q];
+      float* pp = &Pv.x;
+      float* mm = &Mv.x;
+      float* vv = &Vv.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gg = v[4 * q + e];
+        const float mn = omb1 * gg + b1 * mm[e];
+        const float vn = omb2 * (gg * gg) + b2 * vv[e];
+        pp[e] = pp[e] + (-lr) * ((mn / c.bc1) / (sqrtf(vn / c.bc2) + eps));
+        mm[e] = mn, vv[e] = vn;
+      }
+      reinterpret_cast<float4*>(W + off)[q] = Pv;
+      reinterpret_cast<float4*>(mu + off)[q] = Mv;
+      reinterpret_cast<float4*>(nu + off)[q] = Vv;
+    }
+  }
+};
+
+// ==================================================================================================
+// the kernel
+// ==================================================================================================
+// MODE_A / MODE_B: 0 = K-major operand with per-thread fixed rows (rowA/loadA(ctx,row,k,x) | loadB(ctx,n,k,x)),
+//                  1 = MN-major operand (loadA(ctx,k,m8,x) | loadB(ctx,k,n8,x))
+// EPI_ROW: the epilogue takes the Row context (dgrad problems) instead of the row index
+template <bool A_MN, bool B_MN, int A_PLANES, bool EPI_ROW, bool SPLITK, class P>
+__global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restrict__ part, int* __restrict__ tickets) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t mma_done[NS];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int NT = p.NT;
+  const int nst = p.nstage;
+  const uint32_t a_bytes = 128 * BK * 2, b_bytes = (uint32_t)NT * BK * 2;
+  const uint32_t stage_bytes = A_PLANES * a_bytes + 2 * b_bytes;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < NT) tmem_cols <<= 1;
+
+  const typename P::Ctx c = p.ctx(blockIdx.x, blockIdx.y, blockIdx.z);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&mma_done[s], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = make_idesc_bf16(128, NT, A_MN, B_MN);
+
+  // the operand row this thread owns for K-major A (row = tid of the M tile)
+  typename P::Row rowctx;
+  if constexpr (!A_MN || EPI_ROW) rowctx = p.rowA(c, c.m0 + tid);
+
+  const int nkb = c.kend > c.kbeg ? (c.kend - c.kbeg + BK - 1) / BK : 0;
+  for (int it = 0; it < nkb; ++it) {
+    const int s = it % nst;
+    if (it >= nst) mbar_wait(&mma_done[s], ((it / nst) - 1) & 1);
+    uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+    uint8_t* a_lo = a_hi + a_bytes;  // only if A_PLANES == 2
+    uint8_t* b_hi = a_hi + A_PLANES * a_bytes;
+    uint8_t* b_lo = b_hi + b_bytes;
+    const int k0 = c.kbeg + it * BK;
+    // ---- A tile: 128 x 32
+    if constexpr (!A_MN) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float x[8];
+        p.loadA(c, rowctx, k0 + 8 * u, x);
+        const uint32_t off = (uint32_t)u * (128 * 16) + (uint32_t)tid * 16;
+        if constexpr (A_PLANES == 2) {
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi;
+          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        } else {
+          *reinterpret_cast<uint4*>(a_hi + off) = pack8_exact(x);
+        }
+      }
+    } else {
+      const int k = tid & 31;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int grp = (tid >> 5) + 4 * j;  // 16 groups of 8 rows
+        float x[8];
+        p.loadA(c, k0 + k, c.m0 + 8 * grp, x);
+        const uint32_t off = (uint32_t)(k >> 3) * (128 * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
+        if constexpr (A_PLANES == 2) {
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi;
+          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        } else {
+          *reinterpret_cast<uint4*>(a_hi + off) = pack8_exact(x);
+        }
+      }
+    }
+    // ---- B tile: NT x 32
+    if constexpr (!B_MN) {
+      for (int u = tid; u < NT * 4; u += 128) {
+        const int n = u % NT, ku = u / NT;
+        float x[8];
+        p.loadB(c, n, k0 + 8 * ku, x);
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = (uint32_t)ku * ((uint32_t)NT * 16) + (uint32_t)n * 16;
+        *reinterpret_cast<uint4*>(b_hi + off) = hi;
+        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+      }
+    } else {
+      for (int u = tid; u < NT * 4; u += 128) {
+        const int k = u & 31, grp = u >> 5;  // NT/8 groups
+        float x[8];
+        p.loadB(c, k0 + k, 8 * grp, x);
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = (uint32_t)(k >> 3) * ((uint32_t)NT * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
+        *reinterpret_cast<uint4*>(b_hi + off) = hi;
+        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_after_sync();
+      const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)NT * 16;
+#pragma unroll
+      for (int j = 0; j < BK / 16; ++j) {
+        const uint64_t dah = make_smem_desc(smem_u32(a_hi) + 2 * j * a_lbo, a_lbo, 128);
+        const uint64_t dbh = make_smem_desc(smem_u32(b_hi) + 2 * j * b_lbo, b_lbo, 128);
+        const uint64_t dbl = make_smem_desc(smem_u32(b_lo) + 2 * j * b_lbo, b_lbo, 128);
+        mma_bf16(tmem, dah, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);
+        mma_bf16(tmem, dah, dbl, idesc, 1u);
+        if constexpr (A_PLANES == 2) {
+          const uint64_t dal = make_smem_desc(smem_u32(a_lo) + 2 * j * a_lbo, a_lbo, 128);
+          mma_bf16(tmem, dal, dbh, idesc, 1u);
+        }
+      }
+      mma_commit(&mma_done[s]);
+    }
+  }
+  if (nkb > 0) {
+    const int last = nkb - 1;
+    mbar_wait(&mma_done[last % nst], (last / nst) & 1);
+    tcgen05_after_sync();
+  }
+
+  // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32); thread -> accumulator row m0 + tid
+  const int m = c.m0 + tid;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  if constexpr (SPLITK) {
+    const int S = p.S;
+    if (S > 1) {
+      const int z = blockIdx.z / S, sp = blockIdx.z - z * S;
+      const int tiles = gridDim.x * gridDim.y;
+      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+      float* mine = part + ((int64_t)(z * tiles + tile) * S + sp) * ((int64_t)NT * 128);
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        float v[16];
+        if (nkb > 0) tmem_ld16(lane_base + c0, v);
+        else
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) __stcg(mine + (int64_t)(c0 + i) * 128 + tid, v[i]);
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const int t = atomicAdd(&tickets[z * tiles + tile], 1);
+        s_last = (t == S - 1);
+        if (s_last) tickets[z * tiles + tile] = 0;
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        const float* base = part + (int64_t)(z * tiles + tile) * S * ((int64_t)NT * 128);
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float sum = 0.f;
+            for (int q = 0; q < S; ++q) sum += __ldcg(base + (int64_t)q * NT * 128 + (int64_t)(c0 + i) * 128 + tid);
+            v[i] = sum;
+          }
+          p.epi(c, m, c0, v);
+        }
+      }
+      tcgen05_before_sync();
+      __syncthreads();
+      if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+      return;
+    }
+  }
+  for (int c0 = 0; c0 < NT; c0 += 16) {
+    float v[16];
+    if (nkb > 0) tmem_ld16(lane_base + c0, v);
+    else
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    if constexpr (EPI_ROW) p.epi(c, rowctx, c0, v);
+    else p.epi(c, m, c0, v);
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+template <bool A_MN, bool B_MN, int A_PLANES, bool EPI_ROW, bool SPLITK, class P>
+static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tickets, cudaStream_t st) {
+  const size_t smem = (size_t)p.nstage * (A_PLANES * 128 * BK * 2 + 2 * (size_t)p.NT * BK * 2);
+  auto kern = tc_gemm_kernel<A_MN, B_MN, A_PLANES, EPI_ROW, SPLITK, P>;
+  static bool configured = false;  // one flag per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, 128, smem, st>>>(p, part, tickets);
+  return cudaGetLastError();
+}
+
+}  // namespace tcg

@@ -5,6 +5,7 @@
 // The sequence is captured once into a CUDA graph and replayed.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -153,96 +154,113 @@ struct HeadArgs {
   int32_t* count;
   float* q;      // [2K][B][A]
 };
+#define HEAD_MAXA 32
 
-__global__ void __launch_bounds__(256) head_loss_kernel(const HeadArgs a) {
-  extern __shared__ float sm[];
-  const int k = blockIdx.x;
-  const int B = a.B, A = a.A, H = a.H;
-  float* qs = sm;               // [2][B][A]
-  float* coef = sm + 2 * B * A; // [B]
-  float* lterm = coef + B;      // [B]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  const float* W[2] = {a.online + (int64_t)k * a.stride + a.w_off, a.target + (int64_t)k * a.stride + a.w_off};
-  const float* bias[2] = {a.online + (int64_t)k * a.stride + a.b_off, a.target + (int64_t)k * a.stride + a.b_off};
-  const float* hid[2] = {a.hid.get<float>(k), a.hid.get<float>(a.K + k)};
-
-  // 1. Q(theta_k, s_b)[.] and Q(theta_bar_k, s'_b)[.]
-  for (int pair = warp; pair < 2 * B; pair += nwarp) {
-    const int net = pair / B, b = pair - net * B;
-    const float* hv = hid[net] + (int64_t)b * H;
-    for (int act = 0; act < A; ++act) {
-      float s = 0.f;
-      for (int j = lane; j < H; j += 32) s = fmaf(hv[j], __ldg(W[net] + (int64_t)j * A + act), s);
+// Q-values of the final Dense layer: one warp per (net, sample); lanes stride the hidden units and keep all A
+// partial sums (W rows are [A] contiguous), then A warp-shuffle reductions.
+__global__ void __launch_bounds__(128) head_q_kernel(const HeadArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= 2 * a.K * a.B) return;
+  const int net = wid / a.B, b = wid - net * a.B;
+  const int k = net < a.K ? net : net - a.K;
+  const float* base = (net < a.K ? a.online : a.target) + (int64_t)k * a.stride;
+  const float* W = base + a.w_off;
+  const float* hv = a.hid.get<float>(net) + (int64_t)b * a.H;
+  float acc[HEAD_MAXA];
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXA; ++i) acc[i] = 0.f;
+  for (int j = lane; j < a.H; j += 32) {
+    const float h = hv[j];
+    const float* wr = W + (int64_t)j * a.A;
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXA; ++i)
+      if (i < a.A) acc[i] = fmaf(h, __ldg(wr + i), acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXA; ++i) {
+    if (i < a.A) {
+      float s = acc[i];
 #pragma unroll
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) {
-        float v = s + __ldg(bias[net] + act);
-        qs[(net * B + b) * A + act] = v;
-        a.q[((int64_t)(net * a.K + k) * B + b) * A + act] = v;
-      }
+      if (lane == 0) a.q[((int64_t)net * a.B + b) * a.A + i] = s + __ldg(base + a.b_off + i);
     }
   }
-  __syncthreads();
-  // 2. y = r + (1-done) * gamma^n * max_a' Q_target ; delta = Q(s,a) - y
+}
+
+// y = r + (1-done) gamma^n max_a' Q_target; delta = Q(s,a) - y; loss_k = mean delta^2 and the backward of the
+// final layer.  grid (ceil(H/128), K): every CTA recomputes the B coefficients (cheap) and owns 128 hidden units.
+__global__ void __launch_bounds__(128) head_bwd_kernel(const HeadArgs a) {
+  extern __shared__ float sm[];
+  const int k = blockIdx.y, B = a.B, A = a.A, H = a.H, tid = threadIdx.x;
+  float* coef = sm;        // [B]
+  float* lterm = sm + B;   // [B]
+  int* act_s = reinterpret_cast<int*>(sm + 2 * B);  // [B]
+  const float* qo = a.q + (int64_t)k * B * A;
+  const float* qt = a.q + (int64_t)(a.K + k) * B * A;
   for (int b = tid; b < B; b += blockDim.x) {
-    float mx = qs[(B + b) * A];
-    for (int act = 1; act < A; ++act) mx = fmaxf(mx, qs[(B + b) * A + act]);
-    float notdone = a.terminal[b] ? 0.f : 1.f;
-    float y = a.reward[b] + (notdone * a.gamma_n) * mx;
-    float d = qs[b * A + a.action[b]] - y;
+    float mx = qt[b * A];
+    for (int i = 1; i < A; ++i) mx = fmaxf(mx, qt[b * A + i]);
+    const float notdone = a.terminal[b] ? 0.f : 1.f;
+    const float y = a.reward[b] + (notdone * a.gamma_n) * mx;
+    const int ab = a.action[b];
+    const float d = qo[b * A + ab] - y;
     lterm[b] = d * d;
     coef[b] = 2.f * d / (float)B;  // d mean_b(delta^2) / d Q(s_b, a_b)
+    act_s[b] = ab;
   }
   __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += lterm[b];
-    s /= (float)B;
-    a.loss[k] = s;
-    a.loss_sum[k] += (double)s;
-    a.count[k] += 1;  // ScaleByAdamState.count, read by the Adam kernel that follows
+  if (blockIdx.x == 0) {
+    if (tid == 0) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += lterm[b];
+      s /= (float)B;
+      a.loss[k] = s;
+      a.loss_sum[k] += (double)s;
+      a.count[k] += 1;  // ScaleByAdamState.count, read by the Adam kernels that follow
+    }
+    float* gb = a.grad + (int64_t)k * a.stride + a.b_off;
+    for (int i = tid; i < A; i += blockDim.x) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b)
+        if (act_s[b] == i) s += coef[b];
+      gb[i] = s;
+    }
   }
-  // 3. dW[j][act] = sum_b [a_b == act] coef_b h[b][j];  db[act] = sum_b [a_b == act] coef_b
-  float* gW = a.grad + (int64_t)k * a.stride + a.w_off;
-  for (int idx = tid; idx < H * A; idx += blockDim.x) {
-    const int j = idx / A, act = idx - j * A;
+  const int j = blockIdx.x * blockDim.x + tid;
+  if (j >= H) return;
+  const float* hid = a.hid.get<float>(k);
+  const float* W = a.online + (int64_t)k * a.stride + a.w_off + (int64_t)j * A;
+  float* gW = a.grad + (int64_t)k * a.stride + a.w_off + (int64_t)j * A;
+  for (int i = 0; i < A; ++i) {
     float s = 0.f;
     for (int b = 0; b < B; ++b)
-      if (a.action[b] == act) s = fmaf(coef[b], hid[0][(int64_t)b * H + j], s);
-    gW[idx] = s;
+      if (act_s[b] == i) s = fmaf(coef[b], hid[(int64_t)b * H + j], s);
+    gW[i] = s;
   }
-  float* gb = a.grad + (int64_t)k * a.stride + a.b_off;
-  for (int act = tid; act < A; act += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b)
-      if (a.action[b] == act) s += coef[b];
-    gb[act] = s;
-  }
-  // 4. dh[b][j] = relu'(h) * coef_b * W[j][a_b]
   if (a.dhid) {
     float* dh = a.dhid + (int64_t)k * a.dstride;
-    for (int idx = tid; idx < B * H; idx += blockDim.x) {
-      const int b = idx / H, j = idx - b * H;
-      float v = coef[b] * __ldg(W[0] + (int64_t)j * A + a.action[b]);
-      if (a.relu_mask && !(hid[0][idx] > 0.f)) v = 0.f;
-      dh[idx] = v;
+    for (int b = 0; b < B; ++b) {
+      float v = coef[b] * __ldg(W + act_s[b]);
+      if (a.relu_mask && !(hid[(int64_t)b * H + j] > 0.f)) v = 0.f;
+      dh[(int64_t)b * H + j] = v;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // optax.adam (scale_by_adam b1=.9 b2=.999 eps, eps_root=0; scale(-lr); apply_updates)  idqn.py:52,106-107
+// over the float4 range [off4, off4 + n4) of every head's arena
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v,
-                                                   const int32_t* __restrict__ count, int64_t n4_per_head, float lr,
-                                                   float b1, float b2, float eps) {
+                                                   const int32_t* __restrict__ count, int64_t stride4, int64_t off4,
+                                                   int64_t n4, float lr, float b1, float b2, float eps) {
   const int k = blockIdx.y;
   const float t = (float)count[k];  // already incremented for this step
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float omb1 = 1.f - b1, omb2 = 1.f - b2;
-  const int64_t base = (int64_t)k * n4_per_head;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4_per_head;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t base = (int64_t)k * stride4 + off4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 P = p[base + i], G = __ldcs(g + base + i), M = m[base + i], V = v[base + i];
     float* pp = &P.x;
     const float* gg = &G.x;
@@ -284,9 +302,89 @@ static void mark(idqn_handle* h, const char* fmt, int li) {
   }
 }
 
-static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nsamples, NetPtr x, int x_u8, NetPtr w, float* y,
-                            int64_t ystride, int relu) {
+static inline int round16(int n) { return (n + 15) / 16 * 16; }
+static bool use_tc(const idqn_handle* h) { return !(h->cfg.flags & IDQN_F_SIMT_ONLY); }
+
+// which layers the tensor-core kernels cover (vector-load friendly shapes); everything else runs the fp32 SIMT path
+static bool tc_conv_ok(const Layer& l) {
+  const ConvGeom& g = l.g;
+  const bool ic_ok = (g.IC % 8 == 0) || (g.IC == 4 && g.KW % 2 == 0);
+  return l.is_conv && ic_ok && g.OC % 8 == 0 && g.OC <= 256 && g.IC <= 256;
+}
+static bool tc_dense_ok(const idqn_handle* h, const Layer& l) {
+  const ConvGeom& g = l.g;
+  return !l.is_conv && g.IC % 8 == 0 && g.OC % 16 == 0 && h->B <= 256 && g.IC >= 64;
+}
+static int splitk_for(int tiles, int kiters, int sms) {
+  int S = 1;
+  if (tiles < 2 * sms) {
+    S = (2 * sms + tiles - 1) / tiles;
+    S = std::min(S, std::max(1, kiters / 2));
+    S = std::min(S, 64);
+  }
+  return std::max(S, 1);
+}
+
+static int check_ws(idqn_handle* h, int64_t part, int tickets, const char* what, int li) {
+  if (part > h->part_floats || tickets > h->n_tickets) {
+    idqn_set_error("internal: split-K workspace too small (%s layer %d: %lld floats, %d tickets)", what, li,
+                   (long long)part, tickets);
+    return IDQN_EINVAL;
+  }
+  return IDQN_OK;
+}
+
+// ---- forward ---------------------------------------------------------------------------------------------
+// nets: total nets; groups of `nh` consecutive nets share one input (conv0: online heads share s, target heads s')
+static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples, NetPtr x, int x_u8, NetPtr w,
+                            float* y, int64_t ystride, int relu, bool dry, int64_t* ws_part, int* ws_tick) {
   const Layer& l = h->layers[li];
+  const float scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;  // architectures/dqn.py:44
+  if (use_tc(h) && tc_conv_ok(l) && nsamples * l.g.OH * l.g.OW >= 64) {
+    tcg::TcFwdConv p;
+    p.g = l.g, p.g.B = nsamples;
+    p.x = x, p.w = w, p.x_u8 = x_u8;
+    p.w_off = l.w_off, p.b_off = l.b_off;
+    p.y = y, p.ystride = ystride, p.scale = scale, p.relu = relu;
+    p.nh = nh;
+    p.hpt = std::max(1, std::min(nh, 256 / l.g.OC));
+    p.M = nsamples * l.g.OH * l.g.OW, p.K = l.g.Kd;
+    p.NT = round16(p.hpt * l.g.OC);
+    p.vec = 1;
+    p.nstage = tcg::NS;
+    if (dry) return IDQN_OK;
+    dim3 grid((p.M + 127) / 128, (nh + p.hpt - 1) / p.hpt, nz / nh);
+    if (x_u8) CK((tcg::launch_tc<false, true, 1, false, false>(p, grid, h->part, h->tickets, h->stream)));
+    else CK((tcg::launch_tc<false, true, 2, false, false>(p, grid, h->part, h->tickets, h->stream)));
+    mark(h, "tc_fwd_L%d", li);
+    return IDQN_OK;
+  }
+  if (use_tc(h) && tc_dense_ok(h, l) && nsamples <= 256) {
+    tcg::TcFwdDenseT p;
+    p.x = x, p.w = w;
+    p.w_off = l.w_off, p.b_off = l.b_off;
+    p.y = y, p.ystride = ystride, p.relu = relu;
+    p.I = l.g.Kd, p.O = l.g.OC, p.B = nsamples;
+    p.NT = round16(nsamples);
+    p.nstage = tcg::NS;
+    const int mt = (p.O + 127) / 128;
+    p.S = splitk_for(mt * nz, (p.I + 31) / 32, 2 * h->sm_count);  // weight streaming: more CTAs in flight
+    const int it_per = ((p.I + 31) / 32 + p.S - 1) / p.S;
+    p.kchunk = it_per * 32;
+    p.S = (p.I + p.kchunk - 1) / p.kchunk;
+    const int64_t part = p.S > 1 ? (int64_t)nz * mt * p.S * p.NT * 128 : 0;
+    const int tick = p.S > 1 ? nz * mt : 0;
+    if (dry) {
+      *ws_part = std::max(*ws_part, part), *ws_tick = std::max(*ws_tick, tick);
+      return IDQN_OK;
+    }
+    int rc = check_ws(h, part, tick, "tc fwd dense", li);
+    if (rc) return rc;
+    dim3 grid(mt, 1, nz * p.S);
+    CK((tcg::launch_tc<true, false, 2, false, true>(p, grid, h->part, h->tickets, h->stream)));
+    mark(h, "tc_fwd_L%d", li);
+    return IDQN_OK;
+  }
   FwdProb p;
   p.g = l.g;
   p.g.B = nsamples;
@@ -297,7 +395,7 @@ static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nsamples, NetPtr
   p.b_off = l.b_off;
   p.y = y;
   p.ystride = ystride;
-  p.scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;  // architectures/dqn.py:44
+  p.scale = scale;
   p.relu = relu;
   p.nz = nz;
   p.M = nsamples * l.g.OH * l.g.OW;
@@ -306,33 +404,91 @@ static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nsamples, NetPtr
   GemmPlan gp = plan_gemm(p.M, p.N, p.K, nz, h->sm_count, true);
   p.S = gp.S;
   p.kchunk = gp.kchunk;
-  if (gp.part_floats > h->part_floats || gp.tickets > h->n_tickets) {
-    idqn_set_error("internal: split-K workspace too small (fwd layer %d)", li);
-    return IDQN_EINVAL;
+  if (dry) {
+    *ws_part = std::max(*ws_part, gp.part_floats), *ws_tick = std::max(*ws_tick, gp.tickets);
+    return IDQN_OK;
   }
+  int rc = check_ws(h, gp.part_floats, gp.tickets, "fwd", li);
+  if (rc) return rc;
   CK((launch_gemm_simt<true, false>(p, nz * p.S, h->part, h->tickets, h->stream)));
   mark(h, "fwd_L%d", li);
   return IDQN_OK;
 }
 
-static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8) {
+// ---- weight gradient (+ bias gradient through the ones row) -------------------------------------------------
+static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_t* ws_part, int* ws_tick) {
   const Layer& l = h->layers[li];
   const int K = h->K;
-  WgradProb p;
-  p.g = l.g;
+  NetPtr x;
   if (li == 0) {
-    p.x = NetPtr{h->s, h->s, 0, 0, K};
+    x = NetPtr{h->s, h->s, 0, 0, K};
   } else {
     const float* xin = h->act + h->layers[li - 1].act_off;
-    p.x = NetPtr{xin, xin, h->act_stride, h->act_stride, K};
+    x = NetPtr{xin, xin, h->act_stride, h->act_stride, K};
   }
-  p.x_u8 = (li == 0) ? x_u8 : 0;
+  const int xu = (li == 0) ? x_u8 : 0;
+  const float scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;
+  const bool keep = (h->cfg.flags & IDQN_F_KEEP_GRADS) != 0;
+  if (use_tc(h) && tc_dense_ok(h, l)) {
+    // dW = x^T dy with K = batch: the tile is final after one k-block, so Adam runs in the epilogue and the
+    // gradient of the (98%-of-all-parameters) Dense_0 kernel never goes to HBM
+    tcg::TcWgradDenseAdam p;
+    p.x = x;
+    p.dy = h->dact + l.act_off, p.dystride = h->act_stride;
+    p.W = h->online, p.mu = h->mu, p.nu = h->nu, p.grad = keep ? h->grad : nullptr;
+    p.stride = h->stride, p.w_off = l.w_off;
+    p.count = h->count;
+    p.lr = h->cfg.learning_rate, p.b1 = 0.9f, p.b2 = 0.999f, p.eps = h->cfg.adam_eps;
+    p.I = l.g.Kd, p.O = l.g.OC, p.B = h->B;
+    p.NT = std::min(128, round16(p.O));  // 128 TMEM columns and one stage -> 4 CTAs per SM for the Adam streams
+    p.nstage = 1;
+    p.adam = 1;
+    if (dry) return IDQN_OK;
+    dim3 grid((p.I + 1 + 127) / 128, (p.O + p.NT - 1) / p.NT, K);
+    CK((tcg::launch_tc<true, true, 2, false, false>(p, grid, h->part, h->tickets, h->stream)));
+    mark(h, "tc_wgrad_adam_L%d", li);
+    return IDQN_OK;
+  }
+  if (use_tc(h) && tc_conv_ok(l)) {
+    tcg::TcWgradConv p;
+    p.g = l.g;
+    p.x = x, p.x_u8 = xu;
+    p.dy = h->dact + l.act_off, p.dystride = h->act_stride;
+    p.gout = h->grad, p.gstride = h->stride, p.w_off = l.w_off;
+    p.scale = scale;
+    p.M = l.g.Kd + 1, p.K = h->B * l.g.OH * l.g.OW;
+    p.NT = round16(l.g.OC);
+    p.vec = 1;
+    p.nstage = tcg::NS;
+    const int mt = (p.M + 127) / 128;
+    p.S = splitk_for(mt * K, (p.K + 31) / 32, h->sm_count);
+    const int it_per = ((p.K + 31) / 32 + p.S - 1) / p.S;
+    p.kchunk = it_per * 32;
+    p.S = (p.K + p.kchunk - 1) / p.kchunk;
+    const int64_t part = p.S > 1 ? (int64_t)K * mt * p.S * p.NT * 128 : 0;
+    const int tick = p.S > 1 ? K * mt : 0;
+    if (dry) {
+      *ws_part = std::max(*ws_part, part), *ws_tick = std::max(*ws_tick, tick);
+      return IDQN_OK;
+    }
+    int rc = check_ws(h, part, tick, "tc wgrad", li);
+    if (rc) return rc;
+    dim3 grid(mt, 1, K * p.S);
+    if (xu) CK((tcg::launch_tc<true, true, 1, false, true>(p, grid, h->part, h->tickets, h->stream)));
+    else CK((tcg::launch_tc<true, true, 2, false, true>(p, grid, h->part, h->tickets, h->stream)));
+    mark(h, "tc_wgrad_L%d", li);
+    return IDQN_OK;
+  }
+  WgradProb p;
+  p.g = l.g;
+  p.x = x;
+  p.x_u8 = xu;
   p.dy = h->dact + l.act_off;
   p.dystride = h->act_stride;
   p.gout = h->grad;
   p.gstride = h->stride;
   p.w_off = l.w_off;
-  p.scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;
+  p.scale = scale;
   p.nz = K;
   p.M = l.g.Kd + 1;
   p.N = l.g.OC;
@@ -340,19 +496,72 @@ static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8) {
   GemmPlan gp = plan_gemm(p.M, p.N, p.K, K, h->sm_count, true);
   p.S = gp.S;
   p.kchunk = gp.kchunk;
-  if (gp.part_floats > h->part_floats || gp.tickets > h->n_tickets) {
-    idqn_set_error("internal: split-K workspace too small (wgrad layer %d)", li);
-    return IDQN_EINVAL;
+  if (dry) {
+    *ws_part = std::max(*ws_part, gp.part_floats), *ws_tick = std::max(*ws_tick, gp.tickets);
+    return IDQN_OK;
   }
+  int rc = check_ws(h, gp.part_floats, gp.tickets, "wgrad", li);
+  if (rc) return rc;
   CK((launch_gemm_simt<false, false>(p, K * p.S, h->part, h->tickets, h->stream)));
   mark(h, "wgrad_L%d", li);
   return IDQN_OK;
 }
 
-static int launch_dgrad_layer(idqn_handle* h, int li) {  // writes dact of layer li-1
+// ---- data gradient: writes dact of layer li-1 ------------------------------------------------------------------
+static int launch_dgrad_layer(idqn_handle* h, int li) {
   const Layer& l = h->layers[li];
   const Layer& prev = h->layers[li - 1];
   const int K = h->K;
+  const int S = l.g.S;
+  if (S * S > IDQN_MAX_CLASSES) {
+    idqn_set_error("stride %d not supported in dgrad", S);
+    return IDQN_EINVAL;
+  }
+  if (use_tc(h) && tc_dense_ok(h, l)) {
+    tcg::TcDgradDenseT p;
+    p.dy = h->dact + l.act_off, p.dystride = h->act_stride;
+    p.w = NetPtr{h->online, h->online, h->stride, h->stride, K};
+    p.w_off = l.w_off;
+    p.xact = h->act + prev.act_off, p.dx = h->dact + prev.act_off, p.xstride = h->act_stride;
+    p.I = l.g.Kd, p.O = l.g.OC, p.B = h->B;
+    p.NT = round16(h->B);
+    p.nstage = tcg::NS;
+    dim3 grid((p.I + 127) / 128, 1, K);
+    CK((tcg::launch_tc<false, false, 2, true, false>(p, grid, h->part, h->tickets, h->stream)));
+    mark(h, "tc_dgrad_L%d", li);
+    return IDQN_OK;
+  }
+  int cls_niy[IDQN_MAX_CLASSES], cls_nix[IDQN_MAX_CLASSES], maxM = 0;
+  for (int cl = 0; cl < S * S; ++cl) {
+    const int py = cl / S, px = cl % S;
+    cls_niy[cl] = std::max((l.g.IH - py + S - 1) / S, 0);
+    cls_nix[cl] = std::max((l.g.IW - px + S - 1) / S, 0);
+    maxM = std::max(maxM, h->B * cls_niy[cl] * cls_nix[cl]);
+  }
+  const int JH = (l.g.KH + S - 1) / S, JW = (l.g.KW + S - 1) / S;
+  if (use_tc(h) && tc_conv_ok(l)) {
+    tcg::TcDgradConv p;
+    p.g = l.g;
+    p.dy = h->dact + l.act_off, p.dystride = h->act_stride;
+    p.w = NetPtr{h->online, h->online, h->stride, h->stride, K};
+    p.w_off = l.w_off;
+    p.xact = h->act + prev.act_off, p.dx = h->dact + prev.act_off, p.xstride = h->act_stride;
+    p.ncls = S * S, p.JH = JH, p.JW = JW;
+    p.d_jwoc = FastDiv(JW * l.g.OC);
+    p.K = JH * JW * l.g.OC;
+    p.NT = round16(l.g.IC);
+    p.vec = 1;
+    p.nstage = tcg::NS;
+    for (int cl = 0; cl < p.ncls; ++cl) {
+      p.cls_niy[cl] = cls_niy[cl], p.cls_nix[cl] = cls_nix[cl];
+      p.cls_d_n[cl] = FastDiv(std::max(cls_niy[cl] * cls_nix[cl], 1));
+      p.cls_d_nix[cl] = FastDiv(std::max(cls_nix[cl], 1));
+    }
+    dim3 grid((maxM + 127) / 128, 1, K * p.ncls);
+    CK((tcg::launch_tc<false, false, 2, true, false>(p, grid, h->part, h->tickets, h->stream)));
+    mark(h, "tc_dgrad_L%d", li);
+    return IDQN_OK;
+  }
   DgradProb p;
   p.g = l.g;
   p.dy = h->dact + l.act_off;
@@ -364,28 +573,16 @@ static int launch_dgrad_layer(idqn_handle* h, int li) {  // writes dact of layer
   p.xstride = h->act_stride;
   p.nz = K;
   p.S = 1;
-  const int S = l.g.S;
   p.ncls = S * S;
-  if (p.ncls > IDQN_MAX_CLASSES) {
-    idqn_set_error("stride %d not supported in dgrad", S);
-    return IDQN_EINVAL;
-  }
-  p.JH = (l.g.KH + S - 1) / S;
-  p.JW = (l.g.KW + S - 1) / S;
-  p.d_jwoc = FastDiv(p.JW * l.g.OC);
+  p.JH = JH, p.JW = JW;
+  p.d_jwoc = FastDiv(JW * l.g.OC);
   p.N = l.g.IC;
-  p.K = p.JH * p.JW * l.g.OC;
+  p.K = JH * JW * l.g.OC;
   p.kchunk = p.K;
-  int maxM = 0;
   for (int cl = 0; cl < p.ncls; ++cl) {
-    int py = cl / S, px = cl % S;
-    int niy = (l.g.IH - py + S - 1) / S, nix = (l.g.IW - px + S - 1) / S;
-    niy = std::max(niy, 0), nix = std::max(nix, 0);
-    p.cls_niy[cl] = niy;
-    p.cls_nix[cl] = nix;
-    p.cls_d_n[cl] = FastDiv(std::max(niy * nix, 1));
-    p.cls_d_nix[cl] = FastDiv(std::max(nix, 1));
-    maxM = std::max(maxM, h->B * niy * nix);
+    p.cls_niy[cl] = cls_niy[cl], p.cls_nix[cl] = cls_nix[cl];
+    p.cls_d_n[cl] = FastDiv(std::max(cls_niy[cl] * cls_nix[cl], 1));
+    p.cls_d_nix[cl] = FastDiv(std::max(cls_nix[cl], 1));
   }
   p.M = maxM;
   CK((launch_gemm_simt<true, true>(p, K * p.ncls, h->part, h->tickets, h->stream)));
@@ -393,26 +590,43 @@ static int launch_dgrad_layer(idqn_handle* h, int li) {  // writes dact of layer
   return IDQN_OK;
 }
 
-// enqueue one whole learning step on h->stream (batch already staged in h->s/s2/action/reward/terminal)
-static int enqueue_learn_step(idqn_handle* h, int x_u8) {
+static int launch_adam_range(idqn_handle* h, int64_t off, int64_t len, int tag) {
+  if (len <= 0) return IDQN_OK;
+  const int64_t n4 = len / 4;
+  const int bx = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)h->sm_count * 8);
+  dim3 grid(std::max(bx, 1), h->K);
+  adam_kernel<<<grid, 256, 0, h->stream>>>((float4*)h->online, (const float4*)h->grad, (float4*)h->mu, (float4*)h->nu,
+                                           h->count, h->stride / 4, off / 4, n4, h->cfg.learning_rate, 0.9f, 0.999f,
+                                           h->cfg.adam_eps);
+  CK(cudaGetLastError());
+  mark(h, "adam_%d", tag);
+  return IDQN_OK;
+}
+
+// enqueue one whole learning step on h->stream (batch already staged in h->s/s2/action/reward/terminal);
+// dry = only size the split-K workspace
+static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_t* ws_part = nullptr,
+                              int* ws_tick = nullptr) {
   const int K = h->K, L = h->n_layers, B = h->B;
   h->n_launch = 0;
   // forward of 2K nets through all hidden layers
   for (int li = 0; li < L - 1; ++li) {
     NetPtr x;
+    int nh = 1;
     if (li == 0) {
       x = NetPtr{h->s, h->s2, 0, 0, K};
+      nh = K;  // all online heads read s, all target heads read s': concatenate them along N
     } else {
       const float* xin = h->act + h->layers[li - 1].act_off;
       x = NetPtr{xin, xin, h->act_stride, h->act_stride, 2 * K};
     }
     NetPtr w{h->online, h->target, h->stride, h->stride, K};
-    int rc = launch_fwd_layer(h, li, 2 * K, B, x, li == 0 ? x_u8 : 0, w, h->act + h->layers[li].act_off,
-                              h->act_stride, 1);
+    int rc = launch_fwd_layer(h, li, 2 * K, nh, B, x, li == 0 ? x_u8 : 0, w, h->act + h->layers[li].act_off,
+                              h->act_stride, 1, dry, ws_part, ws_tick);
     if (rc) return rc;
   }
   // final layer + loss + its backward
-  {
+  if (!dry) {
     const Layer& l = h->layers[L - 1];
     HeadArgs a;
     if (L >= 2) {
@@ -435,30 +649,42 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8) {
     a.dstride = h->act_stride;
     a.loss = h->loss, a.loss_sum = h->loss_sum, a.count = h->count;
     a.q = h->q;
-    size_t smem = (size_t)(2 * B * h->A + 2 * B) * sizeof(float);
-    head_loss_kernel<<<K, 256, smem, h->stream>>>(a);
+    const int warps = 2 * K * B;
+    head_q_kernel<<<(warps * 32 + 127) / 128, 128, 0, h->stream>>>(a);
     CK(cudaGetLastError());
-    mark(h, "head_loss_L%d", L - 1);
+    mark(h, "head_q_L%d", L - 1);
+    const size_t smem = (size_t)(3 * B) * sizeof(float);
+    head_bwd_kernel<<<dim3((a.H + 127) / 128, K), 128, smem, h->stream>>>(a);
+    CK(cudaGetLastError());
+    mark(h, "head_bwd_L%d", L - 1);
   }
   // backward through the hidden layers
+  int64_t fused_lo = -1, fused_hi = -1;  // arena range whose Adam update was fused into a wgrad epilogue
   for (int li = L - 2; li >= 0; --li) {
-    int rc = launch_wgrad_layer(h, li, x_u8);
-    if (rc) return rc;
-    if (li > 0) {
-      rc = launch_dgrad_layer(h, li);
+    // the dgrad of this layer reads the weights the fused wgrad+Adam kernel overwrites: dgrad first
+    if (li > 0 && !dry) {
+      int rc = launch_dgrad_layer(h, li);
       if (rc) return rc;
     }
+    int rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
+    if (rc) return rc;
+    if (use_tc(h) && tc_dense_ok(h, h->layers[li])) {
+      REQUIRE(fused_lo < 0, "internal: at most one fused wgrad+Adam layer is supported");
+      fused_lo = h->layers[li].w_off;
+      fused_hi = h->layers[li].b_off + h->layers[li].g.OC;
+    }
   }
-  // Adam over the whole arena of every head
-  {
-    int64_t n4 = h->stride / 4;
-    int bx = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)h->sm_count * 8);
-    dim3 grid(bx, K);
-    adam_kernel<<<grid, 256, 0, h->stream>>>((float4*)h->online, (const float4*)h->grad, (float4*)h->mu,
-                                             (float4*)h->nu, h->count, n4, h->cfg.learning_rate, 0.9f, 0.999f,
-                                             h->cfg.adam_eps);
-    CK(cudaGetLastError());
-    mark(h, "adam", 0);
+  if (dry) return IDQN_OK;
+  // Adam over the rest of the arena of every head
+  if (fused_lo < 0) {
+    int rc = launch_adam_range(h, 0, h->stride, 0);
+    if (rc) return rc;
+  } else {
+    const int64_t hi = (fused_hi + 3) / 4 * 4;  // layer starts are 128-byte aligned, so this stays inside the gap
+    int rc = launch_adam_range(h, 0, fused_lo, 0);
+    if (rc) return rc;
+    rc = launch_adam_range(h, hi, h->stride - hi, 1);
+    if (rc) return rc;
   }
   return IDQN_OK;
 }
@@ -490,12 +716,7 @@ int idqn_learn_step_resident(idqn_handle* h, int x_u8, float* losses_host) {
 }
 
 extern "C" int idqn_kernels_per_step(idqn_handle* h) {
-  if (!h) return 0;
-  if (!h->n_launch) {  // dry count without touching state: replicate the launch plan
-    int n = (h->n_layers - 1) + 1 + (h->n_layers - 1) + std::max(h->n_layers - 2, 0) + 1;
-    return n;
-  }
-  return h->n_launch;
+  return h ? h->n_launch : 0;  // launches enqueued by the most recent step capture / profile
 }
 
 extern "C" int idqn_profile_step(idqn_handle* h, int x_u8, int max_entries, float* ms, char* names, int* n_out) {
@@ -561,15 +782,17 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaMalloc(&h->dact, sizeof(float) * h->act_stride * K));
   CK(cudaMemsetAsync(h->dact, 0, sizeof(float) * h->act_stride * K, h->stream));
   CK(cudaMalloc(&h->q, sizeof(float) * 2 * K * B * h->A));
-  // split-K workspace: maximum over every launch the step will make
+  // split-K workspace: maximum over every launch the step (and a stand-alone apply) will make
   int64_t part = 0;
   int tickets = 0;
-  for (int li = 0; li < h->n_layers; ++li) {
-    const ConvGeom& g = h->layers[li].g;
-    GemmPlan f = plan_gemm(B * g.OH * g.OW, g.OC, g.Kd, 2 * K, h->sm_count, true);
-    GemmPlan w = plan_gemm(g.Kd + 1, g.OC, B * g.OH * g.OW, K, h->sm_count, true);
-    part = std::max(part, std::max(f.part_floats, w.part_floats));
-    tickets = std::max(tickets, std::max(f.tickets, w.tickets));
+  rc = enqueue_learn_step(h, 0, true, &part, &tickets);
+  if (rc) return rc;
+  {
+    NetPtr nul{nullptr, nullptr, 0, 0, 1};
+    for (int li = 0; li < h->n_layers; ++li) {
+      rc = launch_fwd_layer(h, li, 1, 1, B, nul, 0, nul, nullptr, 0, 0, true, &part, &tickets);
+      if (rc) return rc;
+    }
   }
   h->part_floats = std::max<int64_t>(part, 1);
   h->n_tickets = std::max(tickets, 1);
@@ -757,7 +980,7 @@ static int enqueue_apply(idqn_handle* h, int which, int head, int u8, int n) {
     }
     const bool last = li == h->n_layers - 1;
     float* y = last ? h->q : h->act + h->layers[li].act_off;
-    int rc = launch_fwd_layer(h, li, 1, n, x, li == 0 ? u8 : 0, w, y, 0, last ? 0 : 1);
+    int rc = launch_fwd_layer(h, li, 1, 1, n, x, li == 0 ? u8 : 0, w, y, 0, last ? 0 : 1, false, nullptr, nullptr);
     if (rc) return rc;
   }
   return IDQN_OK;
