@@ -15,6 +15,8 @@
 //   TcDgradDenseT dx^T[i][b] = W dy^T * relu'(x)       W [i][o], K-major     dy [b][o], K-major
 //   TcWgradDenseAdam dW[i][o] = x^T dy, then Adam      x [b][i], MN-major    dy [b][o], MN-major       (K = batch)
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 #include "gemm_simt.cuh"  // NetPtr
 #include "tc_core.cuh"
@@ -33,6 +35,20 @@ __device__ __forceinline__ void zero8(float* x) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = 0.f;
 }
+// predicated 8-float load: no branch, so the loads of all the units a thread owns can be issued back to back
+__device__ __forceinline__ void ld8p(const float* __restrict__ p, bool ok, float* x) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (ok) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+}
+__device__ __forceinline__ void st16(float* __restrict__ dst, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
 
 // ==================================================================================================
 // problem definitions.  Every problem provides
@@ -44,6 +60,7 @@ __device__ __forceinline__ void zero8(float* x) {
 // ==================================================================================================
 
 struct TcFwdConv {
+  static constexpr bool TILE_EPI = false;
   ConvGeom g;
   NetPtr x, w;
   int x_u8;
@@ -94,79 +111,79 @@ struct TcFwdConv {
   }
   // A unit: row = output pixel, 8 consecutive k = (ky, kx, c..c+7)
   __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* x) const {
-    zero8(x);
-    if (!r.valid || k >= c.kend) return;
     uint32_t ky, rem, kx, ch;
-    g.d_kwic.divmod(k, ky, rem);
+    g.d_kwic.divmod(k < K ? k : 0, ky, rem);
     g.d_ic.divmod(rem, kx, ch);
     const int iy = r.iy0 + (int)ky;
-    if ((unsigned)iy >= (unsigned)g.IH) {
-      if (vec) return;
-    }
-    if (vec && g.IC >= 8) {
+    const bool rowok = r.valid && k < c.kend && (unsigned)iy < (unsigned)g.IH;
+    if (g.IC >= 8) {
       const int ix = r.ix0 + (int)kx;
-      if ((unsigned)ix >= (unsigned)g.IW) return;
-      const int64_t idx = r.base + ((int64_t)iy * g.IW + ix) * g.IC + ch;
+      const bool ok = rowok && (unsigned)ix < (unsigned)g.IW;
+      const int64_t idx = ok ? r.base + ((int64_t)iy * g.IW + ix) * g.IC + ch : 0;
       if (c.xu) {
-        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(c.xu + idx));
+        uint2 raw = make_uint2(0u, 0u);
+        if (ok) raw = __ldg(reinterpret_cast<const uint2*>(c.xu + idx));
         const uint32_t wds[2] = {raw.x, raw.y};
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = (float)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu);
       } else {
-        ld8(c.xf + idx, x);
+        ld8p(c.xf + idx, ok, x);
       }
       return;
     }
-    if (vec && g.IC == 4) {  // two pixels x four stacked frames (the Atari first layer)
+    // IC == 4: two pixels x four stacked frames (the Atari first layer)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ix = r.ix0 + (int)kx + h;
-        if ((int)kx + h >= g.KW || (unsigned)ix >= (unsigned)g.IW) continue;
-        const int64_t idx = r.base + ((int64_t)iy * g.IW + ix) * 4;
-        if (c.xu) {
-          const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(c.xu + idx));
+    for (int h = 0; h < 2; ++h) {
+      const int ix = r.ix0 + (int)kx + h;
+      const bool ok = rowok && (int)kx + h < g.KW && (unsigned)ix < (unsigned)g.IW;
+      const int64_t idx = ok ? r.base + ((int64_t)iy * g.IW + ix) * 4 : 0;
+      if (c.xu) {
+        uint32_t raw = 0u;
+        if (ok) raw = __ldg(reinterpret_cast<const uint32_t*>(c.xu + idx));
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[4 * h + i] = (float)((raw >> (8 * i)) & 0xffu);
-        } else {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(c.xf + idx));
-          x[4 * h] = v.x, x[4 * h + 1] = v.y, x[4 * h + 2] = v.z, x[4 * h + 3] = v.w;
-        }
+        for (int i = 0; i < 4; ++i) x[4 * h + i] = (float)((raw >> (8 * i)) & 0xffu);
+      } else {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = __ldg(reinterpret_cast<const float4*>(c.xf + idx));
+        x[4 * h] = v.x, x[4 * h + 1] = v.y, x[4 * h + 2] = v.z, x[4 * h + 3] = v.w;
       }
-      return;
-    }
-    // generic scalar path
-    for (int i = 0; i < 8; ++i) {
-      const int kk = k + i;
-      if (kk >= c.kend) break;
-      g.d_kwic.divmod(kk, ky, rem);
-      g.d_ic.divmod(rem, kx, ch);
-      const int yy = r.iy0 + (int)ky, xx = r.ix0 + (int)kx;
-      if ((unsigned)yy >= (unsigned)g.IH || (unsigned)xx >= (unsigned)g.IW) continue;
-      const int64_t idx = r.base + ((int64_t)yy * g.IW + xx) * g.IC + ch;
-      x[i] = c.xu ? (float)__ldg(c.xu + idx) : __ldg(c.xf + idx);
     }
   }
   // B unit (MN-major): one k, 8 consecutive n = head*OC + oc..oc+7
   __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* x) const {
-    zero8(x);
-    if (k >= c.kend) return;
-    const int hl = n / g.OC, oc = n - hl * g.OC;
-    if (hl >= c.nheads) return;
-    const float* wk = w.get<float>(c.group * nh + c.head0 + hl) + w_off + (int64_t)k * g.OC + oc;
-    if (vec) {
-      ld8(wk, x);
-    } else {
-      for (int i = 0; i < 8 && oc + i < g.OC; ++i) x[i] = __ldg(wk + i);
-    }
+    uint32_t hl, oc;
+    g.d_oc.divmod(n, hl, oc);
+    const bool ok = k < c.kend && (int)hl < c.nheads;
+    const float* wk = w.get<float>(c.group * nh + c.head0 + (ok ? (int)hl : 0)) + w_off + (int64_t)(ok ? k : 0) * g.OC + oc;
+    ld8p(wk, ok, x);
   }
   __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
     if (m >= M) return;
+    uint32_t hl, oc;
+    g.d_oc.divmod(n0, hl, oc);
+    if ((g.OC & 15) == 0) {  // the 16 columns stay inside one head: vector bias loads and stores
+      if ((int)hl >= c.nheads) return;
+      const int net = c.group * nh + c.head0 + (int)hl;
+      const float* bias = w.get<float>(net) + b_off + oc;
+      float r[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + q);
+        r[4 * q] = v[4 * q] * scale + bb.x, r[4 * q + 1] = v[4 * q + 1] * scale + bb.y;
+        r[4 * q + 2] = v[4 * q + 2] * scale + bb.z, r[4 * q + 3] = v[4 * q + 3] * scale + bb.w;
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = fmaxf(r[i], 0.f);
+      }
+      st16(y + (int64_t)net * ystride + (int64_t)m * g.OC + oc, r);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int n = n0 + i;
-      const int hl = n / g.OC, oc = n - hl * g.OC;
-      if (hl >= c.nheads) break;
-      const int net = c.group * nh + c.head0 + hl;
+      g.d_oc.divmod(n0 + i, hl, oc);
+      if ((int)hl >= c.nheads) break;
+      const int net = c.group * nh + c.head0 + (int)hl;
       float r = v[i] * scale + __ldg(w.get<float>(net) + b_off + oc);
       if (relu) r = fmaxf(r, 0.f);
       y[(int64_t)net * ystride + (int64_t)m * g.OC + oc] = r;
@@ -176,6 +193,7 @@ struct TcFwdConv {
 
 // --------------------------------------------------------------------------------------------------
 struct TcDgradConv {
+  static constexpr bool TILE_EPI = false;
   ConvGeom g;
   const float* dy;
   int64_t dystride;
@@ -227,33 +245,41 @@ struct TcDgradConv {
   }
   // A unit: row = input pixel, k = (jy, jx, co..co+7) -> dy[b, oy, ox, co..]
   __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* x) const {
-    zero8(x);
-    if (!r.valid || k >= c.kend) return;
     uint32_t jy, rem, jx, co;
-    d_jwoc.divmod(k, jy, rem);
+    d_jwoc.divmod(k < K ? k : 0, jy, rem);
     g.d_oc.divmod(rem, jx, co);
     const int ky = c.ky0 + jy * g.S, kx = c.kx0 + jx * g.S;
-    if (ky >= g.KH || kx >= g.KW) return;
     const int ny = r.iy + g.PH - ky, nx = r.ix + g.PW - kx;
-    if (ny < 0 || nx < 0) return;
-    const int oy = ny / g.S, ox = nx / g.S;
-    if (oy >= g.OH || ox >= g.OW) return;
-    ld8(c.dy + (((int64_t)r.b * g.OH + oy) * g.OW + ox) * g.OC + co, x);
+    const int oy = ny / g.S, ox = nx / g.S;  // exact for this stride class when ny, nx >= 0
+    const bool ok = r.valid && k < c.kend && ky < g.KH && kx < g.KW && ny >= 0 && nx >= 0 && oy < g.OH && ox < g.OW;
+    const int64_t idx = ok ? (((int64_t)r.b * g.OH + oy) * g.OW + ox) * g.OC + co : 0;
+    ld8p(c.dy + idx, ok, x);
   }
   // B unit (K-major): row n = input channel c, k = (jy, jx, co..co+7) -> W[ky,kx,c,co..]
   __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* x) const {
-    zero8(x);
-    if (n >= g.IC || k >= c.kend) return;
     uint32_t jy, rem, jx, co;
-    d_jwoc.divmod(k, jy, rem);
+    d_jwoc.divmod(k < K ? k : 0, jy, rem);
     g.d_oc.divmod(rem, jx, co);
     const int ky = c.ky0 + jy * g.S, kx = c.kx0 + jx * g.S;
-    if (ky >= g.KH || kx >= g.KW) return;
-    ld8(c.wk + ((int64_t)(ky * g.KW + kx) * g.IC + n) * g.OC + co, x);
+    const bool ok = n < g.IC && k < c.kend && ky < g.KH && kx < g.KW;
+    const int64_t idx = ok ? ((int64_t)(ky * g.KW + kx) * g.IC + n) * g.OC + co : 0;
+    ld8p(c.wk + idx, ok, x);
   }
   __device__ __forceinline__ void epi(const Ctx& c, const Row& r, int n0, const float* v) const {
     if (!r.valid) return;
     const int64_t base = (((int64_t)r.b * g.IH + r.iy) * g.IW + r.ix) * g.IC;
+    if ((g.IC & 15) == 0) {
+      if (n0 >= g.IC) return;
+      float o[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 xa = __ldg(reinterpret_cast<const float4*>(c.xact + base + n0) + q);
+        o[4 * q] = xa.x > 0.f ? v[4 * q] : 0.f, o[4 * q + 1] = xa.y > 0.f ? v[4 * q + 1] : 0.f;
+        o[4 * q + 2] = xa.z > 0.f ? v[4 * q + 2] : 0.f, o[4 * q + 3] = xa.w > 0.f ? v[4 * q + 3] : 0.f;
+      }
+      st16(c.dx + base + n0, o);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int n = n0 + i;
@@ -265,6 +291,7 @@ struct TcDgradConv {
 
 // --------------------------------------------------------------------------------------------------
 struct TcWgradConv {
+  static constexpr bool TILE_EPI = false;
   ConvGeom g;
   NetPtr x;
   int x_u8;
@@ -302,69 +329,77 @@ struct TcWgradConv {
   // A unit (MN-major): one k = output pixel, 8 consecutive m = (ky, kx, c..c+7); row Kd is the ones row whose
   // product with dy is the bias gradient (it lands on the bias slot right behind the kernel in the arena)
   __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
-    zero8(xx);
-    if (k >= c.kend || m >= M) return;
-    if (m == g.Kd) {
-      xx[0] = 1.f;
-      return;
-    }
+    const bool inr = k < c.kend && m < g.Kd;
     uint32_t b, rem, oy, ox, ky, rem2, kx, ch;
-    g.d_ohow.divmod(k, b, rem);
+    g.d_ohow.divmod(inr ? k : 0, b, rem);
     g.d_ow.divmod(rem, oy, ox);
-    g.d_kwic.divmod(m, ky, rem2);
+    g.d_kwic.divmod(inr ? m : 0, ky, rem2);
     g.d_ic.divmod(rem2, kx, ch);
     const int iy = (int)(oy * g.S + ky) - g.PH;
-    if ((unsigned)iy >= (unsigned)g.IH) return;
+    const bool rowok = inr && (unsigned)iy < (unsigned)g.IH;
     const int64_t sbase = (int64_t)b * g.IH * g.IW * g.IC + (int64_t)iy * g.IW * g.IC;
     if (g.IC >= 8) {
       const int ix = (int)(ox * g.S + kx) - g.PW;
-      if ((unsigned)ix >= (unsigned)g.IW) return;
-      const int64_t idx = sbase + (int64_t)ix * g.IC + ch;
+      const bool ok = rowok && (unsigned)ix < (unsigned)g.IW;
+      const int64_t idx = ok ? sbase + (int64_t)ix * g.IC + ch : 0;
       if (c.xu) {
-        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(c.xu + idx));
+        uint2 raw = make_uint2(0u, 0u);
+        if (ok) raw = __ldg(reinterpret_cast<const uint2*>(c.xu + idx));
         const uint32_t wds[2] = {raw.x, raw.y};
 #pragma unroll
         for (int i = 0; i < 8; ++i) xx[i] = (float)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu);
       } else {
-        ld8(c.xf + idx, xx);
+        ld8p(c.xf + idx, ok, xx);
       }
     } else {  // IC == 4: two pixels
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int ix = (int)(ox * g.S + kx) + h - g.PW;
-        if ((int)kx + h >= g.KW || (unsigned)ix >= (unsigned)g.IW) continue;
-        const int64_t idx = sbase + (int64_t)ix * 4;
+        const bool ok = rowok && (int)kx + h < g.KW && (unsigned)ix < (unsigned)g.IW;
+        const int64_t idx = ok ? sbase + (int64_t)ix * 4 : 0;
         if (c.xu) {
-          const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(c.xu + idx));
+          uint32_t raw = 0u;
+          if (ok) raw = __ldg(reinterpret_cast<const uint32_t*>(c.xu + idx));
 #pragma unroll
           for (int i = 0; i < 4; ++i) xx[4 * h + i] = (float)((raw >> (8 * i)) & 0xffu);
         } else {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(c.xf + idx));
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) v = __ldg(reinterpret_cast<const float4*>(c.xf + idx));
           xx[4 * h] = v.x, xx[4 * h + 1] = v.y, xx[4 * h + 2] = v.z, xx[4 * h + 3] = v.w;
         }
       }
     }
+    if (m == g.Kd && k < c.kend) xx[0] = 1.f;
   }
   // B unit (MN-major): one k = output pixel, 8 consecutive n = oc
   __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* xx) const {
-    zero8(xx);
-    if (k >= c.kend || n >= g.OC) return;
-    ld8(c.dy + (int64_t)k * g.OC + n, xx);
+    const bool ok = k < c.kend && n < g.OC;
+    ld8p(c.dy + (ok ? (int64_t)k * g.OC + n : 0), ok, xx);
   }
   __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
     if (m >= M) return;
+    const float sc = m < g.Kd ? scale : 1.f;
+    if ((g.OC & 15) == 0) {
+      if (n0 >= g.OC) return;
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = v[i] * sc;
+      st16(c.out + (int64_t)m * g.OC + n0, o);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int n = n0 + i;
       if (n >= g.OC) break;
-      c.out[(int64_t)m * g.OC + n] = m < g.Kd ? v[i] * scale : v[i];
+      c.out[(int64_t)m * g.OC + n] = v[i] * sc;
     }
   }
 };
 
 // --------------------------------------------------------------------------------------------------
 // Dense layers with the batch on the N side ("weights are the M operand"): no padding of B=32 to 128 rows.
-struct TcFwdDenseT {  // y[net][b][o] = relu(sum_i x[b][i] W[i][o] + bias[o]);  M = O, N = B, K = I
+struct TcFwdDenseT {
+  static constexpr bool TILE_EPI = false;  // y[net][b][o] = relu(sum_i x[b][i] W[i][o] + bias[o]);  M = O, N = B, K = I
   NetPtr x, w;        // x: [nets][B][I] floats
   int64_t w_off, b_off;
   float* y;
@@ -396,15 +431,13 @@ struct TcFwdDenseT {  // y[net][b][o] = relu(sum_i x[b][i] W[i][o] + bias[o]);  
   __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
   // A unit (MN-major): one k = input feature i, 8 consecutive m = o
   __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
-    zero8(xx);
-    if (k >= c.kend || m >= O) return;
-    ld8(c.wk + (int64_t)k * O + m, xx);
+    const bool ok = k < c.kend && m < O;
+    ld8p(c.wk + (ok ? (int64_t)k * O + m : 0), ok, xx);
   }
   // B unit (K-major): row n = sample b, 8 consecutive k = i
   __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* xx) const {
-    zero8(xx);
-    if (n >= B || k >= c.kend) return;
-    ld8(c.xin + (int64_t)n * I + k, xx);
+    const bool ok = n < B && k < c.kend;
+    ld8p(c.xin + (ok ? (int64_t)n * I + k : 0), ok, xx);
   }
   __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
     if (m >= O) return;
@@ -420,7 +453,8 @@ struct TcFwdDenseT {  // y[net][b][o] = relu(sum_i x[b][i] W[i][o] + bias[o]);  
   }
 };
 
-struct TcDgradDenseT {  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o];  M = I, N = B, K = O
+struct TcDgradDenseT {
+  static constexpr bool TILE_EPI = false;  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o];  M = I, N = B, K = O
   const float* dy;      // [z][B][O]
   int64_t dystride;
   NetPtr w;
@@ -454,15 +488,13 @@ struct TcDgradDenseT {  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o]
   __device__ __forceinline__ Row rowA(const Ctx& c, int m) const { return Row{m, m < I}; }
   // A unit (K-major): row m = input feature i, 8 consecutive k = o
   __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* xx) const {
-    zero8(xx);
-    if (!r.valid || k >= c.kend) return;
-    ld8(c.wk + (int64_t)r.m * O + k, xx);
+    const bool ok = r.valid && k < c.kend;
+    ld8p(c.wk + (ok ? (int64_t)r.m * O + k : 0), ok, xx);
   }
   // B unit (K-major): row n = sample b, 8 consecutive k = o
   __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* xx) const {
-    zero8(xx);
-    if (n >= B || k >= c.kend) return;
-    ld8(c.dy + (int64_t)n * O + k, xx);
+    const bool ok = n < B && k < c.kend;
+    ld8p(c.dy + (ok ? (int64_t)n * O + k : 0), ok, xx);
   }
   __device__ __forceinline__ void epi(const Ctx& c, const Row& r, int n0, const float* v) const {
     if (!r.valid) return;
@@ -476,7 +508,8 @@ struct TcDgradDenseT {  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o]
   }
 };
 
-struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused optax.adam on W, mu, nu
+struct TcWgradDenseAdam {
+  static constexpr bool TILE_EPI = true;  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused optax.adam on W, mu, nu
   NetPtr x;                // [z][B][I]
   const float* dy;         // [z][B][O]
   int64_t dystride;
@@ -491,7 +524,6 @@ struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused o
     const TcWgradDenseAdam* p;
     int m0, n0, kbeg, kend, z;
     const float *xin, *dy;
-    float bc1, bc2;
   };
   __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
     Ctx c;
@@ -502,59 +534,75 @@ struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused o
     c.kbeg = 0, c.kend = B;
     c.xin = x.get<float>(bz);
     c.dy = dy + (int64_t)bz * dystride;
-    const float t = (float)count[bz];
-    c.bc1 = 1.f - powf(b1, t), c.bc2 = 1.f - powf(b2, t);
     return c;
   }
   struct Row {};
   __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
   // A unit (MN-major): one k = sample b, 8 consecutive m = i; row I is the ones row (bias gradient)
   __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
-    zero8(xx);
-    if (k >= c.kend || m > I) return;
-    if (m == I) {
-      xx[0] = 1.f;
-      return;
-    }
-    ld8(c.xin + (int64_t)k * I + m, xx);
+    const bool ok = k < c.kend && m < I;
+    ld8p(c.xin + (ok ? (int64_t)k * I + m : 0), ok, xx);
+    if (m == I && k < c.kend) xx[0] = 1.f;
   }
   // B unit (MN-major): one k = sample b, 8 consecutive n = o (tile-relative n + n0)
   __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* xx) const {
-    zero8(xx);
-    if (k >= c.kend || c.n0 + n >= O) return;
-    ld8(c.dy + (int64_t)k * O + c.n0 + n, xx);
+    const bool ok = k < c.kend && c.n0 + n < O;
+    ld8p(c.dy + (ok ? (int64_t)k * O + c.n0 + n : 0), ok, xx);
   }
-  __device__ __forceinline__ void epi(const Ctx& c, int m, int nrel, const float* v) const {
-    if (m > I) return;  // row I = bias (arena slot b_off = w_off + I*O)
-    const int n = c.n0 + nrel;
-    if (n >= O) return;
-    const int64_t off = (int64_t)c.z * stride + w_off + (int64_t)m * O + n;
-    if (grad) {
+  __device__ __forceinline__ void epi(const Ctx&, int, int, const float*) const {}
+  // Tile epilogue: the 128 x NT gradient tile sits in shared memory (row stride ld); the CTA walks it row-major
+  // so that every warp touches 512 contiguous bytes of W / mu / nu per access (the thread-per-row TMEM layout
+  // would stride by a whole 2 KB weight row), four independent float4 triples in flight per thread.
+  __device__ __forceinline__ void tile_epi(const Ctx& c, const float* __restrict__ tile, int ld, int tid,
+                                           int nthreads) const {
+    const int nf4 = NT >> 2;
+    const int total = 128 * nf4;
+    const AdamCoef ac = adam_coef(b1, b2, lr, eps, count[c.z]);
+    float* __restrict__ Wp = W + (int64_t)c.z * stride + w_off;
+    float* __restrict__ Mp = mu + (int64_t)c.z * stride + w_off;
+    float* __restrict__ Vp = nu + (int64_t)c.z * stride + w_off;
+    float* __restrict__ Gp = grad ? grad + (int64_t)c.z * stride + w_off : nullptr;
+    constexpr int U = 4;
+    for (int i0 = tid; i0 < total; i0 += U * nthreads) {
+      float4 Pv[U], Mv[U], Vv[U], Gv[U];
+      int64_t off[U];
+      bool ok[U];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        reinterpret_cast<float4*>(grad + off)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    }
-    if (!adam) return;
-    const float omb1 = 1.f - b1, omb2 = 1.f - b2;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 Pv = reinterpret_cast<const float4*>(W + off)[q];
-      float4 Mv = reinterpret_cast<const float4*>(mu + off)[q];
-      float4 Vv = reinterpret_cast<const float4*>(nu + off)[q];
-      float* pp = &Pv.x;
-      float* mm = &Mv.x;
-      float* vv = &Vv.x;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float gg = v[4 * q + e];
-        const float mn = omb1 * gg + b1 * mm[e];
-        const float vn = omb2 * (gg * gg) + b2 * vv[e];
-        pp[e] = pp[e] + (-lr) * ((mn / c.bc1) / (sqrtf(vn / c.bc2) + eps));
-        mm[e] = mn, vv[e] = vn;
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nthreads;
+        const int row = i / nf4, c4 = i - row * nf4;
+        const int m = c.m0 + row, n = c.n0 + 4 * c4;
+        ok[u] = i < total && m <= I && n < O;  // row I = bias (arena slot b_off = w_off + I*O)
+        off[u] = ok[u] ? (int64_t)m * O + n : 0;
+        Gv[u] = ok[u] ? *reinterpret_cast<const float4*>(tile + row * ld + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      reinterpret_cast<float4*>(W + off)[q] = Pv;
-      reinterpret_cast<float4*>(mu + off)[q] = Mv;
-      reinterpret_cast<float4*>(nu + off)[q] = Vv;
+      if (adam) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (ok[u]) {
+            Pv[u] = *reinterpret_cast<const float4*>(Wp + off[u]);
+            Mv[u] = *reinterpret_cast<const float4*>(Mp + off[u]);
+            Vv[u] = *reinterpret_cast<const float4*>(Vp + off[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (ok[u]) {
+            adam_elem(ac, Gv[u].x, Pv[u].x, Mv[u].x, Vv[u].x);
+            adam_elem(ac, Gv[u].y, Pv[u].y, Mv[u].y, Vv[u].y);
+            adam_elem(ac, Gv[u].z, Pv[u].z, Mv[u].z, Vv[u].z);
+            adam_elem(ac, Gv[u].w, Pv[u].w, Mv[u].w, Vv[u].w);
+            *reinterpret_cast<float4*>(Wp + off[u]) = Pv[u];
+            *reinterpret_cast<float4*>(Mp + off[u]) = Mv[u];
+            *reinterpret_cast<float4*>(Vp + off[u]) = Vv[u];
+          }
+        }
+      }
+      if (Gp) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (ok[u]) *reinterpret_cast<float4*>(Gp + off[u]) = Gv[u];
+      }
     }
   }
 };
@@ -562,17 +610,20 @@ struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused o
 // ==================================================================================================
 // the kernel
 // ==================================================================================================
-// MODE_A / MODE_B: 0 = K-major operand with per-thread fixed rows (rowA/loadA(ctx,row,k,x) | loadB(ctx,n,k,x)),
-//                  1 = MN-major operand (loadA(ctx,k,m8,x) | loadB(ctx,k,n8,x))
-// EPI_ROW: the epilogue takes the Row context (dgrad problems) instead of the row index
+// A_MN / B_MN: operand is MN-major (loadX(ctx, k, mn8, x)) instead of K-major (loadA(ctx, row, k, x) /
+// loadB(ctx, n, k, x)).  EPI_ROW: the epilogue takes the Row context (dgrad problems).
+// 256 threads: all 8 warps gather; warp w reads TMEM lanes 32*(w%4).. and the column chunks of parity w/4.
+constexpr int NTHR = 256;
+
 template <bool A_MN, bool B_MN, int A_PLANES, bool EPI_ROW, bool SPLITK, class P>
-__global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restrict__ part, int* __restrict__ tickets) {
+__global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restrict__ part, int* __restrict__ tickets) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t mma_done[NS];
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_last;
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row_t = tid & 127, half = tid >> 7;
   const int NT = p.NT;
   const int nst = p.nstage;
   const uint32_t a_bytes = 128 * BK * 2, b_bytes = (uint32_t)NT * BK * 2;
@@ -594,9 +645,8 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restri
   const uint32_t tmem = tmem_base_s;
   const uint32_t idesc = make_idesc_bf16(128, NT, A_MN, B_MN);
 
-  // the operand row this thread owns for K-major A (row = tid of the M tile)
   typename P::Row rowctx;
-  if constexpr (!A_MN || EPI_ROW) rowctx = p.rowA(c, c.m0 + tid);
+  if constexpr (!A_MN || EPI_ROW) rowctx = p.rowA(c, c.m0 + row_t);
 
   const int nkb = c.kend > c.kbeg ? (c.kend - c.kbeg + BK - 1) / BK : 0;
   for (int it = 0; it < nkb; ++it) {
@@ -607,62 +657,61 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restri
     uint8_t* b_hi = a_hi + A_PLANES * a_bytes;
     uint8_t* b_lo = b_hi + b_bytes;
     const int k0 = c.kbeg + it * BK;
-    // ---- A tile: 128 x 32
-    if constexpr (!A_MN) {
+    // ---- A tile (128 x 32): 512 units, two per thread; all loads first, then convert + store
+    {
+      float x[2][8];
+      uint32_t off[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float x[8];
-        p.loadA(c, rowctx, k0 + 8 * u, x);
-        const uint32_t off = (uint32_t)u * (128 * 16) + (uint32_t)tid * 16;
-        if constexpr (A_PLANES == 2) {
-          uint4 hi, lo;
-          split8(x, hi, lo);
-          *reinterpret_cast<uint4*>(a_hi + off) = hi;
-          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      for (int j = 0; j < 2; ++j) {
+        if constexpr (!A_MN) {
+          const int u = 2 * half + j;
+          p.loadA(c, rowctx, k0 + 8 * u, x[j]);
+          off[j] = (uint32_t)u * (128 * 16) + (uint32_t)row_t * 16;
         } else {
-          *reinterpret_cast<uint4*>(a_hi + off) = pack8_exact(x);
+          const int k = tid & 31, grp = (tid >> 5) + 8 * j;  // 16 groups of 8 rows
+          p.loadA(c, k0 + k, c.m0 + 8 * grp, x[j]);
+          off[j] = (uint32_t)(k >> 3) * (128 * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
         }
       }
-    } else {
-      const int k = tid & 31;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int grp = (tid >> 5) + 4 * j;  // 16 groups of 8 rows
-        float x[8];
-        p.loadA(c, k0 + k, c.m0 + 8 * grp, x);
-        const uint32_t off = (uint32_t)(k >> 3) * (128 * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
+      for (int j = 0; j < 2; ++j) {
         if constexpr (A_PLANES == 2) {
           uint4 hi, lo;
-          split8(x, hi, lo);
-          *reinterpret_cast<uint4*>(a_hi + off) = hi;
-          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+          split8(x[j], hi, lo);
+          *reinterpret_cast<uint4*>(a_hi + off[j]) = hi;
+          *reinterpret_cast<uint4*>(a_lo + off[j]) = lo;
         } else {
-          *reinterpret_cast<uint4*>(a_hi + off) = pack8_exact(x);
+          *reinterpret_cast<uint4*>(a_hi + off[j]) = pack8_exact(x[j]);
         }
       }
     }
-    // ---- B tile: NT x 32
-    if constexpr (!B_MN) {
-      for (int u = tid; u < NT * 4; u += 128) {
-        const int n = u % NT, ku = u / NT;
-        float x[8];
-        p.loadB(c, n, k0 + 8 * ku, x);
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        const uint32_t off = (uint32_t)ku * ((uint32_t)NT * 16) + (uint32_t)n * 16;
-        *reinterpret_cast<uint4*>(b_hi + off) = hi;
-        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+    // ---- B tile (NT x 32): NT*4 units
+    for (int u0 = tid; u0 < NT * 4; u0 += 2 * NTHR) {
+      float x[2][8];
+      uint32_t off[2];
+      bool act[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int u = u0 + j * NTHR;
+        act[j] = u < NT * 4;
+        if constexpr (!B_MN) {
+          const int n = act[j] ? u % NT : 0, ku = act[j] ? u / NT : 0;
+          p.loadB(c, act[j] ? n : NT, k0 + 8 * ku, x[j]);
+          off[j] = (uint32_t)ku * ((uint32_t)NT * 16) + (uint32_t)n * 16;
+        } else {
+          const int k = u & 31, grp = act[j] ? u >> 5 : 0;  // NT/8 groups
+          p.loadB(c, act[j] ? k0 + k : c.kend, 8 * grp, x[j]);
+          off[j] = (uint32_t)(k >> 3) * ((uint32_t)NT * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
+        }
       }
-    } else {
-      for (int u = tid; u < NT * 4; u += 128) {
-        const int k = u & 31, grp = u >> 5;  // NT/8 groups
-        float x[8];
-        p.loadB(c, k0 + k, 8 * grp, x);
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        const uint32_t off = (uint32_t)(k >> 3) * ((uint32_t)NT * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
-        *reinterpret_cast<uint4*>(b_hi + off) = hi;
-        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (act[j]) {
+          uint4 hi, lo;
+          split8(x[j], hi, lo);
+          *reinterpret_cast<uint4*>(b_hi + off[j]) = hi;
+          *reinterpret_cast<uint4*>(b_lo + off[j]) = lo;
+        }
       }
     }
     fence_proxy_async_smem();
@@ -691,9 +740,33 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restri
     tcgen05_after_sync();
   }
 
-  // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32); thread -> accumulator row m0 + tid
-  const int m = c.m0 + tid;
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  // ---- epilogue: warp w reads TMEM lanes [32(w%4), +32) -> accumulator row m0 + row_t; the two warps sharing a
+  // lane quadrant take the even / odd 16-column chunks
+  const int m = c.m0 + row_t;
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  auto load_chunk = [&](int c0, float* v) {
+    if (nkb > 0) tmem_ld16(lane_base + c0, v);
+    else
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  };
+
+  if constexpr (P::TILE_EPI) {
+    // all MMAs are complete, the operand ring is dead: stage the tile in shared memory, then walk it row-major
+    float* tile = reinterpret_cast<float*>(smem);
+    const int ld = NT + 4;
+    for (int c0 = 16 * half; c0 < NT; c0 += 32) {
+      float v[16];
+      load_chunk(c0, v);
+      st16(tile + row_t * ld + c0, v);
+    }
+    tcgen05_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+    p.tile_epi(c, tile, ld, tid, NTHR);
+    return;
+  }
+
   if constexpr (SPLITK) {
     const int S = p.S;
     if (S > 1) {
@@ -701,14 +774,11 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restri
       const int tiles = gridDim.x * gridDim.y;
       const int tile = blockIdx.y * gridDim.x + blockIdx.x;
       float* mine = part + ((int64_t)(z * tiles + tile) * S + sp) * ((int64_t)NT * 128);
-      for (int c0 = 0; c0 < NT; c0 += 16) {
+      for (int c0 = 16 * half; c0 < NT; c0 += 32) {
         float v[16];
-        if (nkb > 0) tmem_ld16(lane_base + c0, v);
-        else
+        load_chunk(c0, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) __stcg(mine + (int64_t)(c0 + i) * 128 + tid, v[i]);
+        for (int i = 0; i < 16; ++i) __stcg(mine + (int64_t)(c0 + i) * 128 + row_t, v[i]);
       }
       __threadfence();
       __syncthreads();
@@ -721,13 +791,14 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restri
       if (s_last) {
         __threadfence();
         const float* base = part + (int64_t)(z * tiles + tile) * S * ((int64_t)NT * 128);
-        for (int c0 = 0; c0 < NT; c0 += 16) {
+        for (int c0 = 16 * half; c0 < NT; c0 += 32) {
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float sum = 0.f;
-            for (int q = 0; q < S; ++q) sum += __ldcg(base + (int64_t)q * NT * 128 + (int64_t)(c0 + i) * 128 + tid);
-            v[i] = sum;
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          for (int q = 0; q < S; ++q) {  // fixed order: deterministic
+            const float* src = base + (int64_t)q * NT * 128 + (int64_t)c0 * 128 + row_t;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldcg(src + i * 128);
           }
           p.epi(c, m, c0, v);
         }
@@ -738,12 +809,9 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restri
       return;
     }
   }
-  for (int c0 = 0; c0 < NT; c0 += 16) {
+  for (int c0 = 16 * half; c0 < NT; c0 += 32) {
     float v[16];
-    if (nkb > 0) tmem_ld16(lane_base + c0, v);
-    else
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    load_chunk(c0, v);
     if constexpr (EPI_ROW) p.epi(c, rowctx, c0, v);
     else p.epi(c, m, c0, v);
   }
@@ -754,7 +822,8 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const P p, float* __restri
 
 template <bool A_MN, bool B_MN, int A_PLANES, bool EPI_ROW, bool SPLITK, class P>
 static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tickets, cudaStream_t st) {
-  const size_t smem = (size_t)p.nstage * (A_PLANES * 128 * BK * 2 + 2 * (size_t)p.NT * BK * 2);
+  size_t smem = (size_t)p.nstage * (A_PLANES * 128 * BK * 2 + 2 * (size_t)p.NT * BK * 2);
+  if (P::TILE_EPI) smem = std::max(smem, (size_t)128 * (p.NT + 4) * sizeof(float));
   auto kern = tc_gemm_kernel<A_MN, B_MN, A_PLANES, EPI_ROW, SPLITK, P>;
   static bool configured = false;  // one flag per instantiation
   if (!configured) {
@@ -762,7 +831,7 @@ static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tic
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, 128, smem, st>>>(p, part, tickets);
+  kern<<<grid, NTHR, smem, st>>>(p, part, tickets);
   return cudaGetLastError();
 }
 

@@ -256,25 +256,14 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
                                                    const int32_t* __restrict__ count, int64_t stride4, int64_t off4,
                                                    int64_t n4, float lr, float b1, float b2, float eps) {
   const int k = blockIdx.y;
-  const float t = (float)count[k];  // already incremented for this step
-  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
-  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+  const tc::AdamCoef ac = tc::adam_coef(b1, b2, lr, eps, count[k]);  // count already incremented for this step
   const int64_t base = (int64_t)k * stride4 + off4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 P = p[base + i], G = __ldcs(g + base + i), M = m[base + i], V = v[base + i];
-    float* pp = &P.x;
-    const float* gg = &G.x;
-    float* mm = &M.x;
-    float* vv = &V.x;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float mn = omb1 * gg[e] + b1 * mm[e];
-      float vn = omb2 * (gg[e] * gg[e]) + b2 * vv[e];
-      float upd = (mn / bc1) / (sqrtf(vn / bc2) + eps);
-      pp[e] = pp[e] + (-lr) * upd;
-      mm[e] = mn;
-      vv[e] = vn;
-    }
+    tc::adam_elem(ac, G.x, P.x, M.x, V.x);
+    tc::adam_elem(ac, G.y, P.y, M.y, V.y);
+    tc::adam_elem(ac, G.z, P.z, M.z, V.z);
+    tc::adam_elem(ac, G.w, P.w, M.w, V.w);
     p[base + i] = P;
     m[base + i] = M;
     v[base + i] = V;

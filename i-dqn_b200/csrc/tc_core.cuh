@@ -120,11 +120,14 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    // cvt.rn.bf16x2.f32 packs two conversions in one instruction; hi as fp32 is just its bits << 16
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hp);
+    const float r0 = x[2 * i] - __uint_as_float(hb << 16);
+    const float r1 = x[2 * i + 1] - __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
+    h[i] = hb;
+    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -132,10 +135,33 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 __device__ __forceinline__ uint4 pack8_exact(const float* x) {  // values exactly representable in bf16 (u8 pixels)
   uint32_t h[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    h[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x[2 * i])) |
-           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x[2 * i + 1])) << 16);
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+  }
   return make_uint4(h[0], h[1], h[2], h[3]);
+}
+
+// optax.scale_by_adam + scale(-lr) on one element with MUFU-approximate sqrt/divide (relative error ~2^-22,
+// far inside the 1e-4 parity bar; the IEEE versions cost >100 instructions per element)
+struct AdamCoef {
+  float b1, b2, omb1, omb2, rbc1, rbc2, lr, eps;
+};
+__device__ __forceinline__ AdamCoef adam_coef(float b1, float b2, float lr, float eps, int count) {
+  AdamCoef c;
+  const float t = (float)count;
+  c.b1 = b1, c.b2 = b2, c.omb1 = 1.f - b1, c.omb2 = 1.f - b2;
+  c.rbc1 = 1.f / (1.f - powf(b1, t));
+  c.rbc2 = 1.f / (1.f - powf(b2, t));
+  c.lr = lr, c.eps = eps;
+  return c;
+}
+__device__ __forceinline__ void adam_elem(const AdamCoef& c, float g, float& p, float& m, float& v) {
+  m = fmaf(c.b1, m, c.omb1 * g);
+  v = fmaf(c.b2, v, c.omb2 * (g * g));
+  float sq;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v * c.rbc2));
+  p = fmaf(-c.lr, __fdividef(m * c.rbc1, sq + c.eps), p);
 }
 
 // ---- operand tile addressing (BK = 32 elements = 4 k-units per stage) ------------------------------------------
