@@ -645,10 +645,67 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
   const uint32_t tmem = tmem_base_s;
   const uint32_t idesc = make_idesc_bf16(128, NT, A_MN, B_MN);
 
+  // epilogue row context (dgrad problems) and the two gather rows of a K-major A operand
   typename P::Row rowctx;
-  if constexpr (!A_MN || EPI_ROW) rowctx = p.rowA(c, c.m0 + row_t);
+  if constexpr (EPI_ROW) rowctx = p.rowA(c, c.m0 + row_t);
+  typename P::Row rowg[2];
+  if constexpr (!A_MN) {
+    rowg[0] = p.rowA(c, c.m0 + (tid >> 2));
+    rowg[1] = p.rowA(c, c.m0 + (tid >> 2) + 64);
+  }
+
+  // Unit -> thread mapping: lanes run along the direction that is contiguous in global memory
+  //   K-major  tile [R x 32]: unit e -> kunit = e & 3, row = e >> 2          (4 lanes = 128 contiguous bytes;
+  //                                                                           smem stores: 4 wavefronts, optimal)
+  //   MN-major tile [32 x C]: unit e -> group = (e & 7) + 8 * (e >> 8), k = (e >> 3) & 31
+  //                                                                          (8 lanes = 256 contiguous bytes)
+  // Register double buffering: the loads of k-block i+1 are issued right after block i was converted and stored,
+  // so they are in flight across the barrier, the MMA issue and the next stage wait.
+  constexpr int MAXB = 4;  // NT <= 256 -> at most 4 B units per thread
+  float ra[2][8], rb[MAXB][8];
+  uint32_t offa[2], offb[MAXB];
+  bool actb[MAXB];
+  const int nbu = B_MN ? ((NT + 63) / 64) * 256 : NT * 4;  // B unit slots
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int e = tid + NTHR * j;
+    if constexpr (!A_MN) offa[j] = (uint32_t)(e & 3) * (128 * 16) + (uint32_t)(e >> 2) * 16;
+    else {
+      const int grp = (e & 7) + 8 * (e >> 8), k = (e >> 3) & 31;
+      offa[j] = (uint32_t)(k >> 3) * (128 * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXB; ++j) {
+    const int e = tid + NTHR * j;
+    if constexpr (!B_MN) {
+      actb[j] = e < nbu;
+      offb[j] = (uint32_t)(e & 3) * ((uint32_t)NT * 16) + (uint32_t)(e >> 2) * 16;
+    } else {
+      const int grp = (e & 7) + 8 * (e >> 8), k = (e >> 3) & 31;
+      actb[j] = e < nbu && grp < (NT >> 3);
+      offb[j] = (uint32_t)(k >> 3) * ((uint32_t)NT * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
+    }
+  }
+  auto load_units = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int e = tid + NTHR * j;
+      if constexpr (!A_MN) p.loadA(c, rowg[j], k0 + 8 * (e & 3), ra[j]);
+      else p.loadA(c, k0 + ((e >> 3) & 31), c.m0 + 8 * ((e & 7) + 8 * (e >> 8)), ra[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < MAXB; ++j) {
+      const int e = tid + NTHR * j;
+      if (j * NTHR < nbu) {  // uniform
+        if constexpr (!B_MN) p.loadB(c, actb[j] ? (e >> 2) : NT, k0 + 8 * (e & 3), rb[j]);
+        else p.loadB(c, actb[j] ? k0 + ((e >> 3) & 31) : c.kend, 8 * ((e & 7) + 8 * (e >> 8)), rb[j]);
+      }
+    }
+  };
 
   const int nkb = c.kend > c.kbeg ? (c.kend - c.kbeg + BK - 1) / BK : 0;
+  if (nkb > 0) load_units(c.kbeg);
   for (int it = 0; it < nkb; ++it) {
     const int s = it % nst;
     if (it >= nst) mbar_wait(&mma_done[s], ((it / nst) - 1) & 1);
@@ -656,64 +713,27 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
     uint8_t* a_lo = a_hi + a_bytes;  // only if A_PLANES == 2
     uint8_t* b_hi = a_hi + A_PLANES * a_bytes;
     uint8_t* b_lo = b_hi + b_bytes;
-    const int k0 = c.kbeg + it * BK;
-    // ---- A tile (128 x 32): 512 units, two per thread; all loads first, then convert + store
-    {
-      float x[2][8];
-      uint32_t off[2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if constexpr (!A_MN) {
-          const int u = 2 * half + j;
-          p.loadA(c, rowctx, k0 + 8 * u, x[j]);
-          off[j] = (uint32_t)u * (128 * 16) + (uint32_t)row_t * 16;
-        } else {
-          const int k = tid & 31, grp = (tid >> 5) + 8 * j;  // 16 groups of 8 rows
-          p.loadA(c, k0 + k, c.m0 + 8 * grp, x[j]);
-          off[j] = (uint32_t)(k >> 3) * (128 * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if constexpr (A_PLANES == 2) {
-          uint4 hi, lo;
-          split8(x[j], hi, lo);
-          *reinterpret_cast<uint4*>(a_hi + off[j]) = hi;
-          *reinterpret_cast<uint4*>(a_lo + off[j]) = lo;
-        } else {
-          *reinterpret_cast<uint4*>(a_hi + off[j]) = pack8_exact(x[j]);
-        }
+    for (int j = 0; j < 2; ++j) {
+      if constexpr (A_PLANES == 2) {
+        uint4 hi, lo;
+        split8(ra[j], hi, lo);
+        *reinterpret_cast<uint4*>(a_hi + offa[j]) = hi;
+        *reinterpret_cast<uint4*>(a_lo + offa[j]) = lo;
+      } else {
+        *reinterpret_cast<uint4*>(a_hi + offa[j]) = pack8_exact(ra[j]);
       }
     }
-    // ---- B tile (NT x 32): NT*4 units
-    for (int u0 = tid; u0 < NT * 4; u0 += 2 * NTHR) {
-      float x[2][8];
-      uint32_t off[2];
-      bool act[2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int u = u0 + j * NTHR;
-        act[j] = u < NT * 4;
-        if constexpr (!B_MN) {
-          const int n = act[j] ? u % NT : 0, ku = act[j] ? u / NT : 0;
-          p.loadB(c, act[j] ? n : NT, k0 + 8 * ku, x[j]);
-          off[j] = (uint32_t)ku * ((uint32_t)NT * 16) + (uint32_t)n * 16;
-        } else {
-          const int k = u & 31, grp = act[j] ? u >> 5 : 0;  // NT/8 groups
-          p.loadB(c, act[j] ? k0 + k : c.kend, 8 * grp, x[j]);
-          off[j] = (uint32_t)(k >> 3) * ((uint32_t)NT * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (act[j]) {
-          uint4 hi, lo;
-          split8(x[j], hi, lo);
-          *reinterpret_cast<uint4*>(b_hi + off[j]) = hi;
-          *reinterpret_cast<uint4*>(b_lo + off[j]) = lo;
-        }
+    for (int j = 0; j < MAXB; ++j) {
+      if (j * NTHR < nbu && actb[j]) {
+        uint4 hi, lo;
+        split8(rb[j], hi, lo);
+        *reinterpret_cast<uint4*>(b_hi + offb[j]) = hi;
+        *reinterpret_cast<uint4*>(b_lo + offb[j]) = lo;
       }
     }
+    if (it + 1 < nkb) load_units(c.kbeg + (it + 1) * BK);  // prefetch: in flight across the barrier + MMA issue
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
