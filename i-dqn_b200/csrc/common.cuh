@@ -1,5 +1,6 @@
 // Shared declarations of libidqn_b200 (internal; the public surface is include/idqn_b200.h).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -102,6 +103,13 @@ struct idqn_handle {
   int64_t act_stride;
   float* dact;          // [K][act_stride]   gradients w.r.t. layer outputs
   float* q;             // [2K][B][A] final-layer outputs (debug / apply)
+  // bf16 hi/lo planes of every tensor-core GEMM operand (gemm_tc.cuh), same element indexing as the fp32 master
+  __nv_bfloat16 *won_hi, *won_lo, *wtg_hi, *wtg_lo;  // [K][stride]      online / target weights
+  __nv_bfloat16 *act_hi, *act_lo;                    // [2K][act_stride]
+  __nv_bfloat16 *dact_hi, *dact_lo;                  // [K][act_stride]
+  __nv_bfloat16 *in_hi, *in_lo;                      // [2][B*in_elems]  state, next_state
+  __nv_bfloat16* ones;                               // {1,0 x7 | 0 x8}: bias-gradient row of the wgrad GEMMs
+  int planes_dirty[2];                               // online / target planes stale (host upload)
   // split-K workspace
   float* part;
   int64_t part_floats;

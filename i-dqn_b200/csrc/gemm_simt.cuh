@@ -8,6 +8,7 @@
 // Split-K partials are combined by the last-arriving CTA in a fixed order (deterministic results).
 #pragma once
 #include "common.cuh"
+#include "tc_core.cuh"
 
 struct NetPtr {  // per-net pointer selection: nets [0,zsplit) use p0, the rest p1
   const void* p0;
@@ -28,6 +29,7 @@ struct FwdProb {
   int x_u8;
   int64_t w_off, b_off;
   float* y;
+  __nv_bfloat16 *yh, *yl;  // optional bf16 hi/lo planes of the output (consumed by the tensor-core kernels)
   int64_t ystride;
   float scale;
   int relu;
@@ -41,6 +43,7 @@ struct FwdProb {
     const float* wk;
     const float* bias;
     float* y;
+    __nv_bfloat16 *yh, *yl;
     int M, kbeg, kend, z;
     __device__ __forceinline__ float loadA(int m, int k) const {
       if (m >= M || k >= kend) return 0.f;
@@ -64,6 +67,7 @@ struct FwdProb {
       float v = acc * p->scale + __ldg(bias + n);
       if (p->relu) v = fmaxf(v, 0.f);
       y[(int64_t)m * p->N + n] = v;
+      if (yh) tc::st1_planes(yh + (int64_t)m * p->N + n, yl + (int64_t)m * p->N + n, v);
     }
   };
   __device__ __forceinline__ Ctx ctx(int zz) const {
@@ -77,6 +81,8 @@ struct FwdProb {
     c.xu = x_u8 ? x.get<uint8_t>(z) : nullptr;
     c.xf = x_u8 ? nullptr : x.get<float>(z);
     c.y = y + (int64_t)z * ystride;
+    c.yh = yh ? yh + (int64_t)z * ystride : nullptr;
+    c.yl = yl ? yl + (int64_t)z * ystride : nullptr;
     c.M = M;
     c.kbeg = sp * kchunk;
     c.kend = min(K, c.kbeg + kchunk);
@@ -153,6 +159,7 @@ struct DgradProb {
   int64_t w_off;
   const float* xact;  // layer input activations (relu outputs) [nz][B*IH*IW*IC] for the mask
   float* dx;          // same shape
+  __nv_bfloat16 *dxh, *dxl;  // optional planes of dx
   int64_t xstride;
   int nz, S;          // S: split-K (always 1 here)
   int ncls;           // S_conv^2 stride-parity classes
@@ -168,6 +175,7 @@ struct DgradProb {
     const float* wk;
     const float* xact;
     float* dx;
+    __nv_bfloat16 *dxh, *dxl;
     int M, kbeg, kend, z;
     int py, px, ky0, kx0;
     FastDiv d_n, d_nix;
@@ -211,7 +219,9 @@ struct DgradProb {
       int iy, ix;
       rowdec(m, b, iy, ix);
       int64_t idx = (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + n;
-      dx[idx] = xact[idx] > 0.f ? acc : 0.f;  // relu'(0) = 0 as in jax
+      const float o = xact[idx] > 0.f ? acc : 0.f;  // relu'(0) = 0 as in jax
+      dx[idx] = o;
+      if (dxh) tc::st1_planes(dxh + idx, dxl + idx, o);
     }
   };
   __device__ __forceinline__ Ctx ctx(int zz) const {
@@ -230,6 +240,8 @@ struct DgradProb {
     c.wk = w.get<float>(z) + w_off;
     c.xact = xact + (int64_t)z * xstride;
     c.dx = dx + (int64_t)z * xstride;
+    c.dxh = dxh ? dxh + (int64_t)z * xstride : nullptr;
+    c.dxl = dxl ? dxl + (int64_t)z * xstride : nullptr;
     c.kbeg = 0;
     c.kend = K;
     return c;

@@ -1,11 +1,15 @@
 // tcgen05 implicit-GEMM kernels for the i-DQN step (sm_100a).
 //
-// One CTA (128 threads) owns a 128 x NT accumulator tile in TMEM.  Its threads gather the operands from global
-// memory (im2col / transposed / weight reads, u8 dequant), split fp32 into bf16 hi+lo planes and store them in
-// the UMMA canonical no-swizzle layouts of tc_core.cuh; one thread issues hi*hi + hi*lo + lo*hi tcgen05.mma per
-// 16-wide K slice (fp32-faithful "bf16x3"); a 3-stage smem ring with tcgen05.commit -> mbarrier
-// lets the gather of k-block i+1.. overlap the MMAs of block i.  The epilogue reads TMEM with tcgen05.ld and is
-// fused per problem: bias+relu, relu' mask, deterministic split-K fix-up, or Adam.
+// Every GEMM operand (input frames, activations, activation gradients, weights) is kept in HBM as two bf16
+// planes hi = bf16(x), lo = bf16(x - hi) next to its fp32 master, written once by whoever produces the tensor
+// (forward / dgrad epilogues, the Adam kernels, the input prep kernel).  A CTA (256 threads) owns a 128 x NT fp32
+// accumulator in TMEM and streams 32-wide K blocks through a 4-stage shared-memory ring with 16-byte cp.async
+// copies (zero-fill handles SAME padding and ragged edges), written directly in the UMMA canonical no-swizzle
+// layouts of tc_core.cuh: the main loop is address arithmetic + LDGSTS only, three k-blocks of loads stay in
+// flight, and no transposes are materialised (both K-major and MN-major operands are used).  One thread issues
+// hi*hi + hi*lo + lo*hi tcgen05.mma per 16-wide slice (fp32-faithful "bf16x3"); tcgen05.commit ->
+// mbarrier releases the stage.  Epilogues read TMEM with tcgen05.ld and are fused per problem: bias+relu (+ the
+// output's planes), relu' mask, deterministic split-K fix-up, or Adam (+ the new weight planes).
 //
 // Problems (all dims runtime):                         A operand             B operand
 //   TcFwdConv    y = relu(conv(x)*s + b)               im2col, K-major       weights [k][n], MN-major  (heads concat on N)
@@ -23,75 +27,83 @@
 
 namespace tcg {
 using namespace tc;
+typedef __nv_bfloat16 bf16;
 
-constexpr int NS = 3;  // smem ring depth
+constexpr int NS = 4;      // smem ring depth (max)
+constexpr int NTHR = 256;  // threads per CTA
 
-__device__ __forceinline__ void ld8(const float* __restrict__ p, float* x) {  // 32-byte aligned
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+struct Src {  // source of one 16-byte unit (8 elements) in both planes
+  const bf16* hi;
+  const bf16* lo;
+  bool ok;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? 16 : 0;  // src-size 0 -> the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void zero8(float* x) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = 0.f;
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
-// predicated 8-float load: no branch, so the loads of all the units a thread owns can be issued back to back
-__device__ __forceinline__ void ld8p(const float* __restrict__ p, bool ok, float* x) {
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  if (ok) {
-    a = __ldg(reinterpret_cast<const float4*>(p));
-    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  }
-  x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
 __device__ __forceinline__ void st16(float* __restrict__ dst, const float* v) {
 #pragma unroll
   for (int q = 0; q < 4; ++q)
     reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
+// 16 consecutive elements into both planes (32 bytes each)
+__device__ __forceinline__ void st16_planes(bf16* __restrict__ hi, bf16* __restrict__ lo, const float* v) {
+  uint4 h0, l0, h1, l1;
+  split8(v, h0, l0);
+  split8(v + 8, h1, l1);
+  reinterpret_cast<uint4*>(hi)[0] = h0, reinterpret_cast<uint4*>(hi)[1] = h1;
+  reinterpret_cast<uint4*>(lo)[0] = l0, reinterpret_cast<uint4*>(lo)[1] = l1;
+}
 
 // ==================================================================================================
 // problem definitions.  Every problem provides
-//   Ctx ctx(bx, by, bz)                      per-CTA constants (m0, n0, k range, pointers)
-//   RowA / rowA(ctx, r)                      per-thread decode of the operand row/group the thread owns
-//   loadA(ctx, rowctx, kk, x[8]) ...         one 8-element unit
-//   epi(ctx, m, n0, v[16], ncols)            16 consecutive accumulator columns of row m
-// The kernel template below fixes who loads what.
+//   Ctx ctx(bx, by, bz)          per-CTA constants (m0, k range, plane pointers)
+//   Row rowA(ctx, m)             decode of an operand / epilogue row
+//   srcA / srcB                  global source of one 8-element unit (K-major: (row|n, k8); MN-major: (k, mn8))
+//   epi(ctx, m|row, n0, v[16])   16 consecutive accumulator columns of one row, or tile_epi for TILE_EPI problems
 // ==================================================================================================
 
 struct TcFwdConv {
   static constexpr bool TILE_EPI = false;
   ConvGeom g;
-  NetPtr x, w;
-  int x_u8;
+  NetPtr xh, xl;    // input planes (per net / per group)
+  NetPtr wh, wl;    // weight planes (online nets, then target nets)
+  NetPtr w;         // fp32 arenas (bias)
   int64_t w_off, b_off;
-  float* y;
+  float* y;         // [nets][ystride] fp32 output
+  bf16 *yh, *yl;    // output planes, same indexing
   int64_t ystride;
   float scale;
   int relu;
-  int nh;         // heads concatenated along N inside one group (they share the input)
-  int hpt;        // heads per N tile
-  int M, K, NT;   // NT = UMMA N (multiple of 16)
-  int nstage;     // smem ring depth (<= NS)
-  int vec;        // 8-wide vector loads are legal (IC % 8 == 0 && OC % 8 == 0) or the u8/IC==4 fast path
+  int nh;           // heads concatenated along N inside one group (they share the input)
+  int hpt;          // heads per N tile
+  int M, K, NT;     // NT = UMMA N (multiple of 16)
+  int nstage;
 
   struct Ctx {
-    const TcFwdConv* p;
     int m0, kbeg, kend, group, head0, nheads;
-    const uint8_t* xu;
-    const float* xf;
+    const bf16 *ah, *al;
   };
   __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
     Ctx c;
-    c.p = this;
     c.m0 = bx * 128;
     c.kbeg = 0, c.kend = K;
     c.group = bz;
     c.head0 = by * hpt;
     c.nheads = min(hpt, nh - c.head0);
-    const int net0 = bz * nh;
-    c.xu = x_u8 ? x.get<uint8_t>(net0) : nullptr;
-    c.xf = x_u8 ? nullptr : x.get<float>(net0);
+    c.ah = xh.get<bf16>(bz * nh);
+    c.al = xl.get<bf16>(bz * nh);
     return c;
   }
   struct Row {
@@ -109,53 +121,25 @@ struct TcFwdConv {
     r.base = (int64_t)b * g.IH * g.IW * g.IC;
     return r;
   }
-  // A unit: row = output pixel, 8 consecutive k = (ky, kx, c..c+7)
-  __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* x) const {
+  // A unit: row = output pixel, 8 consecutive k = (ky, kx, c..c+7); `half` selects one of the two pixels when IC == 4
+  __device__ __forceinline__ Src srcA(const Ctx& c, const Row& r, int k, int half) const {
     uint32_t ky, rem, kx, ch;
     g.d_kwic.divmod(k < K ? k : 0, ky, rem);
     g.d_ic.divmod(rem, kx, ch);
-    const int iy = r.iy0 + (int)ky;
-    const bool rowok = r.valid && k < c.kend && (unsigned)iy < (unsigned)g.IH;
-    if (g.IC >= 8) {
-      const int ix = r.ix0 + (int)kx;
-      const bool ok = rowok && (unsigned)ix < (unsigned)g.IW;
-      const int64_t idx = ok ? r.base + ((int64_t)iy * g.IW + ix) * g.IC + ch : 0;
-      if (c.xu) {
-        uint2 raw = make_uint2(0u, 0u);
-        if (ok) raw = __ldg(reinterpret_cast<const uint2*>(c.xu + idx));
-        const uint32_t wds[2] = {raw.x, raw.y};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (float)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu);
-      } else {
-        ld8p(c.xf + idx, ok, x);
-      }
-      return;
-    }
-    // IC == 4: two pixels x four stacked frames (the Atari first layer)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ix = r.ix0 + (int)kx + h;
-      const bool ok = rowok && (int)kx + h < g.KW && (unsigned)ix < (unsigned)g.IW;
-      const int64_t idx = ok ? r.base + ((int64_t)iy * g.IW + ix) * 4 : 0;
-      if (c.xu) {
-        uint32_t raw = 0u;
-        if (ok) raw = __ldg(reinterpret_cast<const uint32_t*>(c.xu + idx));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) x[4 * h + i] = (float)((raw >> (8 * i)) & 0xffu);
-      } else {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) v = __ldg(reinterpret_cast<const float4*>(c.xf + idx));
-        x[4 * h] = v.x, x[4 * h + 1] = v.y, x[4 * h + 2] = v.z, x[4 * h + 3] = v.w;
-      }
-    }
+    const int iy = r.iy0 + (int)ky, ix = r.ix0 + (int)kx + half;
+    const bool ok = r.valid && k < c.kend && (unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW &&
+                    (int)kx + half < g.KW;
+    const int64_t idx = ok ? r.base + ((int64_t)iy * g.IW + ix) * g.IC + ch : 0;
+    return Src{c.ah + idx, c.al + idx, ok};
   }
   // B unit (MN-major): one k, 8 consecutive n = head*OC + oc..oc+7
-  __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* x) const {
+  __device__ __forceinline__ Src srcB(const Ctx& c, int k, int n) const {
     uint32_t hl, oc;
     g.d_oc.divmod(n, hl, oc);
     const bool ok = k < c.kend && (int)hl < c.nheads;
-    const float* wk = w.get<float>(c.group * nh + c.head0 + (ok ? (int)hl : 0)) + w_off + (int64_t)(ok ? k : 0) * g.OC + oc;
-    ld8p(wk, ok, x);
+    const int net = c.group * nh + c.head0 + (ok ? (int)hl : 0);
+    const int64_t idx = w_off + (int64_t)(ok ? k : 0) * g.OC + oc;
+    return Src{wh.get<bf16>(net) + idx, wl.get<bf16>(net) + idx, ok};
   }
   __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
     if (m >= M) return;
@@ -176,7 +160,9 @@ struct TcFwdConv {
 #pragma unroll
         for (int i = 0; i < 16; ++i) r[i] = fmaxf(r[i], 0.f);
       }
-      st16(y + (int64_t)net * ystride + (int64_t)m * g.OC + oc, r);
+      const int64_t o = (int64_t)net * ystride + (int64_t)m * g.OC + oc;
+      st16(y + o, r);
+      if (yh) st16_planes(yh + o, yl + o, r);
       return;
     }
 #pragma unroll
@@ -186,7 +172,9 @@ struct TcFwdConv {
       const int net = c.group * nh + c.head0 + (int)hl;
       float r = v[i] * scale + __ldg(w.get<float>(net) + b_off + oc);
       if (relu) r = fmaxf(r, 0.f);
-      y[(int64_t)net * ystride + (int64_t)m * g.OC + oc] = r;
+      const int64_t o = (int64_t)net * ystride + (int64_t)m * g.OC + oc;
+      y[o] = r;
+      if (yh) st1_planes(yh + o, yl + o, r);
     }
   }
 };
@@ -195,28 +183,26 @@ struct TcFwdConv {
 struct TcDgradConv {
   static constexpr bool TILE_EPI = false;
   ConvGeom g;
-  const float* dy;
+  const bf16 *dyh, *dyl;  // [z][dystride]
   int64_t dystride;
-  NetPtr w;
+  NetPtr wh, wl;          // online weight planes
   int64_t w_off;
-  const float* xact;
+  const float* xact;      // layer input (relu output) fp32, for the mask
   float* dx;
+  bf16 *dxh, *dxl;
   int64_t xstride;
-  int ncls, JH, JW, K, NT, vec, nstage;
+  int ncls, JH, JW, K, NT, nstage;
   FastDiv d_jwoc;
   int cls_niy[IDQN_MAX_CLASSES], cls_nix[IDQN_MAX_CLASSES];
   FastDiv cls_d_n[IDQN_MAX_CLASSES], cls_d_nix[IDQN_MAX_CLASSES];
 
   struct Ctx {
-    const TcDgradConv* p;
     int m0, M, kbeg, kend, z, py, px, ky0, kx0;
     FastDiv d_n, d_nix;
-    const float *dy, *wk, *xact;
-    float* dx;
+    const bf16 *ah, *al, *bh, *bl;
   };
   __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
     Ctx c;
-    c.p = this;
     const int z = bz / ncls, cl = bz - z * ncls;
     c.z = z;
     c.m0 = bx * 128;
@@ -225,10 +211,8 @@ struct TcDgradConv {
     c.d_n = cls_d_n[cl], c.d_nix = cls_d_nix[cl];
     c.M = g.B * cls_niy[cl] * cls_nix[cl];
     c.kbeg = 0, c.kend = K;
-    c.dy = dy + (int64_t)z * dystride;
-    c.wk = w.get<float>(z) + w_off;
-    c.xact = xact + (int64_t)z * xstride;
-    c.dx = dx + (int64_t)z * xstride;
+    c.ah = dyh + (int64_t)z * dystride, c.al = dyl + (int64_t)z * dystride;
+    c.bh = wh.get<bf16>(z) + w_off, c.bl = wl.get<bf16>(z) + w_off;
     return c;
   }
   struct Row {
@@ -244,7 +228,7 @@ struct TcDgradConv {
     return r;
   }
   // A unit: row = input pixel, k = (jy, jx, co..co+7) -> dy[b, oy, ox, co..]
-  __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* x) const {
+  __device__ __forceinline__ Src srcA(const Ctx& c, const Row& r, int k, int) const {
     uint32_t jy, rem, jx, co;
     d_jwoc.divmod(k < K ? k : 0, jy, rem);
     g.d_oc.divmod(rem, jx, co);
@@ -253,38 +237,41 @@ struct TcDgradConv {
     const int oy = ny / g.S, ox = nx / g.S;  // exact for this stride class when ny, nx >= 0
     const bool ok = r.valid && k < c.kend && ky < g.KH && kx < g.KW && ny >= 0 && nx >= 0 && oy < g.OH && ox < g.OW;
     const int64_t idx = ok ? (((int64_t)r.b * g.OH + oy) * g.OW + ox) * g.OC + co : 0;
-    ld8p(c.dy + idx, ok, x);
+    return Src{c.ah + idx, c.al + idx, ok};
   }
   // B unit (K-major): row n = input channel c, k = (jy, jx, co..co+7) -> W[ky,kx,c,co..]
-  __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* x) const {
+  __device__ __forceinline__ Src srcB(const Ctx& c, int n, int k) const {
     uint32_t jy, rem, jx, co;
     d_jwoc.divmod(k < K ? k : 0, jy, rem);
     g.d_oc.divmod(rem, jx, co);
     const int ky = c.ky0 + jy * g.S, kx = c.kx0 + jx * g.S;
     const bool ok = n < g.IC && k < c.kend && ky < g.KH && kx < g.KW;
     const int64_t idx = ok ? ((int64_t)(ky * g.KW + kx) * g.IC + n) * g.OC + co : 0;
-    ld8p(c.wk + idx, ok, x);
+    return Src{c.bh + idx, c.bl + idx, ok};
   }
   __device__ __forceinline__ void epi(const Ctx& c, const Row& r, int n0, const float* v) const {
     if (!r.valid) return;
-    const int64_t base = (((int64_t)r.b * g.IH + r.iy) * g.IW + r.ix) * g.IC;
+    const int64_t base = (int64_t)c.z * xstride + (((int64_t)r.b * g.IH + r.iy) * g.IW + r.ix) * g.IC;
     if ((g.IC & 15) == 0) {
       if (n0 >= g.IC) return;
       float o[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 xa = __ldg(reinterpret_cast<const float4*>(c.xact + base + n0) + q);
+        const float4 xa = __ldg(reinterpret_cast<const float4*>(xact + base + n0) + q);
         o[4 * q] = xa.x > 0.f ? v[4 * q] : 0.f, o[4 * q + 1] = xa.y > 0.f ? v[4 * q + 1] : 0.f;
         o[4 * q + 2] = xa.z > 0.f ? v[4 * q + 2] : 0.f, o[4 * q + 3] = xa.w > 0.f ? v[4 * q + 3] : 0.f;
       }
-      st16(c.dx + base + n0, o);
+      st16(dx + base + n0, o);
+      st16_planes(dxh + base + n0, dxl + base + n0, o);
       return;
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int n = n0 + i;
       if (n >= g.IC) break;
-      c.dx[base + n] = c.xact[base + n] > 0.f ? v[i] : 0.f;
+      const float o = xact[base + n] > 0.f ? v[i] : 0.f;  // relu'(0) = 0 as in jax
+      dx[base + n] = o;
+      st1_planes(dxh + base + n, dxl + base + n, o);
     }
   }
 };
@@ -293,34 +280,29 @@ struct TcDgradConv {
 struct TcWgradConv {
   static constexpr bool TILE_EPI = false;
   ConvGeom g;
-  NetPtr x;
-  int x_u8;
-  const float* dy;
+  NetPtr xh, xl;          // layer input planes
+  const bf16 *dyh, *dyl;
   int64_t dystride;
+  const bf16* ones;       // 16 B {1,0,...} followed by 16 B of zeros: the bias-gradient row
   float* gout;
   int64_t gstride, w_off;
   float scale;
-  int S, kchunk;  // split-K
-  int M, K, NT, vec, nstage;
+  int S, kchunk;          // split-K
+  int M, K, NT, nstage;
 
   struct Ctx {
-    const TcWgradConv* p;
     int m0, kbeg, kend, z, sp;
-    const uint8_t* xu;
-    const float* xf;
-    const float* dy;
+    const bf16 *ah, *al, *bh, *bl;
     float* out;
   };
   __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
     Ctx c;
-    c.p = this;
     c.z = bz / S, c.sp = bz - c.z * S;
     c.m0 = bx * 128;
     c.kbeg = c.sp * kchunk;
     c.kend = min(K, c.kbeg + kchunk);
-    c.xu = x_u8 ? x.get<uint8_t>(c.z) : nullptr;
-    c.xf = x_u8 ? nullptr : x.get<float>(c.z);
-    c.dy = dy + (int64_t)c.z * dystride;
+    c.ah = xh.get<bf16>(c.z), c.al = xl.get<bf16>(c.z);
+    c.bh = dyh + (int64_t)c.z * dystride, c.bl = dyl + (int64_t)c.z * dystride;
     c.out = gout + (int64_t)c.z * gstride + w_off;
     return c;
   }
@@ -328,53 +310,24 @@ struct TcWgradConv {
   __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
   // A unit (MN-major): one k = output pixel, 8 consecutive m = (ky, kx, c..c+7); row Kd is the ones row whose
   // product with dy is the bias gradient (it lands on the bias slot right behind the kernel in the arena)
-  __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
+  __device__ __forceinline__ Src srcA(const Ctx& c, int k, int m, int half) const {
+    if (m == g.Kd) return Src{ones + 4 * half, ones + 8 + 4 * half, k < c.kend && half == 0};
     const bool inr = k < c.kend && m < g.Kd;
     uint32_t b, rem, oy, ox, ky, rem2, kx, ch;
     g.d_ohow.divmod(inr ? k : 0, b, rem);
     g.d_ow.divmod(rem, oy, ox);
     g.d_kwic.divmod(inr ? m : 0, ky, rem2);
     g.d_ic.divmod(rem2, kx, ch);
-    const int iy = (int)(oy * g.S + ky) - g.PH;
-    const bool rowok = inr && (unsigned)iy < (unsigned)g.IH;
-    const int64_t sbase = (int64_t)b * g.IH * g.IW * g.IC + (int64_t)iy * g.IW * g.IC;
-    if (g.IC >= 8) {
-      const int ix = (int)(ox * g.S + kx) - g.PW;
-      const bool ok = rowok && (unsigned)ix < (unsigned)g.IW;
-      const int64_t idx = ok ? sbase + (int64_t)ix * g.IC + ch : 0;
-      if (c.xu) {
-        uint2 raw = make_uint2(0u, 0u);
-        if (ok) raw = __ldg(reinterpret_cast<const uint2*>(c.xu + idx));
-        const uint32_t wds[2] = {raw.x, raw.y};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xx[i] = (float)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu);
-      } else {
-        ld8p(c.xf + idx, ok, xx);
-      }
-    } else {  // IC == 4: two pixels
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ix = (int)(ox * g.S + kx) + h - g.PW;
-        const bool ok = rowok && (int)kx + h < g.KW && (unsigned)ix < (unsigned)g.IW;
-        const int64_t idx = ok ? sbase + (int64_t)ix * 4 : 0;
-        if (c.xu) {
-          uint32_t raw = 0u;
-          if (ok) raw = __ldg(reinterpret_cast<const uint32_t*>(c.xu + idx));
-#pragma unroll
-          for (int i = 0; i < 4; ++i) xx[4 * h + i] = (float)((raw >> (8 * i)) & 0xffu);
-        } else {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) v = __ldg(reinterpret_cast<const float4*>(c.xf + idx));
-          xx[4 * h] = v.x, xx[4 * h + 1] = v.y, xx[4 * h + 2] = v.z, xx[4 * h + 3] = v.w;
-        }
-      }
-    }
-    if (m == g.Kd && k < c.kend) xx[0] = 1.f;
+    const int iy = (int)(oy * g.S + ky) - g.PH, ix = (int)(ox * g.S + kx) + half - g.PW;
+    const bool ok = inr && (unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW && (int)kx + half < g.KW;
+    const int64_t idx = ok ? (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + ch : 0;
+    return Src{c.ah + idx, c.al + idx, ok};
   }
   // B unit (MN-major): one k = output pixel, 8 consecutive n = oc
-  __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* xx) const {
+  __device__ __forceinline__ Src srcB(const Ctx& c, int k, int n) const {
     const bool ok = k < c.kend && n < g.OC;
-    ld8p(c.dy + (ok ? (int64_t)k * g.OC + n : 0), ok, xx);
+    const int64_t idx = ok ? (int64_t)k * g.OC + n : 0;
+    return Src{c.bh + idx, c.bl + idx, ok};
   }
   __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
     if (m >= M) return;
@@ -398,46 +351,47 @@ struct TcWgradConv {
 
 // --------------------------------------------------------------------------------------------------
 // Dense layers with the batch on the N side ("weights are the M operand"): no padding of B=32 to 128 rows.
-struct TcFwdDenseT {
-  static constexpr bool TILE_EPI = false;  // y[net][b][o] = relu(sum_i x[b][i] W[i][o] + bias[o]);  M = O, N = B, K = I
-  NetPtr x, w;        // x: [nets][B][I] floats
+struct TcFwdDenseT {  // y[net][b][o] = relu(sum_i x[b][i] W[i][o] + bias[o]);  M = O, N = B, K = I
+  static constexpr bool TILE_EPI = false;
+  NetPtr xh, xl;      // [nets][B][I] planes
+  NetPtr wh, wl, w;   // weight planes, fp32 arenas (bias)
   int64_t w_off, b_off;
   float* y;
+  bf16 *yh, *yl;
   int64_t ystride;
   int relu;
   int I, O, B;        // K, M, N
   int S, kchunk, NT, nstage;
 
   struct Ctx {
-    const TcFwdDenseT* p;
     int m0, kbeg, kend, z, sp;
-    const float *xin, *wk, *bias;
-    float* y;
+    const bf16 *ah, *al, *bh, *bl;
+    const float* bias;
   };
   __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
     Ctx c;
-    c.p = this;
     c.z = bz / S, c.sp = bz - c.z * S;
     c.m0 = bx * 128;
     c.kbeg = c.sp * kchunk;
     c.kend = min(I, c.kbeg + kchunk);
-    c.xin = x.get<float>(c.z);
-    const float* base = w.get<float>(c.z);
-    c.wk = base + w_off, c.bias = base + b_off;
-    c.y = y + (int64_t)c.z * ystride;
+    c.ah = wh.get<bf16>(c.z) + w_off, c.al = wl.get<bf16>(c.z) + w_off;
+    c.bh = xh.get<bf16>(c.z), c.bl = xl.get<bf16>(c.z);
+    c.bias = w.get<float>(c.z) + b_off;
     return c;
   }
   struct Row {};
   __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
   // A unit (MN-major): one k = input feature i, 8 consecutive m = o
-  __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
+  __device__ __forceinline__ Src srcA(const Ctx& c, int k, int m, int) const {
     const bool ok = k < c.kend && m < O;
-    ld8p(c.wk + (ok ? (int64_t)k * O + m : 0), ok, xx);
+    const int64_t idx = ok ? (int64_t)k * O + m : 0;
+    return Src{c.ah + idx, c.al + idx, ok};
   }
   // B unit (K-major): row n = sample b, 8 consecutive k = i
-  __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* xx) const {
+  __device__ __forceinline__ Src srcB(const Ctx& c, int n, int k) const {
     const bool ok = n < B && k < c.kend;
-    ld8p(c.xin + (ok ? (int64_t)n * I + k : 0), ok, xx);
+    const int64_t idx = ok ? (int64_t)n * I + k : 0;
+    return Src{c.bh + idx, c.bl + idx, ok};
   }
   __device__ __forceinline__ void epi(const Ctx& c, int m, int n0, const float* v) const {
     if (m >= O) return;
@@ -448,38 +402,36 @@ struct TcFwdDenseT {
       if (n >= B) break;
       float r = v[i] + bb;
       if (relu) r = fmaxf(r, 0.f);
-      c.y[(int64_t)n * O + m] = r;
+      const int64_t o = (int64_t)c.z * ystride + (int64_t)n * O + m;
+      y[o] = r;
+      if (yh) st1_planes(yh + o, yl + o, r);
     }
   }
 };
 
-struct TcDgradDenseT {
-  static constexpr bool TILE_EPI = false;  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o];  M = I, N = B, K = O
-  const float* dy;      // [z][B][O]
+struct TcDgradDenseT {  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o];  M = I, N = B, K = O
+  static constexpr bool TILE_EPI = false;
+  const bf16 *dyh, *dyl;  // [z][B][O]
   int64_t dystride;
-  NetPtr w;
+  NetPtr wh, wl;
   int64_t w_off;
-  const float* xact;    // [z][B][I]
+  const float* xact;      // [z][B][I]
   float* dx;
+  bf16 *dxh, *dxl;
   int64_t xstride;
   int I, O, B, NT, nstage;
 
   struct Ctx {
-    const TcDgradDenseT* p;
     int m0, kbeg, kend, z;
-    const float *dy, *wk, *xact;
-    float* dx;
+    const bf16 *ah, *al, *bh, *bl;
   };
   __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
     Ctx c;
-    c.p = this;
     c.z = bz;
     c.m0 = bx * 128;
     c.kbeg = 0, c.kend = O;
-    c.dy = dy + (int64_t)bz * dystride;
-    c.wk = w.get<float>(bz) + w_off;
-    c.xact = xact + (int64_t)bz * xstride;
-    c.dx = dx + (int64_t)bz * xstride;
+    c.ah = wh.get<bf16>(bz) + w_off, c.al = wl.get<bf16>(bz) + w_off;
+    c.bh = dyh + (int64_t)bz * dystride, c.bl = dyl + (int64_t)bz * dystride;
     return c;
   }
   struct Row {
@@ -487,14 +439,16 @@ struct TcDgradDenseT {
   };
   __device__ __forceinline__ Row rowA(const Ctx& c, int m) const { return Row{m, m < I}; }
   // A unit (K-major): row m = input feature i, 8 consecutive k = o
-  __device__ __forceinline__ void loadA(const Ctx& c, const Row& r, int k, float* xx) const {
+  __device__ __forceinline__ Src srcA(const Ctx& c, const Row& r, int k, int) const {
     const bool ok = r.valid && k < c.kend;
-    ld8p(c.wk + (ok ? (int64_t)r.m * O + k : 0), ok, xx);
+    const int64_t idx = ok ? (int64_t)r.m * O + k : 0;
+    return Src{c.ah + idx, c.al + idx, ok};
   }
   // B unit (K-major): row n = sample b, 8 consecutive k = o
-  __device__ __forceinline__ void loadB(const Ctx& c, int n, int k, float* xx) const {
+  __device__ __forceinline__ Src srcB(const Ctx& c, int n, int k) const {
     const bool ok = n < B && k < c.kend;
-    ld8p(c.dy + (ok ? (int64_t)n * O + k : 0), ok, xx);
+    const int64_t idx = ok ? (int64_t)n * O + k : 0;
+    return Src{c.bh + idx, c.bl + idx, ok};
   }
   __device__ __forceinline__ void epi(const Ctx& c, const Row& r, int n0, const float* v) const {
     if (!r.valid) return;
@@ -502,18 +456,22 @@ struct TcDgradDenseT {
     for (int i = 0; i < 16; ++i) {
       const int n = n0 + i;
       if (n >= B) break;
-      const int64_t idx = (int64_t)n * I + r.m;
-      c.dx[idx] = c.xact[idx] > 0.f ? v[i] : 0.f;
+      const int64_t idx = (int64_t)c.z * xstride + (int64_t)n * I + r.m;
+      const float o = xact[idx] > 0.f ? v[i] : 0.f;
+      dx[idx] = o;
+      st1_planes(dxh + idx, dxl + idx, o);
     }
   }
 };
 
-struct TcWgradDenseAdam {
-  static constexpr bool TILE_EPI = true;  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused optax.adam on W, mu, nu
-  NetPtr x;                // [z][B][I]
-  const float* dy;         // [z][B][O]
+struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused optax.adam on W, mu, nu
+  static constexpr bool TILE_EPI = true;
+  NetPtr xh, xl;           // [z][B][I] planes
+  const bf16 *dyh, *dyl;   // [z][B][O] planes
   int64_t dystride;
+  const bf16* ones;
   float *W, *mu, *nu, *grad;  // arenas (grad may be null: gradient never materialised)
+  bf16 *Wh, *Wl;              // weight planes, refreshed with the new W
   int64_t stride, w_off;
   const int32_t* count;
   float lr, b1, b2, eps;
@@ -521,33 +479,33 @@ struct TcWgradDenseAdam {
   int adam;                // 0: only write the gradient
 
   struct Ctx {
-    const TcWgradDenseAdam* p;
     int m0, n0, kbeg, kend, z;
-    const float *xin, *dy;
+    const bf16 *ah, *al, *bh, *bl;
   };
   __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
     Ctx c;
-    c.p = this;
     c.z = bz;
     c.m0 = bx * 128;
     c.n0 = by * NT;
     c.kbeg = 0, c.kend = B;
-    c.xin = x.get<float>(bz);
-    c.dy = dy + (int64_t)bz * dystride;
+    c.ah = xh.get<bf16>(bz), c.al = xl.get<bf16>(bz);
+    c.bh = dyh + (int64_t)bz * dystride, c.bl = dyl + (int64_t)bz * dystride;
     return c;
   }
   struct Row {};
   __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
   // A unit (MN-major): one k = sample b, 8 consecutive m = i; row I is the ones row (bias gradient)
-  __device__ __forceinline__ void loadA(const Ctx& c, int k, int m, float* xx) const {
+  __device__ __forceinline__ Src srcA(const Ctx& c, int k, int m, int) const {
+    if (m == I) return Src{ones, ones + 8, k < c.kend};
     const bool ok = k < c.kend && m < I;
-    ld8p(c.xin + (ok ? (int64_t)k * I + m : 0), ok, xx);
-    if (m == I && k < c.kend) xx[0] = 1.f;
+    const int64_t idx = ok ? (int64_t)k * I + m : 0;
+    return Src{c.ah + idx, c.al + idx, ok};
   }
   // B unit (MN-major): one k = sample b, 8 consecutive n = o (tile-relative n + n0)
-  __device__ __forceinline__ void loadB(const Ctx& c, int k, int n, float* xx) const {
+  __device__ __forceinline__ Src srcB(const Ctx& c, int k, int n) const {
     const bool ok = k < c.kend && c.n0 + n < O;
-    ld8p(c.dy + (ok ? (int64_t)k * O + c.n0 + n : 0), ok, xx);
+    const int64_t idx = ok ? (int64_t)k * O + c.n0 + n : 0;
+    return Src{c.bh + idx, c.bl + idx, ok};
   }
   __device__ __forceinline__ void epi(const Ctx&, int, int, const float*) const {}
   // Tile epilogue: the 128 x NT gradient tile sits in shared memory (row stride ld); the CTA walks it row-major
@@ -558,10 +516,11 @@ struct TcWgradDenseAdam {
     const int nf4 = NT >> 2;
     const int total = 128 * nf4;
     const AdamCoef ac = adam_coef(b1, b2, lr, eps, count[c.z]);
-    float* __restrict__ Wp = W + (int64_t)c.z * stride + w_off;
-    float* __restrict__ Mp = mu + (int64_t)c.z * stride + w_off;
-    float* __restrict__ Vp = nu + (int64_t)c.z * stride + w_off;
-    float* __restrict__ Gp = grad ? grad + (int64_t)c.z * stride + w_off : nullptr;
+    const int64_t hb = (int64_t)c.z * stride + w_off;
+    float* __restrict__ Wp = W + hb;
+    float* __restrict__ Mp = mu + hb;
+    float* __restrict__ Vp = nu + hb;
+    float* __restrict__ Gp = grad ? grad + hb : nullptr;
     constexpr int U = 4;
     for (int i0 = tid; i0 < total; i0 += U * nthreads) {
       float4 Pv[U], Mv[U], Vv[U], Gv[U];
@@ -595,6 +554,10 @@ struct TcWgradDenseAdam {
             *reinterpret_cast<float4*>(Wp + off[u]) = Pv[u];
             *reinterpret_cast<float4*>(Mp + off[u]) = Mv[u];
             *reinterpret_cast<float4*>(Vp + off[u]) = Vv[u];
+            uint2 h2, l2;
+            split4(Pv[u], h2, l2);
+            *reinterpret_cast<uint2*>(Wh + hb + off[u]) = h2;
+            *reinterpret_cast<uint2*>(Wl + hb + off[u]) = l2;
           }
         }
       }
@@ -610,12 +573,11 @@ struct TcWgradDenseAdam {
 // ==================================================================================================
 // the kernel
 // ==================================================================================================
-// A_MN / B_MN: operand is MN-major (loadX(ctx, k, mn8, x)) instead of K-major (loadA(ctx, row, k, x) /
-// loadB(ctx, n, k, x)).  EPI_ROW: the epilogue takes the Row context (dgrad problems).
-// 256 threads: all 8 warps gather; warp w reads TMEM lanes 32*(w%4).. and the column chunks of parity w/4.
-constexpr int NTHR = 256;
-
-template <bool A_MN, bool B_MN, int A_PLANES, bool EPI_ROW, bool SPLITK, class P>
+// A_MN / B_MN: operand is MN-major (srcX(ctx, k, mn8)) instead of K-major (srcA(ctx, row, k) / srcB(ctx, n, k)).
+// A_HALF: A units are two 8-byte halves (first conv layer, IC == 4).  A_PLANES == 1: the A operand is exact in
+// bf16 (uint8 frames), its lo plane is not read.  EPI_ROW: the epilogue takes the Row context (dgrad problems).
+// 256 threads: all 8 warps issue copies; warp w reads TMEM lanes 32*(w%4).. and the column chunks of parity w/4.
+template <bool A_MN, bool B_MN, int A_PLANES, bool A_HALF, bool EPI_ROW, bool SPLITK, class P>
 __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restrict__ part, int* __restrict__ tickets) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t mma_done[NS];
@@ -644,6 +606,7 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
   tcgen05_after_sync();
   const uint32_t tmem = tmem_base_s;
   const uint32_t idesc = make_idesc_bf16(128, NT, A_MN, B_MN);
+  const uint32_t smem_base = smem_u32(smem);
 
   // epilogue row context (dgrad problems) and the two gather rows of a K-major A operand
   typename P::Row rowctx;
@@ -655,14 +618,9 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
   }
 
   // Unit -> thread mapping: lanes run along the direction that is contiguous in global memory
-  //   K-major  tile [R x 32]: unit e -> kunit = e & 3, row = e >> 2          (4 lanes = 128 contiguous bytes;
-  //                                                                           smem stores: 4 wavefronts, optimal)
-  //   MN-major tile [32 x C]: unit e -> group = (e & 7) + 8 * (e >> 8), k = (e >> 3) & 31
-  //                                                                          (8 lanes = 256 contiguous bytes)
-  // Register double buffering: the loads of k-block i+1 are issued right after block i was converted and stored,
-  // so they are in flight across the barrier, the MMA issue and the next stage wait.
+  //   K-major  tile [R x 32]: unit e -> kunit = e & 3, row = e >> 2          (4 lanes = 64 contiguous bytes per plane)
+  //   MN-major tile [32 x C]: unit e -> group = (e & 7) + 8 * (e >> 8), k = (e >> 3) & 31   (8 lanes = 128 bytes)
   constexpr int MAXB = 4;  // NT <= 256 -> at most 4 B units per thread
-  float ra[2][8], rb[MAXB][8];
   uint32_t offa[2], offb[MAXB];
   bool actb[MAXB];
   const int nbu = B_MN ? ((NT + 63) / 64) * 256 : NT * 4;  // B unit slots
@@ -687,72 +645,88 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
       offb[j] = (uint32_t)(k >> 3) * ((uint32_t)NT * 16) + (uint32_t)grp * 128 + (uint32_t)(k & 7) * 16;
     }
   }
-  auto load_units = [&](int k0) {
+  // issue the cp.async copies of k-block kb into ring stage s
+  auto issue = [&](int kb, int s) {
+    const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
+    const uint32_t a_lo = a_hi + a_bytes;
+    const uint32_t b_hi = a_hi + A_PLANES * a_bytes;
+    const uint32_t b_lo = b_hi + b_bytes;
+    const int k0 = c.kbeg + kb * BK;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int e = tid + NTHR * j;
-      if constexpr (!A_MN) p.loadA(c, rowg[j], k0 + 8 * (e & 3), ra[j]);
-      else p.loadA(c, k0 + ((e >> 3) & 31), c.m0 + 8 * ((e & 7) + 8 * (e >> 8)), ra[j]);
+      if constexpr (A_HALF) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          Src s2;
+          if constexpr (!A_MN) s2 = p.srcA(c, rowg[j], k0 + 8 * (e & 3), h);
+          else s2 = p.srcA(c, k0 + ((e >> 3) & 31), c.m0 + 8 * ((e & 7) + 8 * (e >> 8)), h);
+          cp_async8(a_hi + offa[j] + 8 * h, s2.hi, s2.ok);
+          if constexpr (A_PLANES == 2) cp_async8(a_lo + offa[j] + 8 * h, s2.lo, s2.ok);
+        }
+      } else {
+        Src s2;
+        if constexpr (!A_MN) s2 = p.srcA(c, rowg[j], k0 + 8 * (e & 3), 0);
+        else s2 = p.srcA(c, k0 + ((e >> 3) & 31), c.m0 + 8 * ((e & 7) + 8 * (e >> 8)), 0);
+        cp_async16(a_hi + offa[j], s2.hi, s2.ok);
+        if constexpr (A_PLANES == 2) cp_async16(a_lo + offa[j], s2.lo, s2.ok);
+      }
     }
 #pragma unroll
     for (int j = 0; j < MAXB; ++j) {
       const int e = tid + NTHR * j;
-      if (j * NTHR < nbu) {  // uniform
-        if constexpr (!B_MN) p.loadB(c, actb[j] ? (e >> 2) : NT, k0 + 8 * (e & 3), rb[j]);
-        else p.loadB(c, actb[j] ? k0 + ((e >> 3) & 31) : c.kend, 8 * ((e & 7) + 8 * (e >> 8)), rb[j]);
+      if (j * NTHR < nbu && actb[j]) {
+        Src s2;
+        if constexpr (!B_MN) s2 = p.srcB(c, e >> 2, k0 + 8 * (e & 3));
+        else s2 = p.srcB(c, k0 + ((e >> 3) & 31), 8 * ((e & 7) + 8 * (e >> 8)));
+        cp_async16(b_hi + offb[j], s2.hi, s2.ok);
+        cp_async16(b_lo + offb[j], s2.lo, s2.ok);
       }
     }
   };
 
   const int nkb = c.kend > c.kbeg ? (c.kend - c.kbeg + BK - 1) / BK : 0;
-  if (nkb > 0) load_units(c.kbeg);
+  // prologue: fill nst-1 stages (one commit group per k-block, possibly empty, so the group count is uniform)
+  for (int kb = 0; kb < nst - 1; ++kb) {
+    if (kb < nkb) issue(kb, kb);
+    cp_async_commit();
+  }
   for (int it = 0; it < nkb; ++it) {
     const int s = it % nst;
-    if (it >= nst) mbar_wait(&mma_done[s], ((it / nst) - 1) & 1);
-    uint8_t* a_hi = smem + (size_t)s * stage_bytes;
-    uint8_t* a_lo = a_hi + a_bytes;  // only if A_PLANES == 2
-    uint8_t* b_hi = a_hi + A_PLANES * a_bytes;
-    uint8_t* b_lo = b_hi + b_bytes;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if constexpr (A_PLANES == 2) {
-        uint4 hi, lo;
-        split8(ra[j], hi, lo);
-        *reinterpret_cast<uint4*>(a_hi + offa[j]) = hi;
-        *reinterpret_cast<uint4*>(a_lo + offa[j]) = lo;
-      } else {
-        *reinterpret_cast<uint4*>(a_hi + offa[j]) = pack8_exact(ra[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < MAXB; ++j) {
-      if (j * NTHR < nbu && actb[j]) {
-        uint4 hi, lo;
-        split8(rb[j], hi, lo);
-        *reinterpret_cast<uint4*>(b_hi + offb[j]) = hi;
-        *reinterpret_cast<uint4*>(b_lo + offb[j]) = lo;
-      }
-    }
-    if (it + 1 < nkb) load_units(c.kbeg + (it + 1) * BK);  // prefetch: in flight across the barrier + MMA issue
-    fence_proxy_async_smem();
+    // this thread's copies of k-block `it` have landed once at most nst-2 younger groups are pending
+    if (nst >= 4) cp_async_wait<2>();
+    else if (nst == 3) cp_async_wait<1>();
+    else cp_async_wait<0>();
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
       tcgen05_after_sync();
+      const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
+      const uint32_t a_lo = a_hi + a_bytes;
+      const uint32_t b_hi = a_hi + A_PLANES * a_bytes;
+      const uint32_t b_lo = b_hi + b_bytes;
       const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)NT * 16;
 #pragma unroll
       for (int j = 0; j < BK / 16; ++j) {
-        const uint64_t dah = make_smem_desc(smem_u32(a_hi) + 2 * j * a_lbo, a_lbo, 128);
-        const uint64_t dbh = make_smem_desc(smem_u32(b_hi) + 2 * j * b_lbo, b_lbo, 128);
-        const uint64_t dbl = make_smem_desc(smem_u32(b_lo) + 2 * j * b_lbo, b_lbo, 128);
+        const uint64_t dah = make_smem_desc(a_hi + 2 * j * a_lbo, a_lbo, 128);
+        const uint64_t dbh = make_smem_desc(b_hi + 2 * j * b_lbo, b_lbo, 128);
+        const uint64_t dbl = make_smem_desc(b_lo + 2 * j * b_lbo, b_lbo, 128);
         mma_bf16(tmem, dah, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);
         mma_bf16(tmem, dah, dbl, idesc, 1u);
         if constexpr (A_PLANES == 2) {
-          const uint64_t dal = make_smem_desc(smem_u32(a_lo) + 2 * j * a_lbo, a_lbo, 128);
+          const uint64_t dal = make_smem_desc(a_lo + 2 * j * a_lbo, a_lbo, 128);
           mma_bf16(tmem, dal, dbh, idesc, 1u);
         }
       }
       mma_commit(&mma_done[s]);
     }
+    // refill: k-block it+nst-1 goes into the stage the MMAs of iteration it-1 were reading
+    const int nxt = it + nst - 1;
+    if (nxt < nkb) {
+      if (it >= 1) mbar_wait(&mma_done[(it - 1) % nst], ((it - 1) / nst) & 1);
+      issue(nxt, nxt % nst);
+    }
+    cp_async_commit();
   }
   if (nkb > 0) {
     const int last = nkb - 1;
@@ -840,11 +814,11 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
-template <bool A_MN, bool B_MN, int A_PLANES, bool EPI_ROW, bool SPLITK, class P>
+template <bool A_MN, bool B_MN, int A_PLANES, bool A_HALF, bool EPI_ROW, bool SPLITK, class P>
 static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tickets, cudaStream_t st) {
   size_t smem = (size_t)p.nstage * (A_PLANES * 128 * BK * 2 + 2 * (size_t)p.NT * BK * 2);
   if (P::TILE_EPI) smem = std::max(smem, (size_t)128 * (p.NT + 4) * sizeof(float));
-  auto kern = tc_gemm_kernel<A_MN, B_MN, A_PLANES, EPI_ROW, SPLITK, P>;
+  auto kern = tc_gemm_kernel<A_MN, B_MN, A_PLANES, A_HALF, EPI_ROW, SPLITK, P>;
   static bool configured = false;  // one flag per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -853,6 +827,41 @@ static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tic
   }
   kern<<<grid, NTHR, smem, st>>>(p, part, tickets);
   return cudaGetLastError();
+}
+
+// stages that keep two CTAs resident per SM
+static inline int pick_stages(int a_planes, int NT, int kblocks) {
+  const size_t stage = (size_t)a_planes * 128 * BK * 2 + 2 * (size_t)NT * BK * 2;
+  int n = NS;
+  while (n > 2 && n * stage > 100 * 1024) --n;
+  return std::max(2, std::min(n, kblocks + 1));  // the ring needs >= 2 stages
+}
+
+// ---- plane maintenance ------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) planes, 8 elements per thread
+__global__ void __launch_bounds__(256) to_planes_kernel(const float* __restrict__ src, bf16* __restrict__ hi,
+                                                        bf16* __restrict__ lo, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 h, l;
+    split8(x, h, l);
+    reinterpret_cast<uint4*>(hi)[i] = h;
+    reinterpret_cast<uint4*>(lo)[i] = l;
+  }
+}
+// uint8 frames -> hi plane (exact), 8 pixels per thread
+__global__ void __launch_bounds__(256) u8_to_plane_kernel(const uint8_t* __restrict__ src, bf16* __restrict__ hi,
+                                                          int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src) + i);
+    const uint32_t w[2] = {raw.x, raw.y};
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+    reinterpret_cast<uint4*>(hi)[i] = pack8_exact(x);
+  }
 }
 
 }  // namespace tcg

@@ -147,6 +147,7 @@ struct HeadArgs {
   float gamma_n;
   float* grad;   // arena
   float* dhid;   // [K][dstride] gradient w.r.t. the hidden activations (masked by relu'), may be null
+  __nv_bfloat16 *dhid_hi, *dhid_lo;  // its bf16 planes (same offsets)
   int64_t dstride;
   int relu_mask;
   float* loss;
@@ -244,6 +245,8 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const HeadArgs a) {
       float v = coef[b] * __ldg(W + act_s[b]);
       if (a.relu_mask && !(hid[(int64_t)b * H + j] > 0.f)) v = 0.f;
       dh[(int64_t)b * H + j] = v;
+      tc::st1_planes(a.dhid_hi + (int64_t)k * a.dstride + (int64_t)b * H + j,
+                     a.dhid_lo + (int64_t)k * a.dstride + (int64_t)b * H + j, v);
     }
   }
 }
@@ -253,6 +256,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const HeadArgs a) {
 // over the float4 range [off4, off4 + n4) of every head's arena
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v,
+                                                   uint2* __restrict__ ph, uint2* __restrict__ pl,
                                                    const int32_t* __restrict__ count, int64_t stride4, int64_t off4,
                                                    int64_t n4, float lr, float b1, float b2, float eps) {
   const int k = blockIdx.y;
@@ -267,6 +271,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
     p[base + i] = P;
     m[base + i] = M;
     v[base + i] = V;
+    uint2 h2, l2;
+    tc::split4(P, h2, l2);  // keep the bf16 hi/lo planes of the weights current
+    ph[base + i] = h2;
+    pl[base + i] = l2;
   }
 }
 
@@ -323,44 +331,95 @@ static int check_ws(idqn_handle* h, int64_t part, int tickets, const char* what,
   return IDQN_OK;
 }
 
+// ---- planes -----------------------------------------------------------------------------------------------
+// bf16 planes of the input batch (first layer operand of the tensor-core path); part of the captured step
+static int launch_input_planes(idqn_handle* h, int x_u8, int nsamples, int two) {
+  const int64_t n = (int64_t)nsamples * h->in_elems;
+  if (n % 8 != 0) {
+    idqn_set_error("internal: input of %lld elements is not a multiple of 8", (long long)n);
+    return IDQN_EINVAL;
+  }
+  const int64_t full = (int64_t)h->B * h->in_elems;
+  const int blocks = (int)std::min<int64_t>((n / 8 + 255) / 256, 4096);
+  for (int i = 0; i < (two ? 2 : 1); ++i) {
+    const void* src = i ? h->s2 : h->s;
+    if (x_u8)
+      tcg::u8_to_plane_kernel<<<blocks, 256, 0, h->stream>>>((const uint8_t*)src, h->in_hi + i * full, n / 8);
+    else
+      tcg::to_planes_kernel<<<blocks, 256, 0, h->stream>>>((const float*)src, h->in_hi + i * full, h->in_lo + i * full,
+                                                         n / 8);
+    CK(cudaGetLastError());
+    mark(h, "input_planes_%d", i);
+  }
+  return IDQN_OK;
+}
+
+// weights uploaded from the host: rebuild their planes (outside the captured step)
+static int refresh_planes(idqn_handle* h) {
+  for (int w = 0; w < 2; ++w) {
+    if (!h->planes_dirty[w]) continue;
+    const int64_t n8 = (int64_t)h->K * h->stride / 8;
+    const int blocks = (int)std::min<int64_t>((n8 + 255) / 256, 8192);
+    tcg::to_planes_kernel<<<blocks, 256, 0, h->stream>>>(w ? h->target : h->online, w ? h->wtg_hi : h->won_hi,
+                                                       w ? h->wtg_lo : h->won_lo, n8);
+    CK(cudaGetLastError());
+    h->planes_dirty[w] = 0;
+  }
+  return IDQN_OK;
+}
+
 // ---- forward ---------------------------------------------------------------------------------------------
 // nets: total nets; groups of `nh` consecutive nets share one input (conv0: online heads share s, target heads s')
-static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples, NetPtr x, int x_u8, NetPtr w,
-                            float* y, int64_t ystride, int relu, bool dry, int64_t* ws_part, int* ws_tick) {
+// xkind: 0 = layer input is the staged batch (h->s / h->s2, planes in_hi/in_lo), 1 = previous layer's activations
+struct FwdIO {
+  NetPtr x;        // fp32 / u8 input (SIMT path)
+  NetPtr xh, xl;   // its planes (tensor-core path)
+  NetPtr w;        // fp32 arenas
+  NetPtr wh, wl;   // weight planes
+  float* y;
+  __nv_bfloat16 *yh, *yl;
+  int64_t ystride;
+};
+
+static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples, const FwdIO& io, int x_u8, int relu,
+                            bool dry, int64_t* ws_part, int* ws_tick) {
   const Layer& l = h->layers[li];
   const float scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;  // architectures/dqn.py:44
   if (use_tc(h) && tc_conv_ok(l) && nsamples * l.g.OH * l.g.OW >= 64) {
     tcg::TcFwdConv p;
     p.g = l.g, p.g.B = nsamples;
-    p.x = x, p.w = w, p.x_u8 = x_u8;
+    p.xh = io.xh, p.xl = io.xl, p.wh = io.wh, p.wl = io.wl, p.w = io.w;
     p.w_off = l.w_off, p.b_off = l.b_off;
-    p.y = y, p.ystride = ystride, p.scale = scale, p.relu = relu;
+    p.y = io.y, p.yh = io.yh, p.yl = io.yl, p.ystride = io.ystride, p.scale = scale, p.relu = relu;
     p.nh = nh;
     p.hpt = std::max(1, std::min(nh, 256 / l.g.OC));
     p.M = nsamples * l.g.OH * l.g.OW, p.K = l.g.Kd;
     p.NT = round16(p.hpt * l.g.OC);
-    p.vec = 1;
-    p.nstage = tcg::NS;
+    const int planes = (li == 0 && x_u8) ? 1 : 2;
+    p.nstage = tcg::pick_stages(planes, p.NT, (p.K + 31) / 32);
     if (dry) return IDQN_OK;
     dim3 grid((p.M + 127) / 128, (nh + p.hpt - 1) / p.hpt, nz / nh);
-    if (x_u8) CK((tcg::launch_tc<false, true, 1, false, false>(p, grid, h->part, h->tickets, h->stream)));
-    else CK((tcg::launch_tc<false, true, 2, false, false>(p, grid, h->part, h->tickets, h->stream)));
+    const bool halfu = l.g.IC == 4;
+    if (planes == 1 && halfu) CK((tcg::launch_tc<false, true, 1, true, false, false>(p, grid, h->part, h->tickets, h->stream)));
+    else if (planes == 1) CK((tcg::launch_tc<false, true, 1, false, false, false>(p, grid, h->part, h->tickets, h->stream)));
+    else if (halfu) CK((tcg::launch_tc<false, true, 2, true, false, false>(p, grid, h->part, h->tickets, h->stream)));
+    else CK((tcg::launch_tc<false, true, 2, false, false, false>(p, grid, h->part, h->tickets, h->stream)));
     mark(h, "tc_fwd_L%d", li);
     return IDQN_OK;
   }
   if (use_tc(h) && tc_dense_ok(h, l) && nsamples <= 256) {
     tcg::TcFwdDenseT p;
-    p.x = x, p.w = w;
+    p.xh = io.xh, p.xl = io.xl, p.wh = io.wh, p.wl = io.wl, p.w = io.w;
     p.w_off = l.w_off, p.b_off = l.b_off;
-    p.y = y, p.ystride = ystride, p.relu = relu;
+    p.y = io.y, p.yh = io.yh, p.yl = io.yl, p.ystride = io.ystride, p.relu = relu;
     p.I = l.g.Kd, p.O = l.g.OC, p.B = nsamples;
     p.NT = round16(nsamples);
-    p.nstage = tcg::NS;
     const int mt = (p.O + 127) / 128;
     p.S = splitk_for(mt * nz, (p.I + 31) / 32, 2 * h->sm_count);  // weight streaming: more CTAs in flight
     const int it_per = ((p.I + 31) / 32 + p.S - 1) / p.S;
     p.kchunk = it_per * 32;
     p.S = (p.I + p.kchunk - 1) / p.kchunk;
+    p.nstage = tcg::pick_stages(2, p.NT, it_per);
     const int64_t part = p.S > 1 ? (int64_t)nz * mt * p.S * p.NT * 128 : 0;
     const int tick = p.S > 1 ? nz * mt : 0;
     if (dry) {
@@ -370,20 +429,20 @@ static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples
     int rc = check_ws(h, part, tick, "tc fwd dense", li);
     if (rc) return rc;
     dim3 grid(mt, 1, nz * p.S);
-    CK((tcg::launch_tc<true, false, 2, false, true>(p, grid, h->part, h->tickets, h->stream)));
+    CK((tcg::launch_tc<true, false, 2, false, false, true>(p, grid, h->part, h->tickets, h->stream)));
     mark(h, "tc_fwd_L%d", li);
     return IDQN_OK;
   }
   FwdProb p;
   p.g = l.g;
   p.g.B = nsamples;
-  p.x = x;
+  p.x = io.x;
   p.x_u8 = x_u8;
-  p.w = w;
+  p.w = io.w;
   p.w_off = l.w_off;
   p.b_off = l.b_off;
-  p.y = y;
-  p.ystride = ystride;
+  p.y = io.y, p.yh = io.yh, p.yl = io.yl;
+  p.ystride = io.ystride;
   p.scale = scale;
   p.relu = relu;
   p.nz = nz;
@@ -408,12 +467,16 @@ static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples
 static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_t* ws_part, int* ws_tick) {
   const Layer& l = h->layers[li];
   const int K = h->K;
-  NetPtr x;
+  NetPtr x, xh, xl;
   if (li == 0) {
     x = NetPtr{h->s, h->s, 0, 0, K};
+    xh = NetPtr{h->in_hi, h->in_hi, 0, 0, K};
+    xl = NetPtr{h->in_lo, h->in_lo, 0, 0, K};
   } else {
-    const float* xin = h->act + h->layers[li - 1].act_off;
-    x = NetPtr{xin, xin, h->act_stride, h->act_stride, K};
+    const int64_t o = h->layers[li - 1].act_off;
+    x = NetPtr{h->act + o, h->act + o, h->act_stride, h->act_stride, K};
+    xh = NetPtr{h->act_hi + o, h->act_hi + o, h->act_stride, h->act_stride, K};
+    xl = NetPtr{h->act_lo + o, h->act_lo + o, h->act_stride, h->act_stride, K};
   }
   const int xu = (li == 0) ? x_u8 : 0;
   const float scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;
@@ -422,38 +485,41 @@ static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_
     // dW = x^T dy with K = batch: the tile is final after one k-block, so Adam runs in the epilogue and the
     // gradient of the (98%-of-all-parameters) Dense_0 kernel never goes to HBM
     tcg::TcWgradDenseAdam p;
-    p.x = x;
-    p.dy = h->dact + l.act_off, p.dystride = h->act_stride;
+    p.xh = xh, p.xl = xl;
+    p.dyh = h->dact_hi + l.act_off, p.dyl = h->dact_lo + l.act_off, p.dystride = h->act_stride;
+    p.ones = h->ones;
     p.W = h->online, p.mu = h->mu, p.nu = h->nu, p.grad = keep ? h->grad : nullptr;
+    p.Wh = h->won_hi, p.Wl = h->won_lo;
     p.stride = h->stride, p.w_off = l.w_off;
     p.count = h->count;
     p.lr = h->cfg.learning_rate, p.b1 = 0.9f, p.b2 = 0.999f, p.eps = h->cfg.adam_eps;
     p.I = l.g.Kd, p.O = l.g.OC, p.B = h->B;
-    p.NT = std::min(128, round16(p.O));  // 128 TMEM columns and one stage -> 4 CTAs per SM for the Adam streams
-    p.nstage = 1;
+    p.NT = std::min(128, round16(p.O));  // 128 TMEM columns -> more CTAs per SM for the Adam streams
+    p.nstage = 2;
     p.adam = 1;
     if (dry) return IDQN_OK;
     dim3 grid((p.I + 1 + 127) / 128, (p.O + p.NT - 1) / p.NT, K);
-    CK((tcg::launch_tc<true, true, 2, false, false>(p, grid, h->part, h->tickets, h->stream)));
+    CK((tcg::launch_tc<true, true, 2, false, false, false>(p, grid, h->part, h->tickets, h->stream)));
     mark(h, "tc_wgrad_adam_L%d", li);
     return IDQN_OK;
   }
   if (use_tc(h) && tc_conv_ok(l)) {
     tcg::TcWgradConv p;
     p.g = l.g;
-    p.x = x, p.x_u8 = xu;
-    p.dy = h->dact + l.act_off, p.dystride = h->act_stride;
+    p.xh = xh, p.xl = xl;
+    p.dyh = h->dact_hi + l.act_off, p.dyl = h->dact_lo + l.act_off, p.dystride = h->act_stride;
+    p.ones = h->ones;
     p.gout = h->grad, p.gstride = h->stride, p.w_off = l.w_off;
     p.scale = scale;
     p.M = l.g.Kd + 1, p.K = h->B * l.g.OH * l.g.OW;
     p.NT = round16(l.g.OC);
-    p.vec = 1;
-    p.nstage = tcg::NS;
     const int mt = (p.M + 127) / 128;
     p.S = splitk_for(mt * K, (p.K + 31) / 32, h->sm_count);
     const int it_per = ((p.K + 31) / 32 + p.S - 1) / p.S;
     p.kchunk = it_per * 32;
     p.S = (p.K + p.kchunk - 1) / p.kchunk;
+    const int planes = xu ? 1 : 2;
+    p.nstage = tcg::pick_stages(planes, p.NT, it_per);
     const int64_t part = p.S > 1 ? (int64_t)K * mt * p.S * p.NT * 128 : 0;
     const int tick = p.S > 1 ? K * mt : 0;
     if (dry) {
@@ -463,8 +529,11 @@ static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_
     int rc = check_ws(h, part, tick, "tc wgrad", li);
     if (rc) return rc;
     dim3 grid(mt, 1, K * p.S);
-    if (xu) CK((tcg::launch_tc<true, true, 1, false, true>(p, grid, h->part, h->tickets, h->stream)));
-    else CK((tcg::launch_tc<true, true, 2, false, true>(p, grid, h->part, h->tickets, h->stream)));
+    const bool halfu = l.g.IC == 4;
+    if (planes == 1 && halfu) CK((tcg::launch_tc<true, true, 1, true, false, true>(p, grid, h->part, h->tickets, h->stream)));
+    else if (planes == 1) CK((tcg::launch_tc<true, true, 1, false, false, true>(p, grid, h->part, h->tickets, h->stream)));
+    else if (halfu) CK((tcg::launch_tc<true, true, 2, true, false, true>(p, grid, h->part, h->tickets, h->stream)));
+    else CK((tcg::launch_tc<true, true, 2, false, false, true>(p, grid, h->part, h->tickets, h->stream)));
     mark(h, "tc_wgrad_L%d", li);
     return IDQN_OK;
   }
@@ -506,17 +575,19 @@ static int launch_dgrad_layer(idqn_handle* h, int li) {
     idqn_set_error("stride %d not supported in dgrad", S);
     return IDQN_EINVAL;
   }
+  const NetPtr wh{h->won_hi, h->won_hi, h->stride, h->stride, K}, wl{h->won_lo, h->won_lo, h->stride, h->stride, K};
   if (use_tc(h) && tc_dense_ok(h, l)) {
     tcg::TcDgradDenseT p;
-    p.dy = h->dact + l.act_off, p.dystride = h->act_stride;
-    p.w = NetPtr{h->online, h->online, h->stride, h->stride, K};
+    p.dyh = h->dact_hi + l.act_off, p.dyl = h->dact_lo + l.act_off, p.dystride = h->act_stride;
+    p.wh = wh, p.wl = wl;
     p.w_off = l.w_off;
-    p.xact = h->act + prev.act_off, p.dx = h->dact + prev.act_off, p.xstride = h->act_stride;
+    p.xact = h->act + prev.act_off, p.dx = h->dact + prev.act_off;
+    p.dxh = h->dact_hi + prev.act_off, p.dxl = h->dact_lo + prev.act_off, p.xstride = h->act_stride;
     p.I = l.g.Kd, p.O = l.g.OC, p.B = h->B;
     p.NT = round16(h->B);
-    p.nstage = tcg::NS;
+    p.nstage = tcg::pick_stages(2, p.NT, (p.O + 31) / 32);
     dim3 grid((p.I + 127) / 128, 1, K);
-    CK((tcg::launch_tc<false, false, 2, true, false>(p, grid, h->part, h->tickets, h->stream)));
+    CK((tcg::launch_tc<false, false, 2, false, true, false>(p, grid, h->part, h->tickets, h->stream)));
     mark(h, "tc_dgrad_L%d", li);
     return IDQN_OK;
   }
@@ -531,23 +602,23 @@ static int launch_dgrad_layer(idqn_handle* h, int li) {
   if (use_tc(h) && tc_conv_ok(l)) {
     tcg::TcDgradConv p;
     p.g = l.g;
-    p.dy = h->dact + l.act_off, p.dystride = h->act_stride;
-    p.w = NetPtr{h->online, h->online, h->stride, h->stride, K};
+    p.dyh = h->dact_hi + l.act_off, p.dyl = h->dact_lo + l.act_off, p.dystride = h->act_stride;
+    p.wh = wh, p.wl = wl;
     p.w_off = l.w_off;
-    p.xact = h->act + prev.act_off, p.dx = h->dact + prev.act_off, p.xstride = h->act_stride;
+    p.xact = h->act + prev.act_off, p.dx = h->dact + prev.act_off;
+    p.dxh = h->dact_hi + prev.act_off, p.dxl = h->dact_lo + prev.act_off, p.xstride = h->act_stride;
     p.ncls = S * S, p.JH = JH, p.JW = JW;
     p.d_jwoc = FastDiv(JW * l.g.OC);
     p.K = JH * JW * l.g.OC;
     p.NT = round16(l.g.IC);
-    p.vec = 1;
-    p.nstage = tcg::NS;
+    p.nstage = tcg::pick_stages(2, p.NT, (p.K + 31) / 32);
     for (int cl = 0; cl < p.ncls; ++cl) {
       p.cls_niy[cl] = cls_niy[cl], p.cls_nix[cl] = cls_nix[cl];
       p.cls_d_n[cl] = FastDiv(std::max(cls_niy[cl] * cls_nix[cl], 1));
       p.cls_d_nix[cl] = FastDiv(std::max(cls_nix[cl], 1));
     }
     dim3 grid((maxM + 127) / 128, 1, K * p.ncls);
-    CK((tcg::launch_tc<false, false, 2, true, false>(p, grid, h->part, h->tickets, h->stream)));
+    CK((tcg::launch_tc<false, false, 2, false, true, false>(p, grid, h->part, h->tickets, h->stream)));
     mark(h, "tc_dgrad_L%d", li);
     return IDQN_OK;
   }
@@ -559,6 +630,7 @@ static int launch_dgrad_layer(idqn_handle* h, int li) {
   p.w_off = l.w_off;
   p.xact = h->act + prev.act_off;
   p.dx = h->dact + prev.act_off;
+  p.dxh = h->dact_hi + prev.act_off, p.dxl = h->dact_lo + prev.act_off;
   p.xstride = h->act_stride;
   p.nz = K;
   p.S = 1;
@@ -585,8 +657,8 @@ static int launch_adam_range(idqn_handle* h, int64_t off, int64_t len, int tag) 
   const int bx = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)h->sm_count * 8);
   dim3 grid(std::max(bx, 1), h->K);
   adam_kernel<<<grid, 256, 0, h->stream>>>((float4*)h->online, (const float4*)h->grad, (float4*)h->mu, (float4*)h->nu,
-                                           h->count, h->stride / 4, off / 4, n4, h->cfg.learning_rate, 0.9f, 0.999f,
-                                           h->cfg.adam_eps);
+                                           (uint2*)h->won_hi, (uint2*)h->won_lo, h->count, h->stride / 4, off / 4, n4,
+                                           h->cfg.learning_rate, 0.9f, 0.999f, h->cfg.adam_eps);
   CK(cudaGetLastError());
   mark(h, "adam_%d", tag);
   return IDQN_OK;
@@ -598,20 +670,34 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
                               int* ws_tick = nullptr) {
   const int K = h->K, L = h->n_layers, B = h->B;
   h->n_launch = 0;
+  // bf16 planes of the staged batch (operand of the first layer's tensor-core kernels)
+  const bool in_planes = use_tc(h) && (tc_conv_ok(h->layers[0]) || tc_dense_ok(h, h->layers[0]));
+  if (in_planes && !dry) {
+    int rc = launch_input_planes(h, x_u8, B, 1);
+    if (rc) return rc;
+  }
   // forward of 2K nets through all hidden layers
+  const int64_t in_full = (int64_t)B * h->in_elems;
   for (int li = 0; li < L - 1; ++li) {
-    NetPtr x;
+    FwdIO io;
     int nh = 1;
     if (li == 0) {
-      x = NetPtr{h->s, h->s2, 0, 0, K};
+      io.x = NetPtr{h->s, h->s2, 0, 0, K};
+      io.xh = NetPtr{h->in_hi, h->in_hi + in_full, 0, 0, K};
+      io.xl = NetPtr{h->in_lo, h->in_lo + in_full, 0, 0, K};
       nh = K;  // all online heads read s, all target heads read s': concatenate them along N
     } else {
-      const float* xin = h->act + h->layers[li - 1].act_off;
-      x = NetPtr{xin, xin, h->act_stride, h->act_stride, 2 * K};
+      const int64_t o = h->layers[li - 1].act_off;
+      io.x = NetPtr{h->act + o, h->act + o, h->act_stride, h->act_stride, 2 * K};
+      io.xh = NetPtr{h->act_hi + o, h->act_hi + o, h->act_stride, h->act_stride, 2 * K};
+      io.xl = NetPtr{h->act_lo + o, h->act_lo + o, h->act_stride, h->act_stride, 2 * K};
     }
-    NetPtr w{h->online, h->target, h->stride, h->stride, K};
-    int rc = launch_fwd_layer(h, li, 2 * K, nh, B, x, li == 0 ? x_u8 : 0, w, h->act + h->layers[li].act_off,
-                              h->act_stride, 1, dry, ws_part, ws_tick);
+    io.w = NetPtr{h->online, h->target, h->stride, h->stride, K};
+    io.wh = NetPtr{h->won_hi, h->wtg_hi, h->stride, h->stride, K};
+    io.wl = NetPtr{h->won_lo, h->wtg_lo, h->stride, h->stride, K};
+    const int64_t o = h->layers[li].act_off;
+    io.y = h->act + o, io.yh = h->act_hi + o, io.yl = h->act_lo + o, io.ystride = h->act_stride;
+    int rc = launch_fwd_layer(h, li, 2 * K, nh, B, io, li == 0 ? x_u8 : 0, 1, dry, ws_part, ws_tick);
     if (rc) return rc;
   }
   // final layer + loss + its backward
@@ -622,11 +708,13 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
       const float* hid = h->act + h->layers[L - 2].act_off;
       a.hid = NetPtr{hid, hid, h->act_stride, h->act_stride, 2 * K};
       a.dhid = h->dact + h->layers[L - 2].act_off;
+      a.dhid_hi = h->dact_hi + h->layers[L - 2].act_off, a.dhid_lo = h->dact_lo + h->layers[L - 2].act_off;
       a.relu_mask = 1;
     } else {
       REQUIRE(!x_u8, "a network without hidden layers needs float32 inputs");
       a.hid = NetPtr{h->s, h->s2, 0, 0, K};
       a.dhid = nullptr;
+      a.dhid_hi = a.dhid_lo = nullptr;
       a.relu_mask = 0;
     }
     a.H = l.g.Kd, a.A = h->A, a.B = B, a.K = K;
@@ -680,6 +768,10 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
 
 int idqn_learn_step_resident(idqn_handle* h, int x_u8, float* losses_host) {
   x_u8 = x_u8 ? 1 : 0;
+  {
+    int rc = refresh_planes(h);
+    if (rc) return rc;
+  }
   if (h->cfg.flags & IDQN_F_NO_GRAPH) {
     int rc = enqueue_learn_step(h, x_u8);
     if (rc) return rc;
@@ -713,6 +805,10 @@ extern "C" int idqn_profile_step(idqn_handle* h, int x_u8, int max_entries, floa
   CK(cudaSetDevice(h->cfg.device));
   for (int i = 0; i <= IDQN_PROF_MAX; ++i)
     if (!h->prof_ev[i]) CK(cudaEventCreate(&h->prof_ev[i]));
+  {
+    int rc = refresh_planes(h);
+    if (rc) return rc;
+  }
   h->prof_on = 1, h->prof_n = 0;
   CK(cudaEventRecord(h->prof_ev[0], h->stream));
   int rc = enqueue_learn_step(h, x_u8 ? 1 : 0);
@@ -771,15 +867,43 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaMalloc(&h->dact, sizeof(float) * h->act_stride * K));
   CK(cudaMemsetAsync(h->dact, 0, sizeof(float) * h->act_stride * K, h->stream));
   CK(cudaMalloc(&h->q, sizeof(float) * 2 * K * B * h->A));
+  {  // bf16 hi/lo planes
+    const size_t wp = sizeof(__nv_bfloat16) * h->stride * K;
+    __nv_bfloat16** wps[4] = {&h->won_hi, &h->won_lo, &h->wtg_hi, &h->wtg_lo};
+    for (auto pp : wps) {
+      CK(cudaMalloc(pp, wp));
+      CK(cudaMemsetAsync(*pp, 0, wp, h->stream));
+    }
+    const size_t ap = sizeof(__nv_bfloat16) * h->act_stride;
+    CK(cudaMalloc(&h->act_hi, ap * 2 * K));
+    CK(cudaMalloc(&h->act_lo, ap * 2 * K));
+    CK(cudaMalloc(&h->dact_hi, ap * K));
+    CK(cudaMalloc(&h->dact_lo, ap * K));
+    CK(cudaMemsetAsync(h->act_hi, 0, ap * 2 * K, h->stream));
+    CK(cudaMemsetAsync(h->act_lo, 0, ap * 2 * K, h->stream));
+    CK(cudaMemsetAsync(h->dact_hi, 0, ap * K, h->stream));
+    CK(cudaMemsetAsync(h->dact_lo, 0, ap * K, h->stream));
+    const size_t ip = sizeof(__nv_bfloat16) * h->in_elems * B * 2;
+    CK(cudaMalloc(&h->in_hi, ip));
+    CK(cudaMalloc(&h->in_lo, ip));
+    CK(cudaMemsetAsync(h->in_hi, 0, ip, h->stream));
+    CK(cudaMemsetAsync(h->in_lo, 0, ip, h->stream));
+    CK(cudaMalloc(&h->ones, sizeof(__nv_bfloat16) * 16));
+    CK(cudaMemsetAsync(h->ones, 0, sizeof(__nv_bfloat16) * 16, h->stream));
+    const uint16_t one_bits = 0x3F80;  // bf16(1.0)
+    CK(cudaMemcpyAsync(h->ones, &one_bits, 2, cudaMemcpyHostToDevice, h->stream));
+    h->planes_dirty[0] = h->planes_dirty[1] = 0;  // all-zero weights have all-zero planes
+  }
   // split-K workspace: maximum over every launch the step (and a stand-alone apply) will make
   int64_t part = 0;
   int tickets = 0;
   rc = enqueue_learn_step(h, 0, true, &part, &tickets);
   if (rc) return rc;
   {
-    NetPtr nul{nullptr, nullptr, 0, 0, 1};
+    FwdIO nul;
+    memset(&nul, 0, sizeof(nul));
     for (int li = 0; li < h->n_layers; ++li) {
-      rc = launch_fwd_layer(h, li, 1, 1, B, nul, 0, nul, nullptr, 0, 0, true, &part, &tickets);
+      rc = launch_fwd_layer(h, li, 1, 1, B, nul, 0, 0, true, &part, &tickets);
       if (rc) return rc;
     }
   }
@@ -806,6 +930,10 @@ extern "C" int idqn_destroy(idqn_handle* h) {
   void* ptrs[] = {h->online, h->target, h->mu,     h->nu,  h->grad, h->count, h->loss, h->loss_sum, h->s,
                   h->s2,     h->action, h->reward, h->terminal, h->act,  h->dact,  h->q,    h->part,     h->tickets};
   for (void* p : ptrs)
+    if (p) cudaFree(p);
+  void* planes[] = {h->won_hi, h->won_lo, h->wtg_hi, h->wtg_lo, h->act_hi, h->act_lo,
+                    h->dact_hi, h->dact_lo, h->in_hi, h->in_lo, h->ones};
+  for (void* p : planes)
     if (p) cudaFree(p);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->h_i32) cudaFreeHost(h->h_i32);
@@ -862,6 +990,8 @@ extern "C" int idqn_upload(idqn_handle* h, int which, int head, int64_t offset, 
   CK(cudaMemcpyAsync(a + (int64_t)head * h->stride + offset, src, sizeof(float) * n, cudaMemcpyHostToDevice,
                      h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (which == IDQN_ONLINE) h->planes_dirty[0] = 1;
+  if (which == IDQN_TARGET) h->planes_dirty[1] = 1;
   return IDQN_OK;
 }
 extern "C" int idqn_download(idqn_handle* h, int which, int head, int64_t offset, float* dst, int64_t n) {
@@ -932,44 +1062,81 @@ extern "C" int idqn_read_cumulated_losses(idqn_handle* h, double* sums, int rese
   return IDQN_OK;
 }
 
+// the target events move the bf16 planes together with their fp32 masters
 extern "C" int idqn_shift_params(idqn_handle* h) {  // idqn.py:13-17
   REQUIRE(h, "null handle");
   CK(cudaSetDevice(h->cfg.device));
-  for (int k = 0; k + 1 < h->K; ++k)
-    CK(cudaMemcpyAsync(h->online + (int64_t)k * h->stride, h->online + (int64_t)(k + 1) * h->stride,
-                       sizeof(float) * h->stride, cudaMemcpyDeviceToDevice, h->stream));
+  for (int k = 0; k + 1 < h->K; ++k) {
+    const int64_t d = (int64_t)k * h->stride, s = (int64_t)(k + 1) * h->stride;
+    CK(cudaMemcpyAsync(h->online + d, h->online + s, sizeof(float) * h->stride, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->won_hi + d, h->won_hi + s, 2 * h->stride, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->won_lo + d, h->won_lo + s, 2 * h->stride, cudaMemcpyDeviceToDevice, h->stream));
+  }
   return IDQN_OK;
 }
 extern "C" int idqn_sync_target(idqn_handle* h) {  // idqn.py:20-24
   REQUIRE(h, "null handle");
   CK(cudaSetDevice(h->cfg.device));
-  if (h->K > 1)
-    CK(cudaMemcpyAsync(h->target + h->stride, h->online, sizeof(float) * h->stride * (h->K - 1),
-                       cudaMemcpyDeviceToDevice, h->stream));
+  if (h->K > 1) {
+    const int64_t n = h->stride * (h->K - 1);
+    CK(cudaMemcpyAsync(h->target + h->stride, h->online, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->wtg_hi + h->stride, h->won_hi, 2 * n, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->wtg_lo + h->stride, h->won_lo, 2 * n, cudaMemcpyDeviceToDevice, h->stream));
+  }
   return IDQN_OK;
 }
 extern "C" int idqn_copy_online_to_target(idqn_handle* h) {  // idqn.py:78, dqn.py:52
   REQUIRE(h, "null handle");
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaMemcpyAsync(h->target, h->online, sizeof(float) * h->stride * h->K, cudaMemcpyDeviceToDevice, h->stream));
+  const int64_t n = h->stride * h->K;
+  CK(cudaMemcpyAsync(h->target, h->online, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->wtg_hi, h->won_hi, 2 * n, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->wtg_lo, h->won_lo, 2 * n, cudaMemcpyDeviceToDevice, h->stream));
+  return IDQN_OK;
+}
+// planes of externally modified arenas (NCCL / peer copies into idqn_arena_ptr memory) must be rebuilt
+extern "C" int idqn_mark_planes_dirty(idqn_handle* h, int which) {
+  REQUIRE(h && (which == IDQN_ONLINE || which == IDQN_TARGET), "bad argument");
+  h->planes_dirty[which == IDQN_TARGET] = 1;
   return IDQN_OK;
 }
 
 // network.apply of one head on n <= B inputs (already staged in h->s), result in h->q[0..n*A)
 static int enqueue_apply(idqn_handle* h, int which, int head, int u8, int n) {
+  int rc = refresh_planes(h);
+  if (rc) return rc;
+  const bool tgt = which == IDQN_TARGET;
   const float* base = arena_of(h, which) + (int64_t)head * h->stride;
-  NetPtr w{base, base, 0, 0, 1};
-  for (int li = 0; li < h->n_layers; ++li) {
-    NetPtr x;
-    if (li == 0) {
-      x = NetPtr{h->s, h->s, 0, 0, 1};
-    } else {
-      const float* xin = h->act + h->layers[li - 1].act_off;
-      x = NetPtr{xin, xin, 0, 0, 1};
+  const __nv_bfloat16* bh = (tgt ? h->wtg_hi : h->won_hi) + (int64_t)head * h->stride;
+  const __nv_bfloat16* bl = (tgt ? h->wtg_lo : h->won_lo) + (int64_t)head * h->stride;
+  if (use_tc(h) && (tc_conv_ok(h->layers[0]) || tc_dense_ok(h, h->layers[0]))) {
+    if (((int64_t)n * h->in_elems) % 8 == 0) {
+      rc = launch_input_planes(h, u8, n, 0);
+      if (rc) return rc;
     }
+  }
+  for (int li = 0; li < h->n_layers; ++li) {
+    FwdIO io;
+    if (li == 0) {
+      io.x = NetPtr{h->s, h->s, 0, 0, 1};
+      io.xh = NetPtr{h->in_hi, h->in_hi, 0, 0, 1};
+      io.xl = NetPtr{h->in_lo, h->in_lo, 0, 0, 1};
+    } else {
+      const int64_t o = h->layers[li - 1].act_off;
+      io.x = NetPtr{h->act + o, h->act + o, 0, 0, 1};
+      io.xh = NetPtr{h->act_hi + o, h->act_hi + o, 0, 0, 1};
+      io.xl = NetPtr{h->act_lo + o, h->act_lo + o, 0, 0, 1};
+    }
+    io.w = NetPtr{base, base, 0, 0, 1};
+    io.wh = NetPtr{bh, bh, 0, 0, 1};
+    io.wl = NetPtr{bl, bl, 0, 0, 1};
     const bool last = li == h->n_layers - 1;
-    float* y = last ? h->q : h->act + h->layers[li].act_off;
-    int rc = launch_fwd_layer(h, li, 1, 1, n, x, li == 0 ? u8 : 0, w, y, 0, last ? 0 : 1, false, nullptr, nullptr);
+    const int64_t o = h->layers[li].act_off;
+    io.y = last ? h->q : h->act + o;
+    io.yh = last ? nullptr : h->act_hi + o;
+    io.yl = last ? nullptr : h->act_lo + o;
+    io.ystride = 0;
+    rc = launch_fwd_layer(h, li, 1, 1, n, io, li == 0 ? u8 : 0, last ? 0 : 1, false, nullptr, nullptr);
     if (rc) return rc;
   }
   return IDQN_OK;

@@ -142,6 +142,20 @@ __device__ __forceinline__ uint4 pack8_exact(const float* x) {  // values exactl
   return make_uint4(h[0], h[1], h[2], h[3]);
 }
 
+__device__ __forceinline__ void split4(const float4& x, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+  const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&h0), b1 = *reinterpret_cast<const uint32_t*>(&h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(x.x - __uint_as_float(b0 << 16), x.y - __uint_as_float(b0 & 0xffff0000u));
+  const __nv_bfloat162 l1 = __floats2bfloat162_rn(x.z - __uint_as_float(b1 << 16), x.w - __uint_as_float(b1 & 0xffff0000u));
+  hi = make_uint2(b0, b1);
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+__device__ __forceinline__ void st1_planes(__nv_bfloat16* hi, __nv_bfloat16* lo, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *hi = h;
+  *lo = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // optax.scale_by_adam + scale(-lr) on one element with MUFU-approximate sqrt/divide (relative error ~2^-22,
 // far inside the 1e-4 parity bar; the IEEE versions cost >100 instructions per element)
 struct AdamCoef {

@@ -284,5 +284,9 @@ class Engine:
         L.check(self.lib.idqn_best_action(self.h, which, head, L.ptr(x), int(u8), C.byref(out)))
         return int(out.value)
 
+    def mark_planes_dirty(self, which: int) -> None:
+        """An arena was written through its raw pointer (NCCL recv / peer copy): rebuild its bf16 operand planes."""
+        L.check(self.lib.idqn_mark_planes_dirty(self.h, which))
+
     def arena_ptr(self, which: int) -> int:
         return int(self.lib.idqn_arena_ptr(self.h, which))

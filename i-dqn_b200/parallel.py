@@ -132,6 +132,7 @@ def make_sharded_idqn(key, observation_dim, n_actions, n_networks_total: int, fe
                 eng.copy_online_to_target()
                 with torch.cuda.stream(self._stream):
                     exchange_for_shift(self._online, rank, parts, dist, group)
+                eng.mark_planes_dirty(L.ONLINE)  # the arena was rewritten behind the library's back
                 cumulated = eng.cumulated_losses(reset=True)
                 denom = self.target_update_frequency / self.update_to_data
                 logs = {"loss": np.mean(cumulated) / denom}
@@ -141,6 +142,7 @@ def make_sharded_idqn(key, observation_dim, n_actions, n_networks_total: int, fe
             if step % self.target_sync_frequency == 0:
                 with torch.cuda.stream(self._stream):
                     exchange_for_sync(self._online, self._target, rank, parts, dist, group)
+                eng.mark_planes_dirty(L.TARGET)
             return False, {}
 
     torch.cuda.set_device(device)

@@ -91,6 +91,9 @@ int idqn_set_count(idqn_handle* h, const int32_t* count_host);  /* ScaleByAdamSt
 int idqn_get_count(idqn_handle* h, int32_t* count_host);
 /* raw device pointer of an arena ([K][stride] floats) for zero-copy interop (NCCL / peer copies) */
 void* idqn_arena_ptr(idqn_handle* h, int which);
+/* after writing an online/target arena through idqn_arena_ptr (NCCL recv, peer copy): its bf16 operand planes are
+ * rebuilt before the next step */
+int idqn_mark_planes_dirty(idqn_handle* h, int which);
 void* idqn_stream(idqn_handle* h);
 
 /* iDQN.learn_on_batch (idqn.py:96-109) / DQN.learn_on_batch (dqn.py:60-72) on the handle's resident state:
