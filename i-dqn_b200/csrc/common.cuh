@@ -1,5 +1,6 @@
 // Shared declarations of libidqn_b200 (internal; the public surface is include/idqn_b200.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -79,6 +80,16 @@ struct Layer {
 
 #define IDQN_MAX_LAYERS (IDQN_MAX_FEATURES + 1)
 #define IDQN_PROF_MAX 64
+#define IDQN_IMG_LAYERS 3
+
+// per conv layer state of the image-resident tensor-core path (conv_img.cuh): space-to-depth activation planes
+// X2 (input of the layer), zero-embedded output-gradient planes dyZ, and the TMA tensor maps over them
+struct ImgLayerState {
+  alignas(64) CUtensorMap mapX[2], mapW[2], mapZ[2];  // hi, lo
+  __nv_bfloat16 *x2_hi, *x2_lo;   // [nets][B][XRa][C2]  (layer 0: nets = 2 inputs; else 2K nets)
+  __nv_bfloat16 *dz_hi, *dz_lo;   // [K][B][ZRa][OC]
+  int64_t x2_net_stride, dz_net_stride;  // elements
+};
 
 struct idqn_handle {
   idqn_config cfg;
@@ -110,6 +121,14 @@ struct idqn_handle {
   __nv_bfloat16 *in_hi, *in_lo;                      // [2][B*in_elems]  state, next_state
   __nv_bfloat16* ones;                               // {1,0 x7 | 0 x8}: bias-gradient row of the wgrad GEMMs
   int planes_dirty[2];                               // online / target planes stale (host upload)
+  __nv_bfloat16 *wpl_hi, *wpl_lo;                    // the allocation behind won_*/wtg_*: [2K][stride], online first
+  // image-resident conv path (conv_img.cuh); img_on == 0 -> the generic kernels of gemm_tc.cuh run instead
+  int img_on;
+  ImgLayerState il[IDQN_IMG_LAYERS];
+  void* img_host;         // ImgHost (net.cu): geometry and kernel arguments of the three conv layers
+  float* wpart;           // [K][wgroups][wspan] partial conv weight gradients in arena coordinates
+  int wgroups;
+  int64_t wspan;
   // split-K workspace
   float* part;
   int64_t part_floats;

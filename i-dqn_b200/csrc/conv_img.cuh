@@ -1,0 +1,537 @@
+// Image-resident tcgen05 convolution kernels (sm_100a): forward, data gradient and weight gradient of the
+// NatureCNN conv stack (architectures/dqn.py:42-52 of the reference) for batch-32 i-DQN steps.
+//
+// Formulation.  A conv with kernel k, stride s (k % s == 0) and SAME low padding p is a stride-1 T x T conv
+// (T = k/s) over the space-to-depth image X2[by][bx][(ry,rx,c)] = x[s*by+ry-p][s*bx+rx-p][c] with C2 = s*s*IC
+// channels.  X2 is stored with a row pitch P = OW + 2(T-1) >= BW, so for the pitched output index m = oy*P + ox
+//        y[m] = sum_{ty,tx} X2row[m + ty*P + tx] . W2[ty,tx]            (a pure row shift per tap)
+// and one image is a [rows x C2] bf16 matrix that TMA drops into shared memory ONCE (SWIZZLE_128B, 64 channels
+// per 128-byte row); the A operand of every tap is the same shared-memory image read through a UMMA descriptor
+// whose start address is shifted by (ty*P+tx) rows (tma_core.cuh).  Outputs with ox >= OW are wrap-around garbage
+// and are dropped in the epilogue.  The same trick gives
+//   dgrad:  dX2[q] = sum_t dyZ[q + (T-1-ty)*P + (T-1-tx)] . W2[t]^T   with dyZ = dy zero-embedded at (T-1, T-1),
+//   wgrad:  dW2[t] = sum_m X2row[m + shift(t)]^T dyZ[m + (T-1)(P+1)]    (both images resident, K = pixels).
+// Weights are never re-laid out: a 4-D TMA box {OC, s*IC, s, 1} over the flax [KH][KW*IC][OC] kernel IS W2[ty,tx].
+//
+// Precision: bf16 hi/lo planes, three MMAs per product (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM
+// ("bf16x3", fp32-faithful to ~2^-17); uint8 frames are exact in bf16 (two MMAs).
+//
+// conv_taps_kernel (fwd, dgrad): persistent CTAs walk (net, image) units.  Warp roles: 0 = TMA of the image
+// (double-buffered), 1 = TMA of the per-tap weight tiles (ring), 2 = MMA issue, 3..6 = epilogue (TMEM -> bias/relu
+// or relu' -> fp32 + the bf16 planes of the consumer's layout); accumulators double-buffered in TMEM so the
+// epilogue of unit u overlaps the MMAs of unit u+1.
+// conv_wgrad_kernel: CTA = (head, image range); M tiles = tap pairs (the second 64-row group aliases the image at
+// a different row shift through LBO) plus a ones tile for the bias gradient; partial dW per CTA, reduced in a
+// fixed order by the Adam kernel (deterministic).
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "tc_core.cuh"
+#include "tma_core.cuh"
+
+namespace img {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int MAX_TAPS = 16;
+constexpr int NTHREADS = 224;  // 7 warps
+
+// one conv layer in space-to-depth form
+struct Geom {
+  int s, T, ph, pw;
+  int IC, OC, C2, halves;
+  int IH, IW, OH, OW;
+  int BH, BW, P;
+  int XR, XRa, x_chunks, x_chunk_rows;  // X2 rows per image, allocated rows (multiple of the TMA box), boxes per image
+  int ZH, ZR, ZRa, z_chunks, z_chunk_rows;
+  int Kd;
+};
+
+// where the epilogue writes bf16 planes: a consumer's X2 / dyZ / plain layout, all of the form
+//   row = (img * H2 + (y + off) / s) * P + (x + off) / s ;  col = (((y+off) % s) * s + (x+off) % s) * C + c
+struct PlaneDst {
+  bf16 *hi, *lo;
+  int64_t net_stride;   // elements between nets
+  int64_t img_rows;     // allocated rows per image
+  int s, off_y, off_x, P, C, C2;
+};
+__device__ __forceinline__ int64_t plane_index(const PlaneDst& d, int net, int im, int y, int x) {
+  const int yy = y + d.off_y, xx = x + d.off_x;
+  const int by = yy / d.s, ry = yy - by * d.s, bx = xx / d.s, rx = xx - bx * d.s;
+  return (int64_t)net * d.net_stride + ((int64_t)im * d.img_rows + (int64_t)by * d.P + bx) * d.C2 + (ry * d.s + rx) * d.C;
+}
+
+struct TapsArgs {
+  int n_units, imgs, nets_per_g, hpg, n_hg;
+  // A image
+  int a_rows_alloc, a_chunks, a_chunk_rows, a_halves, a_buf_rows;
+  // M
+  int tiles, tpp, P, M_valid, W_valid;  // tiles per image, tiles per pass, pitch, valid rows, valid columns (ox < W_valid)
+  // taps
+  int n_taps, kt;                        // kt = K=16 steps per tap
+  int a_shift[MAX_TAPS];                 // rows
+  int w_c1[MAX_TAPS], w_c2[MAX_TAPS];    // TMA coordinates (dims 1, 2) of the tap's weight box
+  // B tile
+  uint32_t b_box_bytes, b_row_bytes;     // bytes of one box (one net), bytes per row (128 or 64)
+  int N, ring;
+  // epilogue
+  int OH, OW, OC;                        // fwd: output geometry; dgrad: OC = IC of the layer (channels per pixel)
+  int s, ph, pw, IH, IW;                 // dgrad: block -> pixel mapping
+  float scale;
+  NetPtr w;                              // fp32 arenas (bias), fwd
+  int64_t b_off;
+  float* out;                            // fwd: act (+act_off); dgrad: dact of the previous layer (+act_off)
+  const float* mask;                     // dgrad: act of the previous layer (relu' mask)
+  int64_t out_net_stride;
+  PlaneDst dst;
+};
+
+__host__ __device__ inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+struct TapsSmem {
+  uint32_t a_plane_bytes, a_buf_bytes, ring_off, slot_bytes, bar_off, total;
+};
+__host__ __device__ inline TapsSmem taps_smem(const TapsArgs& p, int a_planes) {
+  TapsSmem s;
+  s.a_plane_bytes = (uint32_t)p.a_halves * p.a_buf_rows * 128;
+  s.a_buf_bytes = a_planes * s.a_plane_bytes;
+  s.ring_off = 2 * s.a_buf_bytes;
+  s.slot_bytes = round_up(2 * p.hpg * p.b_box_bytes, 1024);
+  s.bar_off = s.ring_off + p.ring * s.slot_bytes;
+  s.total = s.bar_off + 256 + 1024;  // barriers + alignment slack
+  return s;
+}
+
+// KIND 0: forward (B = weights MN-major, epilogue bias/relu); KIND 1: dgrad (B = weights K-major, epilogue relu')
+template <int KIND, int A_PLANES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                 const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+                 const TapsArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const TapsSmem L = taps_smem(p, A_PLANES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* x_full = bars;            // [2]
+  uint64_t* x_empty = bars + 2;       // [2]
+  uint64_t* acc_full = bars + 4;      // [2]
+  uint64_t* acc_empty = bars + 6;     // [2]
+  uint64_t* w_full = bars + 8;        // [ring]
+  uint64_t* w_empty = bars + 8 + 8;   // [ring]  (ring <= 8)
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int passes = (p.tiles + p.tpp - 1) / p.tpp;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.tpp * p.N) tmem_cols <<= 1;
+
+  // rows of an M tile past the image read whatever follows in shared memory (the other buffer, the ring): they only
+  // produce accumulator rows that the epilogue drops
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 1);
+      mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 4);
+    }
+    for (int i = 0; i < p.ring; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, tmem_cols);
+  fence_proxy_async_smem();
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== image producer =====
+    if (lane == 0) {
+      tma::prefetch_desc(&mapA_hi);
+      if (A_PLANES == 2) tma::prefetch_desc(&mapA_lo);
+      int i = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        const int xb = i & 1;
+        mbar_wait(&x_empty[xb], ((i >> 1) & 1) ^ 1);
+        const int gi = u / p.n_hg;  // (g, img) linear
+        const uint32_t bytes = (uint32_t)A_PLANES * p.a_halves * p.a_chunks * p.a_chunk_rows * 128;
+        tma::expect_tx(&x_full[xb], bytes);
+        const int row0 = gi * p.a_rows_alloc;
+        for (int pl = 0; pl < A_PLANES; ++pl)
+          for (int hf = 0; hf < p.a_halves; ++hf)
+            for (int ch = 0; ch < p.a_chunks; ++ch) {
+              const uint32_t dst = base + xb * L.a_buf_bytes + pl * L.a_plane_bytes + (uint32_t)hf * p.a_buf_rows * 128 +
+                                   (uint32_t)ch * p.a_chunk_rows * 128;
+              tma::load_3d(dst, pl ? &mapA_lo : &mapA_hi, &x_full[xb], 0, hf, row0 + ch * p.a_chunk_rows);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== weight-tap producer =====
+    if (lane == 0) {
+      tma::prefetch_desc(&mapW_hi);
+      tma::prefetch_desc(&mapW_lo);
+      int ws = 0;
+      uint32_t wphase = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int hg = u % p.n_hg, g = (u / p.n_hg) / p.imgs;
+        const int net0 = g * p.nets_per_g + hg * p.hpg;
+        const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
+        for (int ps = 0; ps < passes; ++ps)
+          for (int t = 0; t < p.n_taps; ++t) {
+            mbar_wait(&w_empty[ws], wphase ^ 1);
+            tma::expect_tx(&w_full[ws], 2u * nb * p.b_box_bytes);
+            const uint32_t slot = base + L.ring_off + ws * L.slot_bytes;
+            for (int j = 0; j < nb; ++j) {
+              tma::load_4d(slot + j * p.b_box_bytes, &mapW_hi, &w_full[ws], 0, p.w_c1[t], p.w_c2[t], net0 + j);
+              tma::load_4d(slot + (p.hpg + j) * p.b_box_bytes, &mapW_lo, &w_full[ws], 0, p.w_c1[t], p.w_c2[t], net0 + j);
+            }
+            if (++ws == p.ring) ws = 0, wphase ^= 1;
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.N, false, KIND == 0);
+      const uint32_t b_lt = p.b_row_bytes == 128 ? tma::LT_SW128 : tma::LT_SW64;
+      const uint32_t b_sbo = 8 * p.b_row_bytes;
+      int i = 0, ws = 0, ai = 0;
+      uint32_t wphase = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        const int xb = i & 1;
+        mbar_wait(&x_full[xb], (i >> 1) & 1);
+        const uint32_t a_hi = base + xb * L.a_buf_bytes, a_lo = a_hi + L.a_plane_bytes;
+        for (int ps = 0; ps < passes; ++ps, ++ai) {
+          const int ab = ai & 1;
+          mbar_wait(&acc_empty[ab], ((ai >> 1) & 1) ^ 1);
+          tcgen05_after_sync();
+          const int t0 = ps * p.tpp, t1 = min(p.tiles, t0 + p.tpp);
+          for (int t = 0; t < p.n_taps; ++t) {
+            mbar_wait(&w_full[ws], wphase);
+            tcgen05_after_sync();
+            const uint32_t b_hi = base + L.ring_off + ws * L.slot_bytes, b_lo = b_hi + p.hpg * p.b_box_bytes;
+            for (int tile = t0; tile < t1; ++tile) {
+              const uint32_t d = tmem + (uint32_t)(ab * p.tpp + (tile - t0)) * p.N;
+              const uint32_t arow = (uint32_t)(tile * 128 + p.a_shift[t]) * 128;
+              for (int j = 0; j < p.kt; ++j) {
+                const uint32_t aoff = (uint32_t)(j >> 2) * p.a_buf_rows * 128 + arow + (j & 3) * 32;
+                const uint32_t boff = KIND == 0 ? (uint32_t)j * 16 * p.b_row_bytes : (uint32_t)j * 32;
+                const uint64_t dah = tma::make_desc(a_hi + aoff, 16, 1024, tma::LT_SW128);
+                const uint64_t dbh = tma::make_desc(b_hi + boff, p.b_box_bytes, b_sbo, b_lt);
+                const uint64_t dbl = tma::make_desc(b_lo + boff, p.b_box_bytes, b_sbo, b_lt);
+                mma_bf16(d, dah, dbh, idesc, (t > 0 || j > 0) ? 1u : 0u);
+                mma_bf16(d, dah, dbl, idesc, 1u);
+                if (A_PLANES == 2) {
+                  const uint64_t dal = tma::make_desc(a_lo + aoff, 16, 1024, tma::LT_SW128);
+                  mma_bf16(d, dal, dbh, idesc, 1u);
+                }
+              }
+            }
+            mma_commit(&w_empty[ws]);
+            if (++ws == p.ring) ws = 0, wphase ^= 1;
+          }
+          mma_commit(&acc_full[ab]);
+        }
+        mma_commit(&x_empty[xb]);
+      }
+    }
+  } else {
+    // ===== epilogue warps 3..6: TMEM lane quadrant = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row inside the tile
+    int ai = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int hg = u % p.n_hg, gi = u / p.n_hg, g = gi / p.imgs, im = gi - g * p.imgs;
+      const int net0 = g * p.nets_per_g + hg * p.hpg;
+      const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
+      for (int ps = 0; ps < passes; ++ps, ++ai) {
+        const int ab = ai & 1;
+        mbar_wait(&acc_full[ab], (ai >> 1) & 1);
+        tcgen05_after_sync();
+        const int t0 = ps * p.tpp, t1 = min(p.tiles, t0 + p.tpp);
+        for (int tile = t0; tile < t1; ++tile) {
+          const int m = tile * 128 + r;
+          const int my = m / p.P, mx = m - my * p.P;
+          const bool rowok = m < p.M_valid && mx < p.W_valid;
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tpp + (tile - t0)) * p.N;
+          for (int c0 = 0; c0 < p.N; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + c0, v);  // warp-collective: executed by all lanes
+            if (!rowok) continue;
+            if (KIND == 0) {
+              const int hl = c0 / p.OC, oc = c0 - hl * p.OC;
+              if (hl >= nb) continue;
+              const int net = net0 + hl;
+              const float* bias = p.w.get<float>(net) + p.b_off + oc;
+              float o[16];
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + k4);
+                o[4 * k4] = fmaxf(fmaf(v[4 * k4], p.scale, bb.x), 0.f);
+                o[4 * k4 + 1] = fmaxf(fmaf(v[4 * k4 + 1], p.scale, bb.y), 0.f);
+                o[4 * k4 + 2] = fmaxf(fmaf(v[4 * k4 + 2], p.scale, bb.z), 0.f);
+                o[4 * k4 + 3] = fmaxf(fmaf(v[4 * k4 + 3], p.scale, bb.w), 0.f);
+              }
+              float* dst = p.out + (int64_t)net * p.out_net_stride + (((int64_t)im * p.OH + my) * p.OW + mx) * p.OC + oc;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                reinterpret_cast<float4*>(dst)[k4] = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
+              const int64_t pi = plane_index(p.dst, net, im, my, mx) + oc;
+              uint4 h0, l0, h1, l1;
+              split8(o, h0, l0);
+              split8(o + 8, h1, l1);
+              reinterpret_cast<uint4*>(p.dst.hi + pi)[0] = h0, reinterpret_cast<uint4*>(p.dst.hi + pi)[1] = h1;
+              reinterpret_cast<uint4*>(p.dst.lo + pi)[0] = l0, reinterpret_cast<uint4*>(p.dst.lo + pi)[1] = l1;
+            } else {
+              // row = block (my, mx) of the layer input; columns (ry, rx, c): 16 channels of one input pixel
+              const int blk = c0 / p.OC, c = c0 - blk * p.OC;
+              const int ry = blk / p.s, rx = blk - ry * p.s;
+              const int iy = my * p.s + ry - p.ph, ix = mx * p.s + rx - p.pw;
+              if ((unsigned)iy >= (unsigned)p.IH || (unsigned)ix >= (unsigned)p.IW) continue;
+              const int64_t oi = (int64_t)g * p.out_net_stride + (((int64_t)im * p.IH + iy) * p.IW + ix) * p.OC + c;
+              float o[16];
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 xa = __ldg(reinterpret_cast<const float4*>(p.mask + oi) + k4);
+                o[4 * k4] = xa.x > 0.f ? v[4 * k4] : 0.f, o[4 * k4 + 1] = xa.y > 0.f ? v[4 * k4 + 1] : 0.f;
+                o[4 * k4 + 2] = xa.z > 0.f ? v[4 * k4 + 2] : 0.f, o[4 * k4 + 3] = xa.w > 0.f ? v[4 * k4 + 3] : 0.f;
+              }
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                reinterpret_cast<float4*>(p.out + oi)[k4] = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
+              const int64_t pi = plane_index(p.dst, g, im, iy, ix) + c;
+              uint4 h0, l0, h1, l1;
+              split8(o, h0, l0);
+              split8(o + 8, h1, l1);
+              reinterpret_cast<uint4*>(p.dst.hi + pi)[0] = h0, reinterpret_cast<uint4*>(p.dst.hi + pi)[1] = h1;
+              reinterpret_cast<uint4*>(p.dst.lo + pi)[0] = l0, reinterpret_cast<uint4*>(p.dst.lo + pi)[1] = l1;
+            }
+          }
+        }
+        tcgen05_before_sync();
+        __syncwarp();
+        if (lane == 0) tma::arrive(&acc_empty[ab]);
+      }
+    }
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weight gradient.  CTA = (head z, image range); accumulators of all M tiles live in TMEM across the images.
+struct WgradArgs {
+  int heads, groups, imgs;          // grid = heads * groups; CTA handles images [gidx*ipg, min(imgs, +ipg))
+  int ipg;
+  int x_shared;                     // 1: every head reads the same X2 images (first layer: the staged batch)
+  // images
+  int x_rows_alloc, x_chunks, x_chunk_rows, x_halves, x_buf_rows;
+  int z_rows_alloc, z_chunks, z_chunk_rows, z_buf_rows;
+  uint32_t z_row_bytes;             // 128 (OC = 64) or 64 (OC = 32)
+  int z_start;                      // (T-1)(P+1): row of dyZ that pairs with X2 row 0
+  int k16;                          // K = 16 steps per image (ceil(OH*P / 16))
+  // M tiles: tile i covers two 64-row groups; group 0 at row shift sh0[i] (+ half h0[i]), group 1 at sh1 / h1
+  int n_tiles;
+  int sh0[MAX_TAPS], sh1[MAX_TAPS], hf0[MAX_TAPS], hf1[MAX_TAPS];
+  int row0[MAX_TAPS], row1[MAX_TAPS];  // arena row (of the [Kd][OC] kernel) of group 0 / group 1 row 0; -1 = unused
+  int grp_rows;                     // arena rows per 64-row group that are valid (64, or s*IC runs: see row_map)
+  int run, run_stride;              // group row j -> arena row  rowX + (j / run) * run_stride + j % run
+  int N;                            // OC
+  float scale;
+  float* part;                      // [heads][groups][span] partial gradients in arena coordinates
+  int64_t span, w_off, b_off;       // floats per partial; arena offsets of this layer's kernel / bias
+};
+struct WgradSmem {
+  uint32_t x_plane_bytes, x_bytes, z_plane_bytes, z_bytes, ones_off, bar_off, total;
+};
+__host__ __device__ inline WgradSmem wgrad_smem(const WgradArgs& p, int a_planes) {
+  WgradSmem s;
+  s.x_plane_bytes = (uint32_t)p.x_halves * p.x_buf_rows * 128;
+  s.x_bytes = a_planes * s.x_plane_bytes;
+  s.z_plane_bytes = round_up((uint32_t)p.z_buf_rows * p.z_row_bytes, 1024);
+  s.z_bytes = 2 * s.z_plane_bytes;
+  s.ones_off = s.x_bytes + s.z_bytes;
+  s.bar_off = s.ones_off + 2048;
+  s.total = s.bar_off + 64 + 1024;
+  return s;
+}
+
+template <int A_PLANES>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
+                  const __grid_constant__ CUtensorMap mapZ_hi, const __grid_constant__ CUtensorMap mapZ_lo,
+                  const WgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const WgradSmem L = wgrad_smem(p, A_PLANES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* full = bars;       // image pair landed
+  uint64_t* empty = bars + 1;  // MMAs reading the buffers complete
+  uint64_t* done = bars + 2;   // all MMAs of the CTA complete
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.x / p.groups, gidx = blockIdx.x - z * p.groups;
+  const int im0 = gidx * p.ipg, im1 = min(p.imgs, im0 + p.ipg);
+  const int ncols = (p.n_tiles + 1) * p.N;  // + bias tile
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < ncols) tmem_cols <<= 1;
+
+  for (uint32_t i = tid; i < L.bar_off / 16; i += 192) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // ones tile (MN-major SW128, 16 k-rows x 64 m): element (k, m = 0) = 1 -> accumulator row 0 = sum_k dy[k][:]
+  if (tid < 16) {
+    // row k at k*128 bytes; 16-byte chunk 0 of row k sits at chunk (0 ^ (k & 7))
+    bf16* row = reinterpret_cast<bf16*>(smem + L.ones_off + tid * 128 + ((tid & 7) << 4));
+    row[0] = __float2bfloat16(1.0f);
+  }
+  if (tid == 0) {
+    mbar_init(full, 1), mbar_init(empty, 1), mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+  fence_proxy_async_smem();
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t xs = base, zs = base + L.x_bytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma::prefetch_desc(&mapX_hi), tma::prefetch_desc(&mapZ_hi), tma::prefetch_desc(&mapZ_lo);
+      for (int im = im0, i = 0; im < im1; ++im, ++i) {
+        mbar_wait(empty, (i & 1) ^ 1);
+        const uint32_t bytes = (uint32_t)A_PLANES * p.x_halves * p.x_chunks * p.x_chunk_rows * 128 +
+                               2u * p.z_chunks * p.z_chunk_rows * p.z_row_bytes;
+        tma::expect_tx(full, bytes);
+        const int xrow = ((p.x_shared ? 0 : z) * p.imgs + im) * p.x_rows_alloc, zrow = (z * p.imgs + im) * p.z_rows_alloc;
+        for (int pl = 0; pl < A_PLANES; ++pl)
+          for (int hf = 0; hf < p.x_halves; ++hf)
+            for (int ch = 0; ch < p.x_chunks; ++ch)
+              tma::load_3d(xs + pl * L.x_plane_bytes + (uint32_t)hf * p.x_buf_rows * 128 + (uint32_t)ch * p.x_chunk_rows * 128,
+                           pl ? &mapX_lo : &mapX_hi, full, 0, hf, xrow + ch * p.x_chunk_rows);
+        for (int pl = 0; pl < 2; ++pl)
+          for (int ch = 0; ch < p.z_chunks; ++ch)
+            tma::load_3d(zs + pl * L.z_plane_bytes + (uint32_t)ch * p.z_chunk_rows * p.z_row_bytes, pl ? &mapZ_lo : &mapZ_hi,
+                         full, 0, 0, zrow + ch * p.z_chunk_rows);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.N, true, true);
+      const uint32_t z_lt = p.z_row_bytes == 128 ? tma::LT_SW128 : tma::LT_SW64;
+      const uint32_t z_sbo = 8 * p.z_row_bytes;
+      for (int im = im0, i = 0; im < im1; ++im, ++i) {
+        mbar_wait(full, i & 1);
+        tcgen05_after_sync();
+        for (int j = 0; j < p.k16; ++j) {
+          const uint32_t zoff = (uint32_t)(p.z_start + 16 * j) * p.z_row_bytes;
+          const uint64_t dzh = tma::make_desc(zs + zoff, 16, z_sbo, z_lt);
+          const uint64_t dzl = tma::make_desc(zs + L.z_plane_bytes + zoff, 16, z_sbo, z_lt);
+          const uint32_t acc = (i > 0 || j > 0) ? 1u : 0u;
+          for (int t = 0; t < p.n_tiles; ++t) {
+            const uint32_t o0 = (uint32_t)p.hf0[t] * p.x_buf_rows * 128 + (uint32_t)(p.sh0[t] + 16 * j) * 128;
+            const uint32_t o1 = (uint32_t)p.hf1[t] * p.x_buf_rows * 128 + (uint32_t)(p.sh1[t] + 16 * j) * 128;
+            const uint32_t lbo = o1 - o0;  // second 64-row M group: same image, other shift / half
+            const uint32_t d = tmem + (uint32_t)t * p.N;
+            const uint64_t dxh = tma::make_desc(xs + o0, lbo, 1024, tma::LT_SW128);
+            mma_bf16(d, dxh, dzh, idesc, acc);
+            mma_bf16(d, dxh, dzl, idesc, 1u);
+            if (A_PLANES == 2) {
+              const uint64_t dxl = tma::make_desc(xs + L.x_plane_bytes + o0, lbo, 1024, tma::LT_SW128);
+              mma_bf16(d, dxl, dzh, idesc, 1u);
+            }
+          }
+          // bias gradient: ones^T dy (lo part of dy included)
+          const uint32_t d = tmem + (uint32_t)p.n_tiles * p.N;
+          const uint64_t d1 = tma::make_desc(base + L.ones_off, 16, 1024, tma::LT_SW128);
+          mma_bf16(d, d1, dzh, idesc, acc);
+          mma_bf16(d, d1, dzl, idesc, 1u);
+        }
+        mma_commit(empty);
+      }
+      mma_commit(done);
+    }
+  }
+  // ===== epilogue: warps 2..5 (quadrant = warp % 4) write the partial gradient =====
+  if (warp >= 2) {
+    const int q = warp & 3, r = q * 32 + lane;
+    mbar_wait(done, 0);
+    tcgen05_after_sync();
+    float* part = p.part + ((int64_t)z * p.groups + gidx) * p.span;
+    for (int t = 0; t <= p.n_tiles; ++t) {
+      int64_t arow = -1;
+      float sc = p.scale;
+      if (t < p.n_tiles) {
+        const int grp = r >> 6, j = r & 63;
+        const int r0 = grp ? p.row1[t] : p.row0[t];
+        if (r0 >= 0 && j < p.grp_rows) arow = p.w_off + ((int64_t)r0 + (j / p.run) * p.run_stride + j % p.run) * p.N;
+      } else if (r == 0) {
+        arow = p.b_off, sc = 1.f;
+      }
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)t * p.N;
+      for (int c0 = 0; c0 < p.N; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (arow < 0) continue;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          reinterpret_cast<float4*>(part + arow + c0)[k4] =
+              make_float4(v[4 * k4] * sc, v[4 * k4 + 1] * sc, v[4 * k4 + 2] * sc, v[4 * k4 + 3] * sc);
+      }
+    }
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// staged batch (uint8 or fp32 NHWC) -> X2 planes of the first conv layer (space-to-depth, padded, pitched)
+struct S2dArgs {
+  const void* src[2];  // state, next_state
+  int u8, imgs, IH, IW, IC, s, ph, pw, BH, BW, P, C2;
+  int64_t img_rows;    // allocated rows per image
+  bf16 *hi, *lo;       // [2][imgs][img_rows][C2]
+};
+__global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
+  // one thread per (g, img, by, bx, ry): s*IC contiguous output channels = s input pixels of one input row
+  const int run = a.s * a.IC;
+  const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int ry = (int)(t % a.s);
+    t /= a.s;
+    const int bx = (int)(t % a.BW);
+    t /= a.BW;
+    const int by = (int)(t % a.BH);
+    t /= a.BH;
+    const int im = (int)(t % a.imgs), g = (int)(t / a.imgs);
+    const int iy = by * a.s + ry - a.ph;
+    const int64_t o = (((int64_t)g * a.imgs + im) * a.img_rows + (int64_t)by * a.P + bx) * a.C2 + (int64_t)ry * run;
+    for (int e = 0; e < run; e += 8) {
+      float x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ee = e + k, rx = ee / a.IC, c = ee - rx * a.IC;
+        const int ix = bx * a.s + rx - a.pw;
+        float v = 0.f;
+        if ((unsigned)iy < (unsigned)a.IH && (unsigned)ix < (unsigned)a.IW) {
+          const int64_t si = (((int64_t)im * a.IH + iy) * a.IW + ix) * a.IC + c;
+          const void* src = g ? a.src[1] : a.src[0];
+          v = a.u8 ? (float)__ldg((const uint8_t*)src + si) : __ldg((const float*)src + si);
+        }
+        x[k] = v;
+      }
+      uint4 h, l;
+      split8(x, h, l);
+      *reinterpret_cast<uint4*>(a.hi + o + e) = h;
+      if (!a.u8) *reinterpret_cast<uint4*>(a.lo + o + e) = l;
+    }
+  }
+}
+
+}  // namespace img

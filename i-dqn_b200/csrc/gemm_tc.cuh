@@ -420,6 +420,10 @@ struct TcDgradDenseT {  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o]
   bf16 *dxh, *dxl;
   int64_t xstride;
   int I, O, B, NT, nstage;
+  // optional: planes go to the zero-embedded pitched layout dyZ of the preceding conv layer (conv_img.cuh):
+  // feature i = (y*zW + x)*zC + c  ->  element ((b*zRows + (y+zOff)*zP + x+zOff)*zC + c), head stride zstride
+  int zP, zW, zC, zOff;
+  int64_t zRows, zstride;
 
   struct Ctx {
     int m0, kbeg, kend, z;
@@ -452,6 +456,11 @@ struct TcDgradDenseT {  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o]
   }
   __device__ __forceinline__ void epi(const Ctx& c, const Row& r, int n0, const float* v) const {
     if (!r.valid) return;
+    int64_t zrow = 0;
+    if (zP > 0) {
+      const int pix = r.m / zC, ch = r.m - pix * zC, y = pix / zW, x = pix - y * zW;
+      zrow = (int64_t)c.z * zstride + ((int64_t)(y + zOff) * zP + x + zOff) * zC + ch;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int n = n0 + i;
@@ -459,7 +468,8 @@ struct TcDgradDenseT {  // dx[z][b][i] = relu'(x[b][i]) * sum_o dy[b][o] W[i][o]
       const int64_t idx = (int64_t)c.z * xstride + (int64_t)n * I + r.m;
       const float o = xact[idx] > 0.f ? v[i] : 0.f;
       dx[idx] = o;
-      st1_planes(dxh + idx, dxl + idx, o);
+      const int64_t pi = zP > 0 ? zrow + (int64_t)n * zRows * zC : idx;
+      st1_planes(dxh + pi, dxl + pi, o);
     }
   }
 };

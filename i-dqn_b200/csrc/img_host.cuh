@@ -1,0 +1,330 @@
+// Host side of the image-resident conv path (conv_img.cuh): geometry, buffers, TMA tensor maps, kernel arguments
+// and launches.  Included by net.cu (uses its mark() / CK helpers).
+#pragma once
+#include "conv_img.cuh"
+
+struct ImgHost {
+  img::Geom g[IDQN_IMG_LAYERS];
+  img::TapsArgs fwd[IDQN_IMG_LAYERS], dg[IDQN_IMG_LAYERS];
+  img::WgradArgs wg[IDQN_IMG_LAYERS];
+  img::S2dArgs s2d;
+  int x0_lo_ready;  // layer-0 lo plane written (float inputs)
+};
+
+static int img_chunks(int rows, int* chunk_rows, int* rows_alloc) {
+  const int n = (rows + 255) / 256;
+  int cr = ((rows + n - 1) / n + 7) / 8 * 8;
+  *chunk_rows = cr;
+  *rows_alloc = cr * n;
+  return n;
+}
+
+static bool img_geom(const Layer& l, int layer_index, img::Geom& g) {
+  const ConvGeom& c = l.g;
+  if (!l.is_conv || c.KH != c.KW || c.S < 1 || c.KH % c.S) return false;
+  g.s = c.S, g.T = c.KH / c.S, g.ph = c.PH, g.pw = c.PW;
+  g.IC = c.IC, g.OC = c.OC, g.C2 = c.S * c.S * c.IC;
+  if (g.C2 != 64 && g.C2 != 128) return false;
+  if (g.OC != 32 && g.OC != 64) return false;
+  if (layer_index > 0 && (g.OC != 64 || g.IC % 16)) return false;  // dgrad: 128-byte dy rows, 16-channel chunks
+  const int run = c.S * c.IC;
+  if (run > 64 || 64 % run) return false;
+  if (g.T * g.T > img::MAX_TAPS) return false;
+  g.halves = g.C2 / 64;
+  g.IH = c.IH, g.IW = c.IW, g.OH = c.OH, g.OW = c.OW;
+  g.BH = c.OH + g.T - 1, g.BW = c.OW + g.T - 1, g.P = c.OW + 2 * (g.T - 1);
+  if ((c.IH - 1 + c.PH) / c.S >= g.BH || (c.IW - 1 + c.PW) / c.S >= g.BW) return false;
+  g.XR = g.BH * g.P;
+  g.x_chunks = img_chunks(g.XR, &g.x_chunk_rows, &g.XRa);
+  g.ZH = c.OH + 2 * (g.T - 1), g.ZR = g.ZH * g.P;
+  g.z_chunks = img_chunks(g.ZR, &g.z_chunk_rows, &g.ZRa);
+  g.Kd = c.Kd;
+  return true;
+}
+
+static const size_t IMG_SMEM_MAX = 227 * 1024;
+
+// decide whether the handle can run the image path and build everything it needs
+static int img_setup(idqn_handle* h) {
+  h->img_on = 0;
+  const idqn_config& c = h->cfg;
+  if (c.arch != IDQN_ARCH_CNN || (c.flags & (IDQN_F_SIMT_ONLY | IDQN_F_NO_IMG))) return IDQN_OK;
+  if (h->n_layers < IDQN_IMG_LAYERS + 2 || !tma::encode_fn()) return IDQN_OK;
+  ImgHost* H = new ImgHost();
+  memset(H, 0, sizeof(*H));
+  for (int li = 0; li < IDQN_IMG_LAYERS; ++li)
+    if (!img_geom(h->layers[li], li, H->g[li])) {
+      delete H;
+      return IDQN_OK;
+    }
+  for (int li = 1; li < IDQN_IMG_LAYERS; ++li)
+    if (H->g[li].IC != H->g[li - 1].OC) {
+      delete H;
+      return IDQN_OK;
+    }
+  const Layer& dense = h->layers[IDQN_IMG_LAYERS];
+  if (dense.is_conv || !tc_dense_ok(h, dense)) {
+    delete H;
+    return IDQN_OK;
+  }
+  const int K = h->K, B = h->B;
+  h->img_host = H;
+  // ---- buffers (zero-initialised once: padding positions are never written afterwards) ----
+  for (int li = 0; li < IDQN_IMG_LAYERS; ++li) {
+    const img::Geom& g = H->g[li];
+    ImgLayerState& S = h->il[li];
+    const int xnets = li == 0 ? 2 : 2 * K;
+    S.x2_net_stride = (int64_t)B * g.XRa * g.C2;
+    S.dz_net_stride = (int64_t)B * g.ZRa * g.OC;
+    const size_t xb = sizeof(__nv_bfloat16) * S.x2_net_stride * xnets, zb = sizeof(__nv_bfloat16) * S.dz_net_stride * K;
+    CK(cudaMalloc(&S.x2_hi, xb));
+    CK(cudaMalloc(&S.x2_lo, xb));
+    CK(cudaMalloc(&S.dz_hi, zb));
+    CK(cudaMalloc(&S.dz_lo, zb));
+    CK(cudaMemsetAsync(S.x2_hi, 0, xb, h->stream));
+    CK(cudaMemsetAsync(S.x2_lo, 0, xb, h->stream));
+    CK(cudaMemsetAsync(S.dz_hi, 0, zb, h->stream));
+    CK(cudaMemsetAsync(S.dz_lo, 0, zb, h->stream));
+    // ---- tensor maps ----
+    for (int pl = 0; pl < 2; ++pl) {
+      {  // X2: {64 channels, halves, rows}
+        const uint64_t dims[3] = {64, (uint64_t)g.halves, (uint64_t)xnets * B * g.XRa};
+        const uint64_t str[2] = {128, (uint64_t)g.C2 * 2};
+        const uint32_t box[3] = {64, 1, (uint32_t)g.x_chunk_rows};
+        REQUIRE(tma::encode_bf16(&S.mapX[pl], pl ? S.x2_lo : S.x2_hi, 3, dims, str, box, 128), "tensor map X2 L%d", li);
+      }
+      {  // W: flax kernel [KH][KW*IC][OC] of every net: {OC, KW*IC, KH, 2K}
+        const ConvGeom& cg = h->layers[li].g;
+        const uint64_t dims[4] = {(uint64_t)g.OC, (uint64_t)cg.KW * g.IC, (uint64_t)cg.KH, (uint64_t)2 * K};
+        const uint64_t str[3] = {(uint64_t)g.OC * 2, (uint64_t)cg.KW * g.IC * g.OC * 2, (uint64_t)h->stride * 2};
+        const uint32_t box[4] = {(uint32_t)g.OC, (uint32_t)(g.s * g.IC), (uint32_t)g.s, 1};
+        const __nv_bfloat16* wb = (pl ? h->wpl_lo : h->wpl_hi) + h->layers[li].w_off;
+        REQUIRE(tma::encode_bf16(&S.mapW[pl], wb, 4, dims, str, box, g.OC * 2), "tensor map W L%d", li);
+      }
+      {  // dyZ: {OC, 1, rows}
+        const uint64_t dims[3] = {(uint64_t)g.OC, 1, (uint64_t)K * B * g.ZRa};
+        const uint64_t str[2] = {(uint64_t)g.OC * 2, (uint64_t)g.OC * 2};
+        const uint32_t box[3] = {(uint32_t)g.OC, 1, (uint32_t)g.z_chunk_rows};
+        REQUIRE(tma::encode_bf16(&S.mapZ[pl], pl ? S.dz_lo : S.dz_hi, 3, dims, str, box, g.OC * 2), "tensor map dyZ L%d", li);
+      }
+    }
+  }
+  // ---- partial weight gradients ----
+  h->wspan = dense.w_off;  // the conv layers occupy the arena range [0, Dense_0.w_off)
+  {
+    const int want = std::max(1, h->sm_count / K);
+    const int ipg = (B + want - 1) / std::min(want, B);
+    h->wgroups = (B + ipg - 1) / ipg;
+    const size_t pb = sizeof(float) * h->wspan * h->wgroups * K;
+    CK(cudaMalloc(&h->wpart, pb));
+    CK(cudaMemsetAsync(h->wpart, 0, pb, h->stream));
+  }
+  // ---- kernel arguments ----
+  for (int li = 0; li < IDQN_IMG_LAYERS; ++li) {
+    const img::Geom& g = H->g[li];
+    const Layer& l = h->layers[li];
+    const ConvGeom& cg = l.g;
+    // forward
+    {
+      img::TapsArgs& a = H->fwd[li];
+      a.imgs = B;
+      if (li == 0) {
+        a.nets_per_g = K;
+        a.hpg = std::min(K, std::max(1, 96 / g.OC));
+        a.n_hg = (K + a.hpg - 1) / a.hpg;
+        a.n_units = 2 * B * a.n_hg;
+      } else {
+        a.nets_per_g = 1, a.hpg = 1, a.n_hg = 1, a.n_units = 2 * K * B;
+      }
+      a.a_rows_alloc = g.XRa, a.a_chunks = g.x_chunks, a.a_chunk_rows = g.x_chunk_rows, a.a_halves = g.halves;
+      a.a_buf_rows = g.XRa;
+      a.P = g.P, a.M_valid = g.OH * g.P, a.W_valid = g.OW;
+      a.tiles = (a.M_valid + 127) / 128;
+      a.N = a.hpg * g.OC;
+      a.tpp = std::max(1, std::min(a.tiles, 256 / a.N));
+      a.n_taps = g.T * g.T, a.kt = g.C2 / 16;
+      for (int ty = 0; ty < g.T; ++ty)
+        for (int tx = 0; tx < g.T; ++tx) {
+          const int t = ty * g.T + tx;
+          a.a_shift[t] = ty * g.P + tx;
+          a.w_c1[t] = g.s * tx * g.IC, a.w_c2[t] = g.s * ty;
+        }
+      a.b_box_bytes = (uint32_t)g.C2 * g.OC * 2, a.b_row_bytes = (uint32_t)g.OC * 2;
+      a.OH = g.OH, a.OW = g.OW, a.OC = g.OC;
+      a.scale = li == 0 ? 1.0f / 255.0f : 1.0f;  // architectures/dqn.py:44
+      a.w = NetPtr{h->online, h->target, h->stride, h->stride, K};
+      a.b_off = l.b_off;
+      a.out = h->act + l.act_off, a.out_net_stride = h->act_stride, a.mask = nullptr;
+      if (li + 1 < IDQN_IMG_LAYERS) {
+        const img::Geom& n = H->g[li + 1];
+        a.dst = img::PlaneDst{h->il[li + 1].x2_hi, h->il[li + 1].x2_lo, h->il[li + 1].x2_net_stride, n.XRa,
+                              n.s, n.ph, n.pw, n.P, g.OC, n.C2};
+      } else {
+        a.dst = img::PlaneDst{h->act_hi + l.act_off, h->act_lo + l.act_off, h->act_stride, (int64_t)g.OH * g.OW,
+                              1, 0, 0, g.OW, g.OC, g.OC};
+      }
+      // ring depth: what fits next to the two image buffers
+      const uint32_t slot = img::round_up(2 * a.hpg * a.b_box_bytes, 1024);
+      const uint32_t abuf2 = 2u * (li == 0 ? 1 : 2) * a.a_halves * a.a_buf_rows * 128;  // layer 0: uint8 frames, hi plane only
+      a.ring = (int)std::min<size_t>(4, (IMG_SMEM_MAX - 2048 - abuf2) / slot);
+      const int over = a.tiles * 128 + a.a_shift[a.n_taps - 1] - a.a_buf_rows;
+      if (a.ring < 2 || over * 128 > (int)(a.ring * slot)) {
+        idqn_set_error("internal: image path does not fit shared memory (fwd L%d)", li);
+        return IDQN_EINVAL;
+      }
+    }
+    // data gradient (layers >= 1)
+    if (li > 0) {
+      img::TapsArgs& a = H->dg[li];
+      const Layer& prev = h->layers[li - 1];
+      const img::Geom& pg = H->g[li - 1];
+      a.imgs = B, a.nets_per_g = 1, a.hpg = 1, a.n_hg = 1, a.n_units = K * B;
+      a.a_rows_alloc = g.ZRa, a.a_chunks = g.z_chunks, a.a_chunk_rows = g.z_chunk_rows, a.a_halves = 1;
+      a.a_buf_rows = g.ZRa;
+      a.P = g.P, a.M_valid = g.BH * g.P, a.W_valid = g.BW;
+      a.tiles = (a.M_valid + 127) / 128;
+      a.N = g.C2;
+      a.tpp = std::max(1, std::min(a.tiles, 256 / a.N));
+      a.n_taps = g.T * g.T, a.kt = g.OC / 16;
+      int shmax = 0;
+      for (int ty = 0; ty < g.T; ++ty)
+        for (int tx = 0; tx < g.T; ++tx) {
+          const int t = ty * g.T + tx;
+          a.a_shift[t] = (g.T - 1 - ty) * g.P + (g.T - 1 - tx);
+          shmax = std::max(shmax, a.a_shift[t]);
+          a.w_c1[t] = g.s * tx * g.IC, a.w_c2[t] = g.s * ty;
+        }
+      a.b_box_bytes = (uint32_t)g.C2 * g.OC * 2, a.b_row_bytes = (uint32_t)g.OC * 2;
+      a.OC = g.IC, a.s = g.s, a.ph = g.ph, a.pw = g.pw, a.IH = g.IH, a.IW = g.IW;
+      a.OH = g.OH, a.OW = g.OW;
+      a.scale = 1.f;
+      a.out = h->dact + prev.act_off, a.mask = h->act + prev.act_off, a.out_net_stride = h->act_stride;
+      a.dst = img::PlaneDst{h->il[li - 1].dz_hi, h->il[li - 1].dz_lo, h->il[li - 1].dz_net_stride, pg.ZRa,
+                            1, pg.T - 1, pg.T - 1, pg.P, pg.OC, pg.OC};
+      const uint32_t slot = img::round_up(2 * a.b_box_bytes, 1024);
+      const uint32_t abuf2 = 2u * 2 * a.a_buf_rows * 128;
+      a.ring = (int)std::min<size_t>(4, (IMG_SMEM_MAX - 2048 - abuf2) / slot);
+      const int over = a.tiles * 128 + shmax - a.a_buf_rows;
+      if (a.ring < 2 || over * 128 > (int)(a.ring * slot)) {
+        idqn_set_error("internal: image path does not fit shared memory (dgrad L%d)", li);
+        return IDQN_EINVAL;
+      }
+    }
+    // weight gradient
+    {
+      img::WgradArgs& a = H->wg[li];
+      a.heads = K, a.imgs = B;
+      a.x_shared = li == 0;
+      a.ipg = (B + h->wgroups - 1) / h->wgroups;
+      a.groups = h->wgroups;
+      a.k16 = (g.OH * g.P + 15) / 16;
+      a.z_start = (g.T - 1) * (g.P + 1);
+      const int shmax = (g.T - 1) * g.P + (g.T - 1);
+      a.x_rows_alloc = g.XRa, a.x_chunks = g.x_chunks, a.x_chunk_rows = g.x_chunk_rows, a.x_halves = g.halves;
+      a.x_buf_rows = (std::max(g.XRa, shmax + 16 * a.k16) + 7) / 8 * 8;
+      a.z_rows_alloc = g.ZRa, a.z_chunks = g.z_chunks, a.z_chunk_rows = g.z_chunk_rows;
+      a.z_buf_rows = (std::max(g.ZRa, a.z_start + 16 * a.k16) + 7) / 8 * 8;
+      a.z_row_bytes = (uint32_t)g.OC * 2;
+      // 64-row groups: (tap, c2 / 64), paired into 128-row tiles
+      const int run = g.s * g.IC, ry_per_grp = 64 / run;
+      int ng = 0, gsh[2 * img::MAX_TAPS], ghf[2 * img::MAX_TAPS], grow[2 * img::MAX_TAPS];
+      for (int ty = 0; ty < g.T; ++ty)
+        for (int tx = 0; tx < g.T; ++tx)
+          for (int gq = 0; gq < g.halves; ++gq) {
+            gsh[ng] = ty * g.P + tx, ghf[ng] = gq;
+            grow[ng] = ((g.s * ty + gq * ry_per_grp) * cg.KW + g.s * tx) * g.IC;
+            ++ng;
+          }
+      a.n_tiles = (ng + 1) / 2;
+      if (a.n_tiles > img::MAX_TAPS || (a.n_tiles + 1) * g.OC > 512) {
+        idqn_set_error("internal: wgrad L%d needs too many accumulator tiles", li);
+        return IDQN_EINVAL;
+      }
+      for (int t = 0; t < a.n_tiles; ++t) {
+        const int g0 = 2 * t, g1 = 2 * t + 1 < ng ? 2 * t + 1 : -1;
+        a.sh0[t] = gsh[g0], a.hf0[t] = ghf[g0], a.row0[t] = grow[g0];
+        a.sh1[t] = g1 >= 0 ? gsh[g1] : gsh[g0], a.hf1[t] = g1 >= 0 ? ghf[g1] : ghf[g0], a.row1[t] = g1 >= 0 ? grow[g1] : -1;
+      }
+      a.grp_rows = 64, a.run = run, a.run_stride = cg.KW * g.IC;
+      a.N = g.OC;
+      a.scale = li == 0 ? 1.0f / 255.0f : 1.0f;
+      a.part = h->wpart, a.span = h->wspan, a.w_off = l.w_off, a.b_off = l.b_off;
+    }
+  }
+  // ---- input space-to-depth ----
+  {
+    const img::Geom& g = H->g[0];
+    img::S2dArgs& a = H->s2d;
+    a.src[0] = h->s, a.src[1] = h->s2;
+    a.imgs = B, a.IH = g.IH, a.IW = g.IW, a.IC = g.IC, a.s = g.s, a.ph = g.ph, a.pw = g.pw;
+    a.BH = g.BH, a.BW = g.BW, a.P = g.P, a.C2 = g.C2, a.img_rows = g.XRa;
+    a.hi = h->il[0].x2_hi, a.lo = h->il[0].x2_lo;
+  }
+  h->img_on = 1;
+  return IDQN_OK;
+}
+
+static void img_free(idqn_handle* h) {
+  for (int li = 0; li < IDQN_IMG_LAYERS; ++li) {
+    void* ptrs[] = {h->il[li].x2_hi, h->il[li].x2_lo, h->il[li].dz_hi, h->il[li].dz_lo};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+  }
+  if (h->wpart) cudaFree(h->wpart);
+  if (h->img_host) delete (ImgHost*)h->img_host;
+}
+
+template <class Kern>
+static cudaError_t img_set_smem(Kern kern, size_t bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static int img_launch_s2d(idqn_handle* h, int x_u8) {
+  ImgHost* H = (ImgHost*)h->img_host;
+  img::S2dArgs a = H->s2d;
+  a.u8 = x_u8;
+  const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
+  img::s2d_input_kernel<<<(int)((total + 255) / 256), 256, 0, h->stream>>>(a);
+  CK(cudaGetLastError());
+  mark(h, "s2d_input_L%d", 0);
+  return IDQN_OK;
+}
+
+static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes) {
+  ImgHost* H = (ImgHost*)h->img_host;
+  const img::TapsArgs& a = dgrad ? H->dg[li] : H->fwd[li];
+  const ImgLayerState& S = h->il[li];
+  const img::TapsSmem L = img::taps_smem(a, a_planes);
+  const int grid = std::min(a.n_units, h->sm_count);
+  const CUtensorMap* mA = dgrad ? S.mapZ : S.mapX;
+#define IMG_TAPS_LAUNCH(KIND, PL)                                                                            \
+  do {                                                                                                       \
+    CK(img_set_smem(img::conv_taps_kernel<KIND, PL>, L.total));                                              \
+    img::conv_taps_kernel<KIND, PL><<<grid, img::NTHREADS, L.total, h->stream>>>(mA[0], mA[1], S.mapW[0], S.mapW[1], a); \
+  } while (0)
+  if (dgrad) IMG_TAPS_LAUNCH(1, 2);
+  else if (a_planes == 1) IMG_TAPS_LAUNCH(0, 1);
+  else IMG_TAPS_LAUNCH(0, 2);
+#undef IMG_TAPS_LAUNCH
+  CK(cudaGetLastError());
+  mark(h, dgrad ? "img_dgrad_L%d" : "img_fwd_L%d", li);
+  return IDQN_OK;
+}
+
+static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
+  ImgHost* H = (ImgHost*)h->img_host;
+  const img::WgradArgs& a = H->wg[li];
+  const ImgLayerState& S = h->il[li];
+  const img::WgradSmem L = img::wgrad_smem(a, a_planes);
+  const int grid = a.heads * a.groups;
+  if (a_planes == 1) {
+    CK(img_set_smem(img::conv_wgrad_kernel<1>, L.total));
+    img::conv_wgrad_kernel<1><<<grid, 192, L.total, h->stream>>>(S.mapX[0], S.mapX[1], S.mapZ[0], S.mapZ[1], a);
+  } else {
+    CK(img_set_smem(img::conv_wgrad_kernel<2>, L.total));
+    img::conv_wgrad_kernel<2><<<grid, 192, L.total, h->stream>>>(S.mapX[0], S.mapX[1], S.mapZ[0], S.mapZ[1], a);
+  }
+  CK(cudaGetLastError());
+  mark(h, "img_wgrad_L%d", li);
+  return IDQN_OK;
+}

@@ -254,16 +254,32 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const HeadArgs a) {
 // ------------------------------------------------------------------------------------------
 // optax.adam (scale_by_adam b1=.9 b2=.999 eps, eps_root=0; scale(-lr); apply_updates)  idqn.py:52,106-107
 // over the float4 range [off4, off4 + n4) of every head's arena
+// part != nullptr: the gradient is the sum, in a fixed order, of `groups` partial gradients laid out
+// [head][group][span] in arena coordinates (conv_wgrad_kernel); gout (optional) receives the reduced gradient
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v,
                                                    uint2* __restrict__ ph, uint2* __restrict__ pl,
                                                    const int32_t* __restrict__ count, int64_t stride4, int64_t off4,
-                                                   int64_t n4, float lr, float b1, float b2, float eps) {
+                                                   int64_t n4, float lr, float b1, float b2, float eps,
+                                                   const float4* __restrict__ part, int groups, int64_t span4,
+                                                   float4* __restrict__ gout) {
   const int k = blockIdx.y;
   const tc::AdamCoef ac = tc::adam_coef(b1, b2, lr, eps, count[k]);  // count already incremented for this step
   const int64_t base = (int64_t)k * stride4 + off4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 P = p[base + i], G = __ldcs(g + base + i), M = m[base + i], V = v[base + i];
+    float4 G;
+    if (part) {
+      G = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* src = part + (int64_t)k * groups * span4 + off4 + i;
+      for (int u = 0; u < groups; ++u) {
+        const float4 t = __ldcs(src + (int64_t)u * span4);
+        G.x += t.x, G.y += t.y, G.z += t.z, G.w += t.w;
+      }
+      if (gout) gout[base + i] = G;
+    } else {
+      G = __ldcs(g + base + i);
+    }
+    float4 P = p[base + i], M = m[base + i], V = v[base + i];
     tc::adam_elem(ac, G.x, P.x, M.x, V.x);
     tc::adam_elem(ac, G.y, P.y, M.y, V.y);
     tc::adam_elem(ac, G.z, P.z, M.z, V.z);
@@ -330,6 +346,8 @@ static int check_ws(idqn_handle* h, int64_t part, int tickets, const char* what,
   }
   return IDQN_OK;
 }
+
+#include "img_host.cuh"
 
 // ---- planes -----------------------------------------------------------------------------------------------
 // bf16 planes of the input batch (first layer operand of the tensor-core path); part of the captured step
@@ -566,7 +584,7 @@ static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_
 }
 
 // ---- data gradient: writes dact of layer li-1 ------------------------------------------------------------------
-static int launch_dgrad_layer(idqn_handle* h, int li) {
+static int launch_dgrad_layer(idqn_handle* h, int li, bool img_dst = false) {
   const Layer& l = h->layers[li];
   const Layer& prev = h->layers[li - 1];
   const int K = h->K;
@@ -584,6 +602,12 @@ static int launch_dgrad_layer(idqn_handle* h, int li) {
     p.xact = h->act + prev.act_off, p.dx = h->dact + prev.act_off;
     p.dxh = h->dact_hi + prev.act_off, p.dxl = h->dact_lo + prev.act_off, p.xstride = h->act_stride;
     p.I = l.g.Kd, p.O = l.g.OC, p.B = h->B;
+    p.zP = 0;
+    if (img_dst) {  // the preceding layer is a conv of the image path: its dy planes live in the dyZ layout
+      const img::Geom& pg = ((ImgHost*)h->img_host)->g[li - 1];
+      p.dxh = h->il[li - 1].dz_hi, p.dxl = h->il[li - 1].dz_lo;
+      p.zP = pg.P, p.zW = pg.OW, p.zC = pg.OC, p.zOff = pg.T - 1, p.zRows = pg.ZRa, p.zstride = h->il[li - 1].dz_net_stride;
+    }
     p.NT = round16(h->B);
     p.nstage = tcg::pick_stages(2, p.NT, (p.O + 31) / 32);
     dim3 grid((p.I + 127) / 128, 1, K);
@@ -651,14 +675,17 @@ static int launch_dgrad_layer(idqn_handle* h, int li) {
   return IDQN_OK;
 }
 
-static int launch_adam_range(idqn_handle* h, int64_t off, int64_t len, int tag) {
+static int launch_adam_range(idqn_handle* h, int64_t off, int64_t len, int tag, bool from_partials = false) {
   if (len <= 0) return IDQN_OK;
   const int64_t n4 = len / 4;
   const int bx = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)h->sm_count * 8);
   dim3 grid(std::max(bx, 1), h->K);
+  const bool keep = (h->cfg.flags & IDQN_F_KEEP_GRADS) != 0;
   adam_kernel<<<grid, 256, 0, h->stream>>>((float4*)h->online, (const float4*)h->grad, (float4*)h->mu, (float4*)h->nu,
                                            (uint2*)h->won_hi, (uint2*)h->won_lo, h->count, h->stride / 4, off / 4, n4,
-                                           h->cfg.learning_rate, 0.9f, 0.999f, h->cfg.adam_eps);
+                                           h->cfg.learning_rate, 0.9f, 0.999f, h->cfg.adam_eps,
+                                           from_partials ? (const float4*)h->wpart : nullptr, h->wgroups, h->wspan / 4,
+                                           (from_partials && keep) ? (float4*)h->grad : nullptr);
   CK(cudaGetLastError());
   mark(h, "adam_%d", tag);
   return IDQN_OK;
@@ -670,15 +697,25 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
                               int* ws_tick = nullptr) {
   const int K = h->K, L = h->n_layers, B = h->B;
   h->n_launch = 0;
+  // image-resident TMA conv kernels for the conv stack (uint8 frames); the generic kernels otherwise
+  const bool use_img = h->img_on && x_u8 && !dry;
+  const int n_img = use_img ? IDQN_IMG_LAYERS : 0;
   // bf16 planes of the staged batch (operand of the first layer's tensor-core kernels)
   const bool in_planes = use_tc(h) && (tc_conv_ok(h->layers[0]) || tc_dense_ok(h, h->layers[0]));
-  if (in_planes && !dry) {
+  if (use_img) {
+    int rc = img_launch_s2d(h, x_u8);
+    if (rc) return rc;
+    for (int li = 0; li < n_img; ++li) {
+      rc = img_launch_taps(h, li, false, li == 0 ? 1 : 2);
+      if (rc) return rc;
+    }
+  } else if (in_planes && !dry) {
     int rc = launch_input_planes(h, x_u8, B, 1);
     if (rc) return rc;
   }
   // forward of 2K nets through all hidden layers
   const int64_t in_full = (int64_t)B * h->in_elems;
-  for (int li = 0; li < L - 1; ++li) {
+  for (int li = n_img; li < L - 1; ++li) {
     FwdIO io;
     int nh = 1;
     if (li == 0) {
@@ -739,8 +776,15 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   int64_t fused_lo = -1, fused_hi = -1;  // arena range whose Adam update was fused into a wgrad epilogue
   for (int li = L - 2; li >= 0; --li) {
     // the dgrad of this layer reads the weights the fused wgrad+Adam kernel overwrites: dgrad first
+    if (li < n_img) {
+      int rc = li > 0 ? img_launch_taps(h, li, true, 2) : IDQN_OK;
+      if (rc) return rc;
+      rc = img_launch_wgrad(h, li, li == 0 ? 1 : 2);
+      if (rc) return rc;
+      continue;
+    }
     if (li > 0 && !dry) {
-      int rc = launch_dgrad_layer(h, li);
+      int rc = launch_dgrad_layer(h, li, li == n_img && n_img > 0);
       if (rc) return rc;
     }
     int rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
@@ -758,7 +802,7 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     if (rc) return rc;
   } else {
     const int64_t hi = (fused_hi + 3) / 4 * 4;  // layer starts are 128-byte aligned, so this stays inside the gap
-    int rc = launch_adam_range(h, 0, fused_lo, 0);
+    int rc = launch_adam_range(h, 0, fused_lo, 0, use_img && fused_lo == h->wspan);
     if (rc) return rc;
     rc = launch_adam_range(h, hi, h->stride - hi, 1);
     if (rc) return rc;
@@ -869,11 +913,13 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaMalloc(&h->q, sizeof(float) * 2 * K * B * h->A));
   {  // bf16 hi/lo planes
     const size_t wp = sizeof(__nv_bfloat16) * h->stride * K;
-    __nv_bfloat16** wps[4] = {&h->won_hi, &h->won_lo, &h->wtg_hi, &h->wtg_lo};
+    __nv_bfloat16** wps[2] = {&h->wpl_hi, &h->wpl_lo};  // [2K][stride]: online heads, then target heads
     for (auto pp : wps) {
-      CK(cudaMalloc(pp, wp));
-      CK(cudaMemsetAsync(*pp, 0, wp, h->stream));
+      CK(cudaMalloc(pp, 2 * wp));
+      CK(cudaMemsetAsync(*pp, 0, 2 * wp, h->stream));
     }
+    h->won_hi = h->wpl_hi, h->wtg_hi = h->wpl_hi + h->stride * K;
+    h->won_lo = h->wpl_lo, h->wtg_lo = h->wpl_lo + h->stride * K;
     const size_t ap = sizeof(__nv_bfloat16) * h->act_stride;
     CK(cudaMalloc(&h->act_hi, ap * 2 * K));
     CK(cudaMalloc(&h->act_lo, ap * 2 * K));
@@ -894,6 +940,8 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
     CK(cudaMemcpyAsync(h->ones, &one_bits, 2, cudaMemcpyHostToDevice, h->stream));
     h->planes_dirty[0] = h->planes_dirty[1] = 0;  // all-zero weights have all-zero planes
   }
+  rc = img_setup(h);
+  if (rc) return rc;
   // split-K workspace: maximum over every launch the step (and a stand-alone apply) will make
   int64_t part = 0;
   int tickets = 0;
@@ -931,8 +979,8 @@ extern "C" int idqn_destroy(idqn_handle* h) {
                   h->s2,     h->action, h->reward, h->terminal, h->act,  h->dact,  h->q,    h->part,     h->tickets};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  void* planes[] = {h->won_hi, h->won_lo, h->wtg_hi, h->wtg_lo, h->act_hi, h->act_lo,
-                    h->dact_hi, h->dact_lo, h->in_hi, h->in_lo, h->ones};
+  void* planes[] = {h->wpl_hi, h->wpl_lo, h->act_hi, h->act_lo, h->dact_hi, h->dact_lo, h->in_hi, h->in_lo, h->ones};
+  img_free(h);
   for (void* p : planes)
     if (p) cudaFree(p);
   if (h->h_loss) cudaFreeHost(h->h_loss);
