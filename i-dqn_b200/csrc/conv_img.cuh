@@ -36,6 +36,16 @@ typedef __nv_bfloat16 bf16;
 constexpr int MAX_TAPS = 16;
 constexpr int NTHREADS = 224;  // 7 warps
 
+// debug timeline (IDQN_TL=<kernel tag> in the environment): lane 0 of every role of CTA 0 stamps clock64 at its
+// pipeline events; read back with idqn_debug_timeline.  Costs one predictable branch when off.
+constexpr int TL_MAX = 4096;
+__device__ unsigned long long g_tl[TL_MAX];
+__device__ int g_tl_n;
+// fire-and-forget store (no atomic: a returning atomic would stall the role ~0.5 us per stamp); slot = tag
+__device__ __forceinline__ void tl_stamp(int on, int tag) {
+  if (on && blockIdx.x == 0 && tag < TL_MAX) g_tl[tag] = ((unsigned long long)clock64() << 16) | (unsigned)tag;
+}
+
 // one conv layer in space-to-depth form
 struct Geom {
   int s, T, ph, pw;
@@ -84,6 +94,7 @@ struct TapsArgs {
   const float* mask;                     // dgrad: act of the previous layer (relu' mask)
   int64_t out_net_stride;
   PlaneDst dst;
+  int debug;
 };
 
 __host__ __device__ inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
@@ -102,7 +113,10 @@ __host__ __device__ inline TapsSmem taps_smem(const TapsArgs& p, int a_planes) {
   return s;
 }
 
-// KIND 0: forward (B = weights MN-major, epilogue bias/relu); KIND 1: dgrad (B = weights K-major, epilogue relu')
+// KIND 0: forward (B = weights MN-major, epilogue bias/relu); KIND 1: dgrad (B = weights K-major, epilogue relu').
+// Split products: the hi and lo weight tiles of a tap sit next to each other in the ring slot, so ONE MMA of width
+// 2N computes A_hi*[B_hi | B_lo] (the A tile, the larger operand, is read from shared memory once for both), a
+// second MMA of width N adds A_lo*B_hi into the first N columns; the epilogue sums the two column sets.
 template <int KIND, int A_PLANES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
@@ -123,8 +137,9 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int passes = (p.tiles + p.tpp - 1) / p.tpp;
+  const int N = p.N, N2 = 2 * p.N;   // accumulator columns per tile: [0,N) hi*hi + lo*hi, [N,2N) hi*lo
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.tpp * p.N) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * p.tpp * N2) tmem_cols <<= 1;
 
   // rows of an M tile past the image read whatever follows in shared memory (the other buffer, the ring): they only
   // produce accumulator rows that the epilogue drops
@@ -142,16 +157,16 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   __syncthreads();
   tcgen05_after_sync();
   const uint32_t tmem = tmem_base_s;
+  if (tid == 0) tl_stamp(p.debug, 1);
 
   if (warp == 0) {
     // ===== image producer =====
-    if (lane == 0) {
-      tma::prefetch_desc(&mapA_hi);
-      if (A_PLANES == 2) tma::prefetch_desc(&mapA_lo);
+    if (elect_one()) {
       int i = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const int xb = i & 1;
         mbar_wait(&x_empty[xb], ((i >> 1) & 1) ^ 1);
+        tl_stamp(p.debug, 1000 + i);
         const int gi = u / p.n_hg;  // (g, img) linear
         const uint32_t bytes = (uint32_t)A_PLANES * p.a_halves * p.a_chunks * p.a_chunk_rows * 128;
         tma::expect_tx(&x_full[xb], bytes);
@@ -167,18 +182,17 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     }
   } else if (warp == 1) {
     // ===== weight-tap producer =====
-    if (lane == 0) {
-      tma::prefetch_desc(&mapW_hi);
-      tma::prefetch_desc(&mapW_lo);
-      int ws = 0;
+    if (elect_one()) {
+      int ws = 0, ui = 0;
       uint32_t wphase = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ui) {
         const int hg = u % p.n_hg, g = (u / p.n_hg) / p.imgs;
         const int net0 = g * p.nets_per_g + hg * p.hpg;
         const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
         for (int ps = 0; ps < passes; ++ps)
           for (int t = 0; t < p.n_taps; ++t) {
             mbar_wait(&w_empty[ws], wphase ^ 1);
+            tl_stamp(p.debug, 2000 + (ui * passes + ps) * 16 + t);
             tma::expect_tx(&w_full[ws], 2u * nb * p.b_box_bytes);
             const uint32_t slot = base + L.ring_off + ws * L.slot_bytes;
             for (int j = 0; j < nb; ++j) {
@@ -190,49 +204,69 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       }
     }
   } else if (warp == 2) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.N, false, KIND == 0);
+    // ===== MMA issuer: one elected lane walks the whole pipeline =====
+    if (elect_one()) {
+      const uint32_t idesc2 = make_idesc_bf16(128, N2, false, KIND == 0);  // A_hi * [B_hi | B_lo]
+      const uint32_t idesc1 = make_idesc_bf16(128, N, false, KIND == 0);   // A_lo * B_hi
       const uint32_t b_lt = p.b_row_bytes == 128 ? tma::LT_SW128 : tma::LT_SW64;
-      const uint32_t b_sbo = 8 * p.b_row_bytes;
+      const uint32_t a_hi32 = tma::desc_hi32(1024, tma::LT_SW128), b_hi32 = tma::desc_hi32(8 * p.b_row_bytes, b_lt);
+      const uint32_t half16 = (uint32_t)p.a_buf_rows * 8;                 // next 64-channel half of the image
+      const uint32_t bstep = KIND == 0 ? p.b_row_bytes : 2u;              // K = 16 step of B: 16 rows (MN-major) or 32 bytes
       int i = 0, ws = 0, ai = 0;
       uint32_t wphase = 0;
+      const bool any = blockIdx.x < p.n_units;
+      if (any) {  // waits of the very first step
+        mbar_wait(&x_full[0], 0);
+        mbar_wait(&w_full[0], 0);
+        tcgen05_after_sync();
+      }
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const int xb = i & 1;
-        mbar_wait(&x_full[xb], (i >> 1) & 1);
+        const bool last_unit = u + (int)gridDim.x >= p.n_units;
         const uint32_t a_hi = base + xb * L.a_buf_bytes, a_lo = a_hi + L.a_plane_bytes;
         for (int ps = 0; ps < passes; ++ps, ++ai) {
           const int ab = ai & 1;
-          mbar_wait(&acc_empty[ab], ((ai >> 1) & 1) ^ 1);
-          tcgen05_after_sync();
           const int t0 = ps * p.tpp, t1 = min(p.tiles, t0 + p.tpp);
           for (int t = 0; t < p.n_taps; ++t) {
-            mbar_wait(&w_full[ws], wphase);
-            tcgen05_after_sync();
-            const uint32_t b_hi = base + L.ring_off + ws * L.slot_bytes, b_lo = b_hi + p.hpg * p.b_box_bytes;
+            tl_stamp(p.debug, 3000 + ai * 32 + t);
+            const uint32_t b_hi = base + L.ring_off + ws * L.slot_bytes;
+            // descriptor low words; offsets in 16-byte units.  B: N groups at LBO = box bytes (hi boxes then lo boxes)
+            const uint32_t bh0 = tma::desc_lo32(b_hi, p.b_box_bytes);
+            const uint32_t ah0 = tma::desc_lo32(a_hi, 16) + (uint32_t)p.a_shift[t] * 8;
+            const uint32_t al0 = tma::desc_lo32(a_lo, 16) + (uint32_t)p.a_shift[t] * 8;
             for (int tile = t0; tile < t1; ++tile) {
-              const uint32_t d = tmem + (uint32_t)(ab * p.tpp + (tile - t0)) * p.N;
-              const uint32_t arow = (uint32_t)(tile * 128 + p.a_shift[t]) * 128;
-              for (int j = 0; j < p.kt; ++j) {
-                const uint32_t aoff = (uint32_t)(j >> 2) * p.a_buf_rows * 128 + arow + (j & 3) * 32;
-                const uint32_t boff = KIND == 0 ? (uint32_t)j * 16 * p.b_row_bytes : (uint32_t)j * 32;
-                const uint64_t dah = tma::make_desc(a_hi + aoff, 16, 1024, tma::LT_SW128);
-                const uint64_t dbh = tma::make_desc(b_hi + boff, p.b_box_bytes, b_sbo, b_lt);
-                const uint64_t dbl = tma::make_desc(b_lo + boff, p.b_box_bytes, b_sbo, b_lt);
-                mma_bf16(d, dah, dbh, idesc, (t > 0 || j > 0) ? 1u : 0u);
-                mma_bf16(d, dah, dbl, idesc, 1u);
-                if (A_PLANES == 2) {
-                  const uint64_t dal = tma::make_desc(a_lo + aoff, 16, 1024, tma::LT_SW128);
-                  mma_bf16(d, dal, dbh, idesc, 1u);
+              const uint32_t d = tmem + (uint32_t)(ab * p.tpp + (tile - t0)) * N2;
+              uint32_t ah = ah0 + (uint32_t)tile * 1024, al = al0 + (uint32_t)tile * 1024, bh = bh0;
+              for (int j4 = 0; j4 < p.kt; j4 += 4) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  if (t == 0 && j4 == 0 && jj == 0) tma::mma_bf16_split<false>(d, ah, a_hi32, bh, b_hi32, idesc2);
+                  else tma::mma_bf16_split<true>(d, ah + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc2);
+                  if (A_PLANES == 2) tma::mma_bf16_split<true>(d, al + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc1);
                 }
+                ah += half16, al += half16, bh += 4 * bstep;
               }
             }
             mma_commit(&w_empty[ws]);
+            const bool last_tap = t == p.n_taps - 1, last_pass = ps == passes - 1;
+            if (last_tap) {
+              mma_commit(&acc_full[ab]);
+              if (last_pass) mma_commit(&x_empty[xb]);
+            }
+            tl_stamp(p.debug, 3000 + ai * 32 + 16 + t);
             if (++ws == p.ring) ws = 0, wphase ^= 1;
+            // waits of the NEXT step, issued while the MMAs just queued drain
+            if (!(last_tap && last_pass && last_unit)) {
+              if (last_tap) {
+                const int an = ai + 1;
+                mbar_wait(&acc_empty[an & 1], ((an >> 1) & 1) ^ 1);
+                if (last_pass) mbar_wait(&x_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+              }
+              mbar_wait(&w_full[ws], wphase);
+              tcgen05_after_sync();
+            }
           }
-          mma_commit(&acc_full[ab]);
         }
-        mma_commit(&x_empty[xb]);
       }
     }
   } else {
@@ -248,16 +282,27 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         const int ab = ai & 1;
         mbar_wait(&acc_full[ab], (ai >> 1) & 1);
         tcgen05_after_sync();
+        if (warp == 3 && lane == 0) tl_stamp(p.debug, 1200 + 2 * ai);
         const int t0 = ps * p.tpp, t1 = min(p.tiles, t0 + p.tpp);
         for (int tile = t0; tile < t1; ++tile) {
           const int m = tile * 128 + r;
           const int my = m / p.P, mx = m - my * p.P;
           const bool rowok = m < p.M_valid && mx < p.W_valid;
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tpp + (tile - t0)) * p.N;
-          for (int c0 = 0; c0 < p.N; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);  // warp-collective: executed by all lanes
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tpp + (tile - t0)) * N2;
+          // per-row bases, computed once per tile
+          int64_t orow = 0, prow = 0;
+          if (KIND == 0) {
+            orow = (((int64_t)im * p.OH + my) * p.OW + mx) * p.OC;
+            prow = plane_index(p.dst, 0, im, my, mx);
+          }
+          for (int c0 = 0; c0 < N; c0 += 16) {
+            float v[16], v2[16];
+            tmem_ld16_nowait(taddr + c0, v);
+            tmem_ld16_nowait(taddr + N + c0, v2);
+            tmem_ld_wait();
             if (!rowok) continue;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += v2[e];
             if (KIND == 0) {
               const int hl = c0 / p.OC, oc = c0 - hl * p.OC;
               if (hl >= nb) continue;
@@ -272,11 +317,11 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                 o[4 * k4 + 2] = fmaxf(fmaf(v[4 * k4 + 2], p.scale, bb.z), 0.f);
                 o[4 * k4 + 3] = fmaxf(fmaf(v[4 * k4 + 3], p.scale, bb.w), 0.f);
               }
-              float* dst = p.out + (int64_t)net * p.out_net_stride + (((int64_t)im * p.OH + my) * p.OW + mx) * p.OC + oc;
+              float* dst = p.out + (int64_t)net * p.out_net_stride + orow + oc;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4)
                 reinterpret_cast<float4*>(dst)[k4] = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
-              const int64_t pi = plane_index(p.dst, net, im, my, mx) + oc;
+              const int64_t pi = (int64_t)net * p.dst.net_stride + prow + oc;
               uint4 h0, l0, h1, l1;
               split8(o, h0, l0);
               split8(o + 8, h1, l1);
@@ -310,6 +355,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         }
         tcgen05_before_sync();
         __syncwarp();
+        if (warp == 3 && lane == 0) tl_stamp(p.debug, 1201 + 2 * ai);
         if (lane == 0) tma::arrive(&acc_empty[ab]);
       }
     }
@@ -341,6 +387,7 @@ struct WgradArgs {
   float scale;
   float* part;                      // [heads][groups][span] partial gradients in arena coordinates
   int64_t span, w_off, b_off;       // floats per partial; arena offsets of this layer's kernel / bias
+  int debug;
 };
 struct WgradSmem {
   uint32_t x_plane_bytes, x_bytes, z_plane_bytes, z_bytes, ones_off, bar_off, total;
@@ -398,12 +445,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
   tcgen05_after_sync();
   const uint32_t tmem = tmem_base_s;
   const uint32_t xs = base, zs = base + L.x_bytes;
+  if (tid == 0) tl_stamp(p.debug, 1);
 
   if (warp == 0) {
-    if (lane == 0) {
-      tma::prefetch_desc(&mapX_hi), tma::prefetch_desc(&mapZ_hi), tma::prefetch_desc(&mapZ_lo);
-      for (int im = im0, i = 0; im < im1; ++im, ++i) {
-        mbar_wait(empty, (i & 1) ^ 1);
+    for (int im = im0, i = 0; im < im1; ++im, ++i) {
+      mbar_wait(empty, (i & 1) ^ 1);
+      if (elect_one()) {
+        tl_stamp(p.debug, 1000 + i);
         const uint32_t bytes = (uint32_t)A_PLANES * p.x_halves * p.x_chunks * p.x_chunk_rows * 128 +
                                2u * p.z_chunks * p.z_chunk_rows * p.z_row_bytes;
         tma::expect_tx(full, bytes);
@@ -418,42 +466,56 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
             tma::load_3d(zs + pl * L.z_plane_bytes + (uint32_t)ch * p.z_chunk_rows * p.z_row_bytes, pl ? &mapZ_lo : &mapZ_hi,
                          full, 0, 0, zrow + ch * p.z_chunk_rows);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_bf16(128, p.N, true, true);
       const uint32_t z_lt = p.z_row_bytes == 128 ? tma::LT_SW128 : tma::LT_SW64;
-      const uint32_t z_sbo = 8 * p.z_row_bytes;
+      const uint32_t x_hi32 = tma::desc_hi32(1024, tma::LT_SW128), z_hi32 = tma::desc_hi32(8 * p.z_row_bytes, z_lt);
+      // per tile: descriptor low word of the hi plane at k = 0 (start address | LBO = distance to the second M group)
+      uint32_t xlo[MAX_TAPS];
+#pragma unroll
+      for (int t = 0; t < MAX_TAPS; ++t) {
+        if (t < p.n_tiles) {
+          const uint32_t o0 = (uint32_t)p.hf0[t] * p.x_buf_rows * 128 + (uint32_t)p.sh0[t] * 128;
+          const uint32_t o1 = (uint32_t)p.hf1[t] * p.x_buf_rows * 128 + (uint32_t)p.sh1[t] * 128;
+          xlo[t] = tma::desc_lo32(xs + o0, o1 - o0);
+        }
+      }
+      const uint32_t xpl16 = L.x_plane_bytes >> 4, ones_lo = tma::desc_lo32(base + L.ones_off, 16);
+      const uint32_t zh0 = tma::desc_lo32(zs + (uint32_t)p.z_start * p.z_row_bytes, 16), zpl16 = L.z_plane_bytes >> 4;
+      const uint32_t dbias = tmem + (uint32_t)p.n_tiles * p.N;
       for (int im = im0, i = 0; im < im1; ++im, ++i) {
         mbar_wait(full, i & 1);
         tcgen05_after_sync();
+        if (elect_one()) {
+        tl_stamp(p.debug, 3000 + 2 * i);
         for (int j = 0; j < p.k16; ++j) {
-          const uint32_t zoff = (uint32_t)(p.z_start + 16 * j) * p.z_row_bytes;
-          const uint64_t dzh = tma::make_desc(zs + zoff, 16, z_sbo, z_lt);
-          const uint64_t dzl = tma::make_desc(zs + L.z_plane_bytes + zoff, 16, z_sbo, z_lt);
-          const uint32_t acc = (i > 0 || j > 0) ? 1u : 0u;
-          for (int t = 0; t < p.n_tiles; ++t) {
-            const uint32_t o0 = (uint32_t)p.hf0[t] * p.x_buf_rows * 128 + (uint32_t)(p.sh0[t] + 16 * j) * 128;
-            const uint32_t o1 = (uint32_t)p.hf1[t] * p.x_buf_rows * 128 + (uint32_t)(p.sh1[t] + 16 * j) * 128;
-            const uint32_t lbo = o1 - o0;  // second 64-row M group: same image, other shift / half
-            const uint32_t d = tmem + (uint32_t)t * p.N;
-            const uint64_t dxh = tma::make_desc(xs + o0, lbo, 1024, tma::LT_SW128);
-            mma_bf16(d, dxh, dzh, idesc, acc);
-            mma_bf16(d, dxh, dzl, idesc, 1u);
-            if (A_PLANES == 2) {
-              const uint64_t dxl = tma::make_desc(xs + L.x_plane_bytes + o0, lbo, 1024, tma::LT_SW128);
-              mma_bf16(d, dxl, dzh, idesc, 1u);
+          const uint32_t zh = zh0 + (uint32_t)j * p.z_row_bytes, zl = zh + zpl16;  // 16 rows = row_bytes 16-byte units
+          const uint32_t xk = (uint32_t)j * 128;                                      // 16 rows of 128 bytes
+          const bool first = i == 0 && j == 0;
+#pragma unroll
+          for (int t = 0; t < MAX_TAPS; ++t) {
+            if (t < p.n_tiles) {
+              const uint32_t d = tmem + (uint32_t)t * p.N;
+              if (first) tma::mma_bf16_split<false>(d, xlo[t] + xk, x_hi32, zh, z_hi32, idesc);
+              else tma::mma_bf16_split<true>(d, xlo[t] + xk, x_hi32, zh, z_hi32, idesc);
+              tma::mma_bf16_split<true>(d, xlo[t] + xk, x_hi32, zl, z_hi32, idesc);
+              if (A_PLANES == 2) tma::mma_bf16_split<true>(d, xlo[t] + xk + xpl16, x_hi32, zh, z_hi32, idesc);
             }
           }
           // bias gradient: ones^T dy (lo part of dy included)
-          const uint32_t d = tmem + (uint32_t)p.n_tiles * p.N;
-          const uint64_t d1 = tma::make_desc(base + L.ones_off, 16, 1024, tma::LT_SW128);
-          mma_bf16(d, d1, dzh, idesc, acc);
-          mma_bf16(d, d1, dzl, idesc, 1u);
+          if (first) tma::mma_bf16_split<false>(dbias, ones_lo, x_hi32, zh, z_hi32, idesc);
+          else tma::mma_bf16_split<true>(dbias, ones_lo, x_hi32, zh, z_hi32, idesc);
+          tma::mma_bf16_split<true>(dbias, ones_lo, x_hi32, zl, z_hi32, idesc);
         }
         mma_commit(empty);
+        tl_stamp(p.debug, 3001 + 2 * i);
+        if (im == im1 - 1) mma_commit(done);
+        }
+        __syncwarp();
       }
-      mma_commit(done);
     }
   }
   // ===== epilogue: warps 2..5 (quadrant = warp % 4) write the partial gradient =====
@@ -461,6 +523,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
     const int q = warp & 3, r = q * 32 + lane;
     mbar_wait(done, 0);
     tcgen05_after_sync();
+    if (warp == 2 && lane == 0) tl_stamp(p.debug, 1200);
     float* part = p.part + ((int64_t)z * p.groups + gidx) * p.span;
     for (int t = 0; t <= p.n_tiles; ++t) {
       int64_t arow = -1;
@@ -484,6 +547,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
       }
     }
   }
+  if (warp == 2 && lane == 0) tl_stamp(p.debug, 1201);
   tcgen05_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, tmem_cols);

@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
     else cp_async_wait<0>();
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {  // one elected lane: no per-instruction ELECT/BRA.U.ANY waterfall (tc_core.cuh)
       tcgen05_after_sync();
       const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes;
       const uint32_t a_lo = a_hi + a_bytes;

@@ -141,7 +141,7 @@ static int img_setup(idqn_handle* h) {
       a.P = g.P, a.M_valid = g.OH * g.P, a.W_valid = g.OW;
       a.tiles = (a.M_valid + 127) / 128;
       a.N = a.hpg * g.OC;
-      a.tpp = std::max(1, std::min(a.tiles, 256 / a.N));
+      a.tpp = std::max(1, std::min(a.tiles, 128 / a.N));  // 2 buffers x tpp tiles x 2N columns <= 512
       a.n_taps = g.T * g.T, a.kt = g.C2 / 16;
       for (int ty = 0; ty < g.T; ++ty)
         for (int tx = 0; tx < g.T; ++tx) {
@@ -184,7 +184,7 @@ static int img_setup(idqn_handle* h) {
       a.P = g.P, a.M_valid = g.BH * g.P, a.W_valid = g.BW;
       a.tiles = (a.M_valid + 127) / 128;
       a.N = g.C2;
-      a.tpp = std::max(1, std::min(a.tiles, 256 / a.N));
+      a.tpp = std::max(1, std::min(a.tiles, 128 / a.N));
       a.n_taps = g.T * g.T, a.kt = g.OC / 16;
       int shmax = 0;
       for (int ty = 0; ty < g.T; ++ty)
@@ -274,6 +274,24 @@ static void img_free(idqn_handle* h) {
   if (h->img_host) delete (ImgHost*)h->img_host;
 }
 
+// IDQN_TL=fwd2 / dgrad1 / wgrad0 ...: the matching launch records its pipeline timeline (conv_img.cuh)
+static int img_debug_on(const char* kind, int li) {
+  const char* e = getenv("IDQN_TL");
+  if (!e) return 0;
+  char tag[32];
+  snprintf(tag, sizeof(tag), "%s%d", kind, li);
+  if (strcmp(e, tag)) return 0;
+  static unsigned long long zeros[img::TL_MAX];
+  cudaMemcpyToSymbol(img::g_tl, zeros, sizeof(zeros));
+  return 1;
+}
+extern "C" int idqn_debug_timeline(unsigned long long* out, int max_entries) {
+  cudaDeviceSynchronize();
+  const int n = std::min((int)img::TL_MAX, max_entries);
+  cudaMemcpyFromSymbol(out, img::g_tl, sizeof(unsigned long long) * n);
+  return n;
+}
+
 template <class Kern>
 static cudaError_t img_set_smem(Kern kern, size_t bytes) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -292,7 +310,8 @@ static int img_launch_s2d(idqn_handle* h, int x_u8) {
 
 static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes) {
   ImgHost* H = (ImgHost*)h->img_host;
-  const img::TapsArgs& a = dgrad ? H->dg[li] : H->fwd[li];
+  img::TapsArgs a = dgrad ? H->dg[li] : H->fwd[li];
+  a.debug = img_debug_on(dgrad ? "dgrad" : "fwd", li);
   const ImgLayerState& S = h->il[li];
   const img::TapsSmem L = img::taps_smem(a, a_planes);
   const int grid = std::min(a.n_units, h->sm_count);
@@ -313,7 +332,8 @@ static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes) {
 
 static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
   ImgHost* H = (ImgHost*)h->img_host;
-  const img::WgradArgs& a = H->wg[li];
+  img::WgradArgs a = H->wg[li];
+  a.debug = img_debug_on("wgrad", li);
   const ImgLayerState& S = h->il[li];
   const img::WgradSmem L = img::wgrad_smem(a, a_planes);
   const int grid = a.heads * a.groups;
