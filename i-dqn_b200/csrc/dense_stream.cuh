@@ -1,0 +1,234 @@
+// Weight-streaming tcgen05 kernels for the big Dense layer (Dense_0: 7744 x 512) at batch 32 (sm_100a).
+//
+// At batch 32 the layer is bound by reading its 15.9 MB kernel once per net: the weights are the M-side operand
+// (128 rows per tile), the batch sits on N.  A persistent CTA streams 64-deep K blocks of the weight planes
+// (hi, lo) and of the small batch operand through a TMA ring (SWIZZLE_128B, tma_core.cuh); per K = 16 step
+//     W_hi * [x_hi | x_lo]   (one MMA, N = 64: the batch planes sit next to each other in the stage)
+//   + W_lo * x_hi            (one MMA, N = 32)
+// accumulate in TMEM ("bf16x3" split, fp32-faithful); the epilogue adds the two column sets.
+//   MODE 0  forward   y[b][o]  = relu(sum_i x[b][i] W[i][o] + bias[o])      A = W^T: MN-major, rows = i, M = o
+//           split-K over units; partial tiles are combined by the last-arriving unit in split order (deterministic)
+//   MODE 1  dgrad     dx[b][i] = relu'(x[b][i]) sum_o dy[b][o] W[i][o]       A = W:   K-major, rows = i = M, K = o
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "tc_core.cuh"
+#include "tma_core.cuh"
+
+namespace dense {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int NTHREADS = 192;  // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue
+constexpr int BKD = 64;        // K depth of a stage (128-byte rows)
+constexpr int NB = 32;         // batch columns
+
+struct Args {
+  int n_units, tiles, splits, kb_per_unit;  // unit = (net, tile, split); kb_per_unit K blocks each
+  int nets;
+  int stages;
+  // forward
+  int I, O;
+  NetPtr w;             // fp32 arenas (bias)
+  int64_t b_off;
+  float* y;             // [nets][ystride]  (fwd)  /  dx [heads][xstride] (dgrad)
+  bf16 *yh, *yl;        // planes of the output
+  int64_t ystride;
+  const float* xact;    // dgrad: layer input (relu output), same indexing as dx
+  float* part;          // fwd: [nets*tiles][splits][32][128]
+  int* tickets;         // fwd: [nets*tiles]
+  // dgrad planes destination: dyZ layout of the preceding conv layer (zP > 0) or plain
+  int zP, zW, zC, zOff;
+  int64_t zRows, zstride;
+};
+
+struct Smem {
+  uint32_t a_bytes, b_bytes, stage_bytes, bar_off, total;
+};
+__host__ __device__ inline Smem smem_layout(const Args& p) {
+  Smem s;
+  s.a_bytes = 128 * BKD * 2;    // one plane of the weight tile: 16 KB
+  s.b_bytes = NB * BKD * 2;     // one plane of the batch tile: 4 KB
+  s.stage_bytes = 2 * s.a_bytes + 2 * s.b_bytes;
+  s.bar_off = p.stages * s.stage_bytes;
+  s.total = s.bar_off + 256 + 1024;
+  return s;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                    const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                    const Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const Smem L = smem_layout(p);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* full = bars;             // [stages]
+  uint64_t* empty = bars + 8;        // [stages]
+  uint64_t* acc_full = bars + 16;    // [2]
+  uint64_t* acc_empty = bars + 18;   // [2]
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < p.stages; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 128);  // 2 accumulator buffers x 64 columns
+  fence_proxy_async_smem();
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int sp = u % p.splits, nt = u / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
+        for (int kb = 0; kb < p.kb_per_unit; ++kb) {
+          mbar_wait(&empty[st], ph ^ 1);
+          tma::expect_tx(&full[st], L.stage_bytes);
+          const uint32_t s0 = base + st * L.stage_bytes;
+          const int k0 = (sp * p.kb_per_unit + kb) * BKD;
+          if (MODE == 0) {
+            // A = W^T: two 64-wide o groups x 64 i rows per plane
+            for (int g = 0; g < 2; ++g) {
+              tma::load_3d(s0 + g * 8192, &mapA_hi, &full[st], tile * 128 + g * 64, k0, net);
+              tma::load_3d(s0 + L.a_bytes + g * 8192, &mapA_lo, &full[st], tile * 128 + g * 64, k0, net);
+            }
+          } else {
+            // A = W: 128 i rows x 64 o
+            tma::load_3d(s0, &mapA_hi, &full[st], k0, tile * 128, net);
+            tma::load_3d(s0 + L.a_bytes, &mapA_lo, &full[st], k0, tile * 128, net);
+          }
+          tma::load_3d(s0 + 2 * L.a_bytes, &mapB_hi, &full[st], k0, 0, net);
+          tma::load_3d(s0 + 2 * L.a_bytes + L.b_bytes, &mapB_lo, &full[st], k0, 0, net);
+          if (++st == p.stages) st = 0, ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc2 = make_idesc_bf16(128, 2 * NB, MODE == 0, false);
+      const uint32_t idesc1 = make_idesc_bf16(128, NB, MODE == 0, false);
+      const uint32_t hi32 = tma::desc_hi32(1024, tma::LT_SW128);
+      const uint32_t astep = MODE == 0 ? 128u : 2u;  // K = 16: 16 rows of 128 B (MN-major) or 32 bytes (K-major)
+      int st = 0, ai = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ai) {
+        const int ab = ai & 1;
+        mbar_wait(&acc_empty[ab], ((ai >> 1) & 1) ^ 1);
+        const uint32_t d = tmem + (uint32_t)ab * 2 * NB;
+        for (int kb = 0; kb < p.kb_per_unit; ++kb) {
+          mbar_wait(&full[st], ph);
+          tcgen05_after_sync();
+          const uint32_t s0 = base + st * L.stage_bytes;
+          const uint32_t a_lbo = MODE == 0 ? 8192u : 16u;  // MN-major: second 64-wide o group; K-major: unused
+          const uint32_t ah = tma::desc_lo32(s0, a_lbo), al = tma::desc_lo32(s0 + L.a_bytes, a_lbo);
+          const uint32_t bh = tma::desc_lo32(s0 + 2 * L.a_bytes, 16);
+#pragma unroll
+          for (int j = 0; j < BKD / 16; ++j) {
+            if (kb == 0 && j == 0) tma::mma_bf16_split<false>(d, ah, hi32, bh, hi32, idesc2);
+            else tma::mma_bf16_split<true>(d, ah + j * astep, hi32, bh + 2 * j, hi32, idesc2);
+            tma::mma_bf16_split<true>(d, al + j * astep, hi32, bh + 2 * j, hi32, idesc1);
+          }
+          mma_commit(&empty[st]);
+          if (++st == p.stages) st = 0, ph ^= 1;
+        }
+        mma_commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4; thread = accumulator row (o or i) =====
+    const int q = warp & 3, r = q * 32 + lane;
+    const int et = tid - 64;  // 0..127
+    int ai = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ai) {
+      const int ab = ai & 1;
+      const int sp = u % p.splits, nt = u / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
+      mbar_wait(&acc_full[ab], (ai >> 1) & 1);
+      tcgen05_after_sync();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * 2 * NB;
+      float v[NB];
+      {
+        float a0[16], a1[16], b0[16], b1[16];
+        tmem_ld16_nowait(taddr, a0);
+        tmem_ld16_nowait(taddr + 16, a1);
+        tmem_ld16_nowait(taddr + 32, b0);
+        tmem_ld16_nowait(taddr + 48, b1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = a0[e] + b0[e], v[16 + e] = a1[e] + b1[e];
+      }
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) tma::arrive(&acc_empty[ab]);  // accumulator drained into registers
+      const int row = tile * 128 + r;              // o (fwd) / i (dgrad)
+      if (MODE == 0) {
+        bool reduce = p.splits == 1;
+        if (p.splits > 1) {
+          float* mine = p.part + ((int64_t)nt * p.splits + sp) * (NB * 128);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) __stcg(mine + b * 128 + r, v[b]);
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+          if (et == 0) {
+            const int t = atomicAdd(&p.tickets[nt], 1);
+            s_last = (t == p.splits - 1);
+            if (s_last) p.tickets[nt] = 0;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          reduce = s_last != 0;
+          if (reduce) {
+            __threadfence();
+            const float* src = p.part + (int64_t)nt * p.splits * (NB * 128) + r;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) v[b] = 0.f;
+            for (int s2 = 0; s2 < p.splits; ++s2)  // fixed order: deterministic
+#pragma unroll
+              for (int b = 0; b < NB; ++b) v[b] += __ldcg(src + ((int64_t)s2 * NB + b) * 128);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // s_last is reused by the next unit
+        }
+        if (reduce && row < p.O) {
+          const float bb = __ldg(p.w.get<float>(net) + p.b_off + row);
+          const int64_t o0 = (int64_t)net * p.ystride + row;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const float o = fmaxf(v[b] + bb, 0.f);
+            p.y[o0 + (int64_t)b * p.O] = o;
+            st1_planes(p.yh + o0 + (int64_t)b * p.O, p.yl + o0 + (int64_t)b * p.O, o);
+          }
+        }
+      } else {
+        if (row < p.I) {
+          int64_t zrow = 0;
+          if (p.zP > 0) {
+            const int pix = row / p.zC, ch = row - pix * p.zC, yy = pix / p.zW, xx = pix - yy * p.zW;
+            zrow = (int64_t)net * p.zstride + ((int64_t)(yy + p.zOff) * p.zP + xx + p.zOff) * p.zC + ch;
+          }
+          const int64_t x0 = (int64_t)net * p.ystride + row;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const int64_t idx = x0 + (int64_t)b * p.I;
+            const float o = __ldg(p.xact + idx) > 0.f ? v[b] : 0.f;
+            p.y[idx] = o;
+            const int64_t pi = p.zP > 0 ? zrow + (int64_t)b * p.zRows * p.zC : idx;
+            st1_planes(p.yh + pi, p.yl + pi, o);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace dense

@@ -2,13 +2,19 @@
 // and launches.  Included by net.cu (uses its mark() / CK helpers).
 #pragma once
 #include "conv_img.cuh"
+#include "dense_stream.cuh"
 
 struct ImgHost {
   img::Geom g[IDQN_IMG_LAYERS];
   img::TapsArgs fwd[IDQN_IMG_LAYERS], dg[IDQN_IMG_LAYERS];
   img::WgradArgs wg[IDQN_IMG_LAYERS];
   img::S2dArgs s2d;
-  int x0_lo_ready;  // layer-0 lo plane written (float inputs)
+  // weight-streaming kernels of the big Dense layer (dense_stream.cuh)
+  int dense_on;
+  alignas(64) CUtensorMap dmapWf[2], dmapWd[2], dmapX[2], dmapDy[2];
+  dense::Args dfwd, ddg;
+  float* dpart;
+  int* dtickets;
 };
 
 static int img_chunks(int rows, int* chunk_rows, int* rows_alloc) {
@@ -260,6 +266,67 @@ static int img_setup(idqn_handle* h) {
     a.BH = g.BH, a.BW = g.BW, a.P = g.P, a.C2 = g.C2, a.img_rows = g.XRa;
     a.hi = h->il[0].x2_hi, a.lo = h->il[0].x2_lo;
   }
+  // ---- big Dense layer: weight-streaming kernels ----
+  {
+    const int li = IDQN_IMG_LAYERS;
+    const Layer& prev = h->layers[li - 1];
+    const int I = dense.g.Kd, O = dense.g.OC;
+    H->dense_on = B == dense::NB && O % 128 == 0 && I % 64 == 0 && O % 64 == 0;
+    if (H->dense_on) {
+      for (int pl = 0; pl < 2; ++pl) {
+        const __nv_bfloat16* wb = (pl ? h->wpl_lo : h->wpl_hi) + dense.w_off;
+        const uint64_t wdims[3] = {(uint64_t)O, (uint64_t)I, (uint64_t)2 * K};
+        const uint64_t wstr[2] = {(uint64_t)O * 2, (uint64_t)h->stride * 2};
+        const uint32_t boxf[3] = {64, 64, 1}, boxd[3] = {64, 128, 1};
+        REQUIRE(tma::encode_bf16(&H->dmapWf[pl], wb, 3, wdims, wstr, boxf, 128), "tensor map dense W (fwd)");
+        REQUIRE(tma::encode_bf16(&H->dmapWd[pl], wb, 3, wdims, wstr, boxd, 128), "tensor map dense W (dgrad)");
+        const __nv_bfloat16* xb = (pl ? h->act_lo : h->act_hi) + prev.act_off;
+        const uint64_t xdims[3] = {(uint64_t)I, (uint64_t)B, (uint64_t)2 * K};
+        const uint64_t xstr[2] = {(uint64_t)I * 2, (uint64_t)h->act_stride * 2};
+        const uint32_t boxx[3] = {64, (uint32_t)B, 1};
+        REQUIRE(tma::encode_bf16(&H->dmapX[pl], xb, 3, xdims, xstr, boxx, 128), "tensor map dense x");
+        const __nv_bfloat16* yb = (pl ? h->dact_lo : h->dact_hi) + dense.act_off;
+        const uint64_t ydims[3] = {(uint64_t)O, (uint64_t)B, (uint64_t)K};
+        const uint64_t ystr[2] = {(uint64_t)O * 2, (uint64_t)h->act_stride * 2};
+        REQUIRE(tma::encode_bf16(&H->dmapDy[pl], yb, 3, ydims, ystr, boxx, 128), "tensor map dense dy");
+      }
+      const int kblocks = (I + 63) / 64;
+      {
+        dense::Args& a = H->dfwd;
+        a.nets = 2 * K, a.tiles = O / 128;
+        // split K so that the units fill the machine in whole rounds
+        int best = 1;
+        double best_eff = 0;
+        for (int sp = 1; sp <= 16; ++sp) {
+          const int units = a.nets * a.tiles * sp, rounds = (units + h->sm_count - 1) / h->sm_count;
+          const double eff = (double)units / ((double)rounds * h->sm_count);
+          if (eff > best_eff + 0.02 && (kblocks + sp - 1) / sp >= 4) best_eff = eff, best = sp;
+        }
+        a.splits = best, a.kb_per_unit = (kblocks + best - 1) / best;
+        a.n_units = a.nets * a.tiles * a.splits;
+        a.stages = 5;
+        a.I = I, a.O = O;
+        a.w = NetPtr{h->online, h->target, h->stride, h->stride, K};
+        a.b_off = dense.b_off;
+        a.y = h->act + dense.act_off, a.yh = h->act_hi + dense.act_off, a.yl = h->act_lo + dense.act_off;
+        a.ystride = h->act_stride;
+        CK(cudaMalloc(&H->dpart, sizeof(float) * (size_t)a.n_units * dense::NB * 128));
+        CK(cudaMalloc(&H->dtickets, sizeof(int) * a.nets * a.tiles));
+        CK(cudaMemsetAsync(H->dtickets, 0, sizeof(int) * a.nets * a.tiles, h->stream));
+        a.part = H->dpart, a.tickets = H->dtickets;
+      }
+      {
+        dense::Args& a = H->ddg;
+        a.nets = K, a.tiles = (I + 127) / 128, a.splits = 1, a.kb_per_unit = O / 64;
+        a.n_units = a.nets * a.tiles;
+        a.stages = 5;
+        a.I = I, a.O = O;
+        a.y = h->dact + prev.act_off, a.xact = h->act + prev.act_off, a.ystride = h->act_stride;
+        a.yh = h->dact_hi + prev.act_off, a.yl = h->dact_lo + prev.act_off;
+        a.zP = 0;
+      }
+    }
+  }
   h->img_on = 1;
   return IDQN_OK;
 }
@@ -271,7 +338,12 @@ static void img_free(idqn_handle* h) {
       if (p) cudaFree(p);
   }
   if (h->wpart) cudaFree(h->wpart);
-  if (h->img_host) delete (ImgHost*)h->img_host;
+  if (h->img_host) {
+    ImgHost* H = (ImgHost*)h->img_host;
+    if (H->dpart) cudaFree(H->dpart);
+    if (H->dtickets) cudaFree(H->dtickets);
+    delete H;
+  }
 }
 
 // IDQN_TL=fwd2 / dgrad1 / wgrad0 ...: the matching launch records its pipeline timeline (conv_img.cuh)
@@ -346,5 +418,32 @@ static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
   }
   CK(cudaGetLastError());
   mark(h, "img_wgrad_L%d", li);
+  return IDQN_OK;
+}
+
+// forward (dgrad == false) or data gradient of the big Dense layer; z_dst: dgrad planes go to the dyZ layout of the
+// preceding conv layer
+static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst) {
+  ImgHost* H = (ImgHost*)h->img_host;
+  dense::Args a = dgrad ? H->ddg : H->dfwd;
+  const int li = IDQN_IMG_LAYERS;
+  if (dgrad && z_dst) {
+    const img::Geom& pg = H->g[li - 1];
+    a.yh = h->il[li - 1].dz_hi, a.yl = h->il[li - 1].dz_lo;
+    a.zP = pg.P, a.zW = pg.OW, a.zC = pg.OC, a.zOff = pg.T - 1, a.zRows = pg.ZRa, a.zstride = h->il[li - 1].dz_net_stride;
+  }
+  const dense::Smem L = dense::smem_layout(a);
+  const int grid = std::min(a.n_units, h->sm_count);
+  if (dgrad) {
+    CK(img_set_smem(dense::dense_stream_kernel<1>, L.total));
+    dense::dense_stream_kernel<1><<<grid, dense::NTHREADS, L.total, h->stream>>>(H->dmapWd[0], H->dmapWd[1], H->dmapDy[0],
+                                                                               H->dmapDy[1], a);
+  } else {
+    CK(img_set_smem(dense::dense_stream_kernel<0>, L.total));
+    dense::dense_stream_kernel<0><<<grid, dense::NTHREADS, L.total, h->stream>>>(H->dmapWf[0], H->dmapWf[1], H->dmapX[0],
+                                                                               H->dmapX[1], a);
+  }
+  CK(cudaGetLastError());
+  mark(h, dgrad ? "dense_dgrad_L%d" : "dense_fwd_L%d", li);
   return IDQN_OK;
 }

@@ -715,7 +715,13 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   }
   // forward of 2K nets through all hidden layers
   const int64_t in_full = (int64_t)B * h->in_elems;
+  const bool use_dense = h->img_on && !dry && ((ImgHost*)h->img_host)->dense_on;  // dense_stream.cuh for Dense_0
   for (int li = n_img; li < L - 1; ++li) {
+    if (use_dense && li == IDQN_IMG_LAYERS) {
+      int rc = dense_launch(h, false, false);
+      if (rc) return rc;
+      continue;
+    }
     FwdIO io;
     int nh = 1;
     if (li == 0) {
@@ -784,7 +790,8 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
       continue;
     }
     if (li > 0 && !dry) {
-      int rc = launch_dgrad_layer(h, li, li == n_img && n_img > 0);
+      int rc = (use_dense && li == IDQN_IMG_LAYERS) ? dense_launch(h, true, n_img > 0)
+                                                   : launch_dgrad_layer(h, li, li == n_img && n_img > 0);
       if (rc) return rc;
     }
     int rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
