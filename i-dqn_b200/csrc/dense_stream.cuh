@@ -7,15 +7,17 @@
 //   + W_lo * x_hi            (one MMA, N = 32)
 // accumulate in TMEM ("bf16x3" split, fp32-faithful); the epilogue adds the two column sets.
 //   MODE 0  forward   y[b][o]  = relu(sum_i x[b][i] W[i][o] + bias[o])      A = W^T: MN-major, rows = i, M = o
-//           split-K over units; partial tiles are combined by the last-arriving unit in split order (deterministic)
+//           split-K over units; the partial tiles are summed in split order by the consumer (head_q_kernel)
 //   MODE 1  dgrad     dx[b][i] = relu'(x[b][i]) sum_o dy[b][o] W[i][o]       A = W:   K-major, rows = i = M, K = o
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "tc_core.cuh"
 #include "tma_core.cuh"
+#include "conv_img.cuh"  // tl_stamp
 
 namespace dense {
+using img::tl_stamp;
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
@@ -40,6 +42,7 @@ struct Args {
   // dgrad planes destination: dyZ layout of the preceding conv layer (zP > 0) or plain
   int zP, zW, zC, zOff;
   int64_t zRows, zstride;
+  int debug;
 };
 
 struct Smem {
@@ -70,7 +73,6 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
   uint64_t* acc_full = bars + 16;    // [2]
   uint64_t* acc_empty = bars + 18;   // [2]
   __shared__ uint32_t tmem_base_s;
-  __shared__ int s_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -87,12 +89,13 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
 
   if (warp == 0) {
     if (elect_one()) {
-      int st = 0;
+      int st = 0, ui = 0;
       uint32_t ph = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ui) {
         const int sp = u % p.splits, nt = u / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
         for (int kb = 0; kb < p.kb_per_unit; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
+          tl_stamp(p.debug, 2000 + ui * 16 + kb);
           tma::expect_tx(&full[st], L.stage_bytes);
           const uint32_t s0 = base + st * L.stage_bytes;
           const int k0 = (sp * p.kb_per_unit + kb) * BKD;
@@ -128,6 +131,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
         for (int kb = 0; kb < p.kb_per_unit; ++kb) {
           mbar_wait(&full[st], ph);
           tcgen05_after_sync();
+          tl_stamp(p.debug, 3000 + ai * 32 + kb);
           const uint32_t s0 = base + st * L.stage_bytes;
           const uint32_t a_lbo = MODE == 0 ? 8192u : 16u;  // MN-major: second 64-wide o group; K-major: unused
           const uint32_t ah = tma::desc_lo32(s0, a_lbo), al = tma::desc_lo32(s0 + L.a_bytes, a_lbo);
@@ -139,6 +143,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
             tma::mma_bf16_split<true>(d, al + j * astep, hi32, bh + 2 * j, hi32, idesc1);
           }
           mma_commit(&empty[st]);
+          tl_stamp(p.debug, 3000 + ai * 32 + 16 + kb);
           if (++st == p.stages) st = 0, ph ^= 1;
         }
         mma_commit(&acc_full[ab]);
@@ -154,6 +159,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
       const int sp = u % p.splits, nt = u / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
       mbar_wait(&acc_full[ab], (ai >> 1) & 1);
       tcgen05_after_sync();
+      if (et == 0) tl_stamp(p.debug, 1200 + 2 * ai);
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * 2 * NB;
       float v[NB];
       {
@@ -171,30 +177,13 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
       if (lane == 0) tma::arrive(&acc_empty[ab]);  // accumulator drained into registers
       const int row = tile * 128 + r;              // o (fwd) / i (dgrad)
       if (MODE == 0) {
-        bool reduce = p.splits == 1;
+        const bool reduce = p.splits == 1;
         if (p.splits > 1) {
+          // split-K: store the partial tile; the consumer (head_q_kernel) sums the splits in a fixed order together
+          // with bias and relu -- no fence / ticket handshake on this kernel's critical path
           float* mine = p.part + ((int64_t)nt * p.splits + sp) * (NB * 128);
 #pragma unroll
           for (int b = 0; b < NB; ++b) __stcg(mine + b * 128 + r, v[b]);
-          __threadfence();
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-          if (et == 0) {
-            const int t = atomicAdd(&p.tickets[nt], 1);
-            s_last = (t == p.splits - 1);
-            if (s_last) p.tickets[nt] = 0;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          reduce = s_last != 0;
-          if (reduce) {
-            __threadfence();
-            const float* src = p.part + (int64_t)nt * p.splits * (NB * 128) + r;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) v[b] = 0.f;
-            for (int s2 = 0; s2 < p.splits; ++s2)  // fixed order: deterministic
-#pragma unroll
-              for (int b = 0; b < NB; ++b) v[b] += __ldcg(src + ((int64_t)s2 * NB + b) * 128);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // s_last is reused by the next unit
         }
         if (reduce && row < p.O) {
           const float bb = __ldg(p.w.get<float>(net) + p.b_off + row);
@@ -224,6 +213,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
           }
         }
       }
+      if (et == 0) tl_stamp(p.debug, 1201 + 2 * ai);
     }
   }
   tcgen05_before_sync();

@@ -427,6 +427,7 @@ static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst) {
   ImgHost* H = (ImgHost*)h->img_host;
   dense::Args a = dgrad ? H->ddg : H->dfwd;
   const int li = IDQN_IMG_LAYERS;
+  a.debug = img_debug_on(dgrad ? "ddgrad" : "dfwd", li);
   if (dgrad && z_dst) {
     const img::Geom& pg = H->g[li - 1];
     a.yh = h->il[li - 1].dz_hi, a.yl = h->il[li - 1].dz_lo;

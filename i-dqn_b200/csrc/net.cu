@@ -154,25 +154,40 @@ struct HeadArgs {
   double* loss_sum;
   int32_t* count;
   float* q;      // [2K][B][A]
+  // deferred split-K reduce of the preceding Dense layer (dense_stream.cuh): partial tiles [net*ptiles + tile][split][32][128]
+  const float* part;
+  int ptiles, psplits;
+  int64_t pb_off;  // arena offset of that layer's bias
 };
 #define HEAD_MAXA 32
 
-// Q-values of the final Dense layer: one warp per (net, sample); lanes stride the hidden units and keep all A
-// partial sums (W rows are [A] contiguous), then A warp-shuffle reductions.
+// Q-values of the final Dense layer: one 128-thread CTA per (net, sample); threads stride the hidden units, keep all
+// A partial sums (W rows are [A] contiguous) and finish with warp shuffles + a fixed-order cross-warp sum.  When the preceding Dense layer ran split-K
+// (dense_stream.cuh) its partial tiles are summed here, in split order, together with its bias and relu, and the
+// hidden activations are materialised for the backward kernels.
 __global__ void __launch_bounds__(128) head_q_kernel(const HeadArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wid >= 2 * a.K * a.B) return;
-  const int net = wid / a.B, b = wid - net * a.B;
+  __shared__ float red[4][HEAD_MAXA];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int net = blockIdx.x / a.B, b = blockIdx.x - net * a.B;
   const int k = net < a.K ? net : net - a.K;
   const float* base = (net < a.K ? a.online : a.target) + (int64_t)k * a.stride;
   const float* W = base + a.w_off;
-  const float* hv = a.hid.get<float>(net) + (int64_t)b * a.H;
+  float* hv = const_cast<float*>(a.hid.get<float>(net)) + (int64_t)b * a.H;
   float acc[HEAD_MAXA];
 #pragma unroll
   for (int i = 0; i < HEAD_MAXA; ++i) acc[i] = 0.f;
-  for (int j = lane; j < a.H; j += 32) {
-    const float h = hv[j];
+  for (int j = tid; j < a.H; j += 128) {
+    float h;
+    if (a.part) {
+      const float* src = a.part + ((int64_t)(net * a.ptiles + (j >> 7)) * a.psplits) * (32 * 128) + b * 128 + (j & 127);
+      h = __ldg(base + a.pb_off + j);
+#pragma unroll 4
+      for (int sp = 0; sp < a.psplits; ++sp) h += __ldcg(src + (int64_t)sp * (32 * 128));  // fixed order
+      h = fmaxf(h, 0.f);
+      hv[j] = h;
+    } else {
+      h = hv[j];
+    }
     const float* wr = W + (int64_t)j * a.A;
 #pragma unroll
     for (int i = 0; i < HEAD_MAXA; ++i)
@@ -184,14 +199,17 @@ __global__ void __launch_bounds__(128) head_q_kernel(const HeadArgs a) {
       float s = acc[i];
 #pragma unroll
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) a.q[((int64_t)net * a.B + b) * a.A + i] = s + __ldg(base + a.b_off + i);
+      if (lane == 0) red[warp][i] = s;
     }
   }
+  __syncthreads();
+  if (tid < a.A) a.q[((int64_t)net * a.B + b) * a.A + tid] = ((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid])) + __ldg(base + a.b_off + tid);
 }
 
 // y = r + (1-done) gamma^n max_a' Q_target; delta = Q(s,a) - y; loss_k = mean delta^2 and the backward of the
-// final layer.  grid (ceil(H/128), K): every CTA recomputes the B coefficients (cheap) and owns 128 hidden units.
-__global__ void __launch_bounds__(128) head_bwd_kernel(const HeadArgs a) {
+// final layer.  grid (ceil(H/32), K), 256 threads: every CTA recomputes the B coefficients (cheap) and owns 32
+// hidden units: thread (b-slot, 4 units) writes dL/dhidden, threads (unit, action) the kernel gradient.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
   extern __shared__ float sm[];
   const int k = blockIdx.y, B = a.B, A = a.A, H = a.H, tid = threadIdx.x;
   float* coef = sm;        // [B]
@@ -228,25 +246,38 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const HeadArgs a) {
       gb[i] = s;
     }
   }
-  const int j = blockIdx.x * blockDim.x + tid;
-  if (j >= H) return;
+  const int j0 = blockIdx.x * 32;
   const float* hid = a.hid.get<float>(k);
-  const float* W = a.online + (int64_t)k * a.stride + a.w_off + (int64_t)j * A;
-  float* gW = a.grad + (int64_t)k * a.stride + a.w_off + (int64_t)j * A;
-  for (int i = 0; i < A; ++i) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b)
-      if (act_s[b] == i) s = fmaf(coef[b], hid[(int64_t)b * H + j], s);
-    gW[i] = s;
+  const float* Wk = a.online + (int64_t)k * a.stride + a.w_off;
+  // kernel gradient: 32 units x A actions
+  for (int e = tid; e < 32 * A; e += blockDim.x) {
+    const int j = j0 + e / A, i = e - (e / A) * A;
+    if (j < H) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b)
+        if (act_s[b] == i) s = fmaf(coef[b], hid[(int64_t)b * H + j], s);
+      a.grad[(int64_t)k * a.stride + a.w_off + (int64_t)j * A + i] = s;
+    }
   }
   if (a.dhid) {
+    // dL/dhidden[b][j] = coef_b W[j][a_b], masked by relu'; thread = (b-slot of 8 lanes x 4 units)
     float* dh = a.dhid + (int64_t)k * a.dstride;
-    for (int b = 0; b < B; ++b) {
-      float v = coef[b] * __ldg(W + act_s[b]);
-      if (a.relu_mask && !(hid[(int64_t)b * H + j] > 0.f)) v = 0.f;
-      dh[(int64_t)b * H + j] = v;
-      tc::st1_planes(a.dhid_hi + (int64_t)k * a.dstride + (int64_t)b * H + j,
-                     a.dhid_lo + (int64_t)k * a.dstride + (int64_t)b * H + j, v);
+    __nv_bfloat16* dhh = a.dhid_hi + (int64_t)k * a.dstride;
+    __nv_bfloat16* dhl = a.dhid_lo + (int64_t)k * a.dstride;
+    const int jj = (tid & 7) * 4;
+    for (int b = tid >> 3; b < B; b += blockDim.x >> 3) {
+      const float cb = coef[b];
+      const int ab = act_s[b];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + jj + u;
+        if (j < H) {
+          float v = cb * __ldg(Wk + (int64_t)j * A + ab);
+          if (a.relu_mask && !(hid[(int64_t)b * H + j] > 0.f)) v = 0.f;
+          dh[(int64_t)b * H + j] = v;
+          tc::st1_planes(dhh + (int64_t)b * H + j, dhl + (int64_t)b * H + j, v);
+        }
+      }
     }
   }
 }
@@ -769,12 +800,16 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     a.dstride = h->act_stride;
     a.loss = h->loss, a.loss_sum = h->loss_sum, a.count = h->count;
     a.q = h->q;
-    const int warps = 2 * K * B;
-    head_q_kernel<<<(warps * 32 + 127) / 128, 128, 0, h->stream>>>(a);
+    a.part = nullptr, a.ptiles = a.psplits = 0, a.pb_off = 0;
+    if (use_dense && L - 2 == IDQN_IMG_LAYERS) {
+      const dense::Args& df = ((ImgHost*)h->img_host)->dfwd;
+      if (df.splits > 1) a.part = df.part, a.ptiles = df.tiles, a.psplits = df.splits, a.pb_off = h->layers[L - 2].b_off;
+    }
+    head_q_kernel<<<2 * K * B, 128, 0, h->stream>>>(a);
     CK(cudaGetLastError());
     mark(h, "head_q_L%d", L - 1);
     const size_t smem = (size_t)(3 * B) * sizeof(float);
-    head_bwd_kernel<<<dim3((a.H + 127) / 128, K), 128, smem, h->stream>>>(a);
+    head_bwd_kernel<<<dim3((a.H + 31) / 32, K), 256, smem, h->stream>>>(a);
     CK(cudaGetLastError());
     mark(h, "head_bwd_L%d", L - 1);
   }

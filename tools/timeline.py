@@ -29,7 +29,7 @@ def name(tag):
     if 1200 <= tag < 2000:
         return f"E  pass {(tag - 1200) // 2} " + ("done" if tag & 1 else "acc_full seen")
     if 2000 <= tag < 3000:
-        return f"W  pass {(tag - 2000) // 16} tap {(tag - 2000) % 16} load issued"
+        return f"W  pass {(tag - 2000) // 16} tap {(tag - 2000) % 16} load issued (slot free)"
     k = tag - 3000
     return f"M  pass {k // 32} tap {k % 16} " + ("issued+commit" if k % 32 >= 16 else "w_full seen")
 
