@@ -148,7 +148,7 @@ def run_ours(args):
         agent = make_sharded_idqn(0, OBS, A, k_total, FEATS, "cnn", LR, GAMMA, 1, 1, T_FREQ, D_FREQ, EPS, rank=rank,
                                   world_size=world, device=local)
     else:
-        agent = iDQN(0, OBS, A, k_total, FEATS, "cnn", LR, GAMMA, 1, 1, T_FREQ, D_FREQ, EPS, device=local)
+        agent = iDQN(0, OBS, A, k_total, FEATS, "cnn", LR, GAMMA, 1, 1, T_FREQ, D_FREQ, EPS, device=local, flags=args.flags)
     eng = agent._engine
     # independent target draw so theta_bar != theta
     tgt = iDQN.__new__(iDQN)
@@ -320,6 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="IDQN_F_* engine flags (A/B experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

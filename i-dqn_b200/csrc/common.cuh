@@ -31,6 +31,27 @@ void idqn_set_error(const char* fmt, ...);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the learning step calls pdl_trigger() first thing (the next
+// kernel of the stream / graph may then be scheduled as SM resources free up and run its prologue: barrier init,
+// TMEM allocation, tensor-map prefetch, weight tiles) and pdl_wait() before it touches anything the step produces
+// (full completion + visibility of all earlier kernels).  Without the launch attribute both are no-ops.
+// Measured on B200 (K = 5 step, CUDA graph): 0.481 ms with the attribute, 0.458 ms without -- opt-in (IDQN_F_PDL).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // division by a runtime constant with one mul.hi + shift (valid for 0 <= n < 2^31)
 struct FastDiv {
   uint32_t d, mul, shr;
@@ -124,6 +145,7 @@ struct idqn_handle {
   __nv_bfloat16 *wpl_hi, *wpl_lo;                    // the allocation behind won_*/wtg_*: [2K][stride], online first
   // image-resident conv path (conv_img.cuh); img_on == 0 -> the generic kernels of gemm_tc.cuh run instead
   int img_on;
+  int pdl;                // launch the step's kernels with programmatic stream serialization
   ImgLayerState il[IDQN_IMG_LAYERS];
   void* img_host;         // ImgHost (net.cu): geometry and kernel arguments of the three conv layers
   float* wpart;           // [K][wgroups][wspan] partial conv weight gradients in arena coordinates

@@ -162,6 +162,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   if (warp == 0) {
     // ===== image producer =====
     if (elect_one()) {
+      pdl_wait();  // the image is produced by the preceding kernels (the weight tiles of warp 1 are not)
       int i = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const int xb = i & 1;
@@ -269,11 +270,14 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         }
       }
     }
+    __syncwarp();
+    pdl_trigger();  // the bulk of this CTA's work is queued: let the next kernel's CTAs start their prologue
   } else {
     // ===== epilogue warps 3..6: TMEM lane quadrant = warp % 4 =====
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row inside the tile
     int ai = 0;
+    pdl_wait();
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int hg = u % p.n_hg, gi = u / p.n_hg, g = gi / p.imgs, im = gi - g * p.imgs;
       const int net0 = g * p.nets_per_g + hg * p.hpg;
@@ -419,6 +423,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
   uint64_t* done = bars + 2;   // all MMAs of the CTA complete
   __shared__ uint32_t tmem_base_s;
 
+  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.x / p.groups, gidx = blockIdx.x - z * p.groups;
   const int im0 = gidx * p.ipg, im1 = min(p.imgs, im0 + p.ipg);
@@ -448,6 +453,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
   if (tid == 0) tl_stamp(p.debug, 1);
 
   if (warp == 0) {
+    pdl_wait();
     for (int im = im0, i = 0; im < im1; ++im, ++i) {
       mbar_wait(empty, (i & 1) ^ 1);
       if (elect_one()) {
@@ -521,6 +527,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
   // ===== epilogue: warps 2..5 (quadrant = warp % 4) write the partial gradient =====
   if (warp >= 2) {
     const int q = warp & 3, r = q * 32 + lane;
+    pdl_wait();
     mbar_wait(done, 0);
     tcgen05_after_sync();
     if (warp == 2 && lane == 0) tl_stamp(p.debug, 1200);
@@ -563,6 +570,8 @@ struct S2dArgs {
 };
 __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
   // one thread per (g, img, by, bx, ry): s*IC contiguous output channels = s input pixels of one input row
+  pdl_trigger();
+  pdl_wait();
   const int run = a.s * a.IC;
   const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -576,6 +585,27 @@ __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
     const int im = (int)(t % a.imgs), g = (int)(t / a.imgs);
     const int iy = by * a.s + ry - a.ph;
     const int64_t o = (((int64_t)g * a.imgs + im) * a.img_rows + (int64_t)by * a.P + bx) * a.C2 + (int64_t)ry * run;
+    if (a.u8 && a.IC == 4 && a.s == 4 && (a.pw & 1) == 0 && (a.IW & 1) == 0) {
+      // Atari frames: the run is 4 pixels x 4 stacked frames = 16 source bytes, 8-byte aligned pixel pairs
+      const uint8_t* src = (const uint8_t*)(g ? a.src[1] : a.src[0]);
+      const int ix0 = bx * 4 - a.pw;
+      uint2 raw[2];
+#pragma unroll
+      for (int hp = 0; hp < 2; ++hp) {
+        const int ix = ix0 + 2 * hp;
+        const bool ok = (unsigned)iy < (unsigned)a.IH && ix >= 0 && ix + 1 < a.IW;
+        raw[hp] = ok ? __ldg(reinterpret_cast<const uint2*>(src + (((int64_t)im * a.IH + iy) * a.IW + ix) * 4)) : make_uint2(0, 0);
+      }
+      const uint32_t w[4] = {raw[0].x, raw[0].y, raw[1].x, raw[1].y};
+#pragma unroll
+      for (int hv = 0; hv < 2; ++hv) {
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (float)((w[2 * hv + (k >> 2)] >> (8 * (k & 3))) & 0xffu);
+        *reinterpret_cast<uint4*>(a.hi + o + 8 * hv) = pack8_exact(x);
+      }
+      continue;
+    }
     for (int e = 0; e < run; e += 8) {
       float x[8];
 #pragma unroll

@@ -74,6 +74,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
   uint64_t* acc_empty = bars + 18;   // [2]
   __shared__ uint32_t tmem_base_s;
 
+  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < p.stages; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
@@ -89,6 +90,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
 
   if (warp == 0) {
     if (elect_one()) {
+      pdl_wait();
       int st = 0, ui = 0;
       uint32_t ph = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ui) {
@@ -154,6 +156,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
     const int q = warp & 3, r = q * 32 + lane;
     const int et = tid - 64;  // 0..127
     int ai = 0;
+    pdl_wait();
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ai) {
       const int ab = ai & 1;
       const int sp = u % p.splits, nt = u / p.splits, tile = nt % p.tiles, net = nt / p.tiles;

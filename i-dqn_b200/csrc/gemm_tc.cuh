@@ -594,6 +594,8 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_last;
 
+  pdl_trigger();
+  pdl_wait();  // this kernel reads its operands right away
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row_t = tid & 127, half = tid >> 7;
   const int NT = p.NT;
@@ -825,7 +827,7 @@ __global__ void __launch_bounds__(NTHR) tc_gemm_kernel(const P p, float* __restr
 }
 
 template <bool A_MN, bool B_MN, int A_PLANES, bool A_HALF, bool EPI_ROW, bool SPLITK, class P>
-static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tickets, cudaStream_t st) {
+static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tickets, cudaStream_t st, bool pdl = false) {
   size_t smem = (size_t)p.nstage * (A_PLANES * 128 * BK * 2 + 2 * (size_t)p.NT * BK * 2);
   if (P::TILE_EPI) smem = std::max(smem, (size_t)128 * (p.NT + 4) * sizeof(float));
   auto kern = tc_gemm_kernel<A_MN, B_MN, A_PLANES, A_HALF, EPI_ROW, SPLITK, P>;
@@ -835,8 +837,7 @@ static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tic
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, NTHR, smem, st>>>(p, part, tickets);
-  return cudaGetLastError();
+  return launch_pdl(pdl, kern, grid, dim3(NTHR), smem, st, p, part, tickets);
 }
 
 // stages that keep two CTAs resident per SM

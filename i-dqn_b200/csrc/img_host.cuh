@@ -374,8 +374,7 @@ static int img_launch_s2d(idqn_handle* h, int x_u8) {
   img::S2dArgs a = H->s2d;
   a.u8 = x_u8;
   const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
-  img::s2d_input_kernel<<<(int)((total + 255) / 256), 256, 0, h->stream>>>(a);
-  CK(cudaGetLastError());
+  CK(launch_pdl(h->pdl, img::s2d_input_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, h->stream, a));
   mark(h, "s2d_input_L%d", 0);
   return IDQN_OK;
 }
@@ -391,7 +390,8 @@ static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes) {
 #define IMG_TAPS_LAUNCH(KIND, PL)                                                                            \
   do {                                                                                                       \
     CK(img_set_smem(img::conv_taps_kernel<KIND, PL>, L.total));                                              \
-    img::conv_taps_kernel<KIND, PL><<<grid, img::NTHREADS, L.total, h->stream>>>(mA[0], mA[1], S.mapW[0], S.mapW[1], a); \
+    CK(launch_pdl(h->pdl, img::conv_taps_kernel<KIND, PL>, dim3(grid), dim3(img::NTHREADS), L.total, h->stream, mA[0],  \
+                  mA[1], S.mapW[0], S.mapW[1], a));                                                           \
   } while (0)
   if (dgrad) IMG_TAPS_LAUNCH(1, 2);
   else if (a_planes == 1) IMG_TAPS_LAUNCH(0, 1);
@@ -411,10 +411,12 @@ static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
   const int grid = a.heads * a.groups;
   if (a_planes == 1) {
     CK(img_set_smem(img::conv_wgrad_kernel<1>, L.total));
-    img::conv_wgrad_kernel<1><<<grid, 192, L.total, h->stream>>>(S.mapX[0], S.mapX[1], S.mapZ[0], S.mapZ[1], a);
+    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<1>, dim3(grid), dim3(192), L.total, h->stream, S.mapX[0], S.mapX[1],
+                  S.mapZ[0], S.mapZ[1], a));
   } else {
     CK(img_set_smem(img::conv_wgrad_kernel<2>, L.total));
-    img::conv_wgrad_kernel<2><<<grid, 192, L.total, h->stream>>>(S.mapX[0], S.mapX[1], S.mapZ[0], S.mapZ[1], a);
+    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<2>, dim3(grid), dim3(192), L.total, h->stream, S.mapX[0], S.mapX[1],
+                  S.mapZ[0], S.mapZ[1], a));
   }
   CK(cudaGetLastError());
   mark(h, "img_wgrad_L%d", li);
@@ -437,12 +439,12 @@ static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst) {
   const int grid = std::min(a.n_units, h->sm_count);
   if (dgrad) {
     CK(img_set_smem(dense::dense_stream_kernel<1>, L.total));
-    dense::dense_stream_kernel<1><<<grid, dense::NTHREADS, L.total, h->stream>>>(H->dmapWd[0], H->dmapWd[1], H->dmapDy[0],
-                                                                               H->dmapDy[1], a);
+    CK(launch_pdl(h->pdl, dense::dense_stream_kernel<1>, dim3(grid), dim3(dense::NTHREADS), L.total, h->stream,
+                  H->dmapWd[0], H->dmapWd[1], H->dmapDy[0], H->dmapDy[1], a));
   } else {
     CK(img_set_smem(dense::dense_stream_kernel<0>, L.total));
-    dense::dense_stream_kernel<0><<<grid, dense::NTHREADS, L.total, h->stream>>>(H->dmapWf[0], H->dmapWf[1], H->dmapX[0],
-                                                                               H->dmapX[1], a);
+    CK(launch_pdl(h->pdl, dense::dense_stream_kernel<0>, dim3(grid), dim3(dense::NTHREADS), L.total, h->stream,
+                  H->dmapWf[0], H->dmapWf[1], H->dmapX[0], H->dmapX[1], a));
   }
   CK(cudaGetLastError());
   mark(h, dgrad ? "dense_dgrad_L%d" : "dense_fwd_L%d", li);
