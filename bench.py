@@ -288,7 +288,11 @@ def kernel_roofline(name: str, ms: float, k_heads: int, pk):
     mac = {"fwd_L0": 2 * 3_612_672, "fwd_L1": 2 * 3_964_928, "fwd_L2": 2 * 4_460_544, "fwd_L3": 2 * 3_964_928,
            "wgrad_L0": 3_612_672, "wgrad_L1": 3_964_928, "wgrad_L2": 4_460_544, "wgrad_L3": 3_964_928,
            "dgrad_L1": 3_964_928, "dgrad_L2": 4_460_544, "dgrad_L3": 3_964_928}
-    base = name[3:] if name.startswith("tc_") else name
+    base = name
+    for prefix in ("tc_", "img_", "dense_"):
+        if base.startswith(prefix):
+            base = base[len(prefix):]
+    tensor_path = base != name
     dense0 = 7744 * 512 + 512
     if base.startswith("wgrad_adam"):
         # reads W, mu, nu and writes W, mu, nu of Dense_0 (+ the 1 MB of activations feeding the outer product)
@@ -300,7 +304,7 @@ def kernel_roofline(name: str, ms: float, k_heads: int, pk):
         gb = 7 * n * 4 * k_heads / 1e9
         ach = gb / (ms * 1e-3)
         return {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
-    if base in ("fwd_L3", "dgrad_L3") and name.startswith("tc_"):
+    if base in ("fwd_L3", "dgrad_L3") and tensor_path:
         # weight streaming (M or N = batch 32): bound by reading the 15.9 MB Dense_0 kernel per net
         nets = 2 * k_heads if base == "fwd_L3" else k_heads
         gb = dense0 * 4 * nets / 1e9

@@ -50,6 +50,7 @@ SYMBOLS = {
     "idqn_read_cumulated_losses": (_I, [_P, _P, _I]),
     "idqn_kernels_per_step": (_I, [_P]),
     "idqn_profile_step": (_I, [_P, _I, _I, _P, _P, C.POINTER(_I)]),
+    "idqn_debug_timeline": (_I, [_P, _I]),
     "idqn_shift_params": (_I, [_P]),
     "idqn_sync_target": (_I, [_P]),
     "idqn_copy_online_to_target": (_I, [_P]),

@@ -116,6 +116,9 @@ int idqn_read_cumulated_losses(idqn_handle* h, double* sums_host, int reset);
  * event after every launch -> ms[i] / names[32*i..] per kernel, in launch order (uses the staged batch) */
 int idqn_kernels_per_step(idqn_handle* h);
 int idqn_profile_step(idqn_handle* h, int state_is_u8, int max_entries, float* ms, char* names, int* n_out);
+/* pipeline timeline of CTA 0 of the kernel named by the IDQN_TL environment variable (fwd0..2, dgrad1..2, wgrad0..2,
+ * dfwd3, ddgrad3) during the most recent step: entries (clock64 << 16 | tag), 0 = unused; returns the entry count */
+int idqn_debug_timeline(unsigned long long* out, int max_entries);
 
 /* shift_params (idqn.py:13-17), sync_target_params (idqn.py:20-24), target_params = params.copy() (idqn.py:78) */
 int idqn_shift_params(idqn_handle* h);

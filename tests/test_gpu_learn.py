@@ -136,6 +136,25 @@ def test_nature_cnn_production_path_without_materialised_grads():
     run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 2, 3, 2, 3, 3e-4, 1.5e-4, u8=True, check_grads=False)
 
 
+def test_nature_cnn_generic_tensor_path():
+    """IDQN_F_NO_IMG: the generic tcgen05 implicit-GEMM kernels (gemm_tc.cuh) instead of the image-resident TMA
+    conv kernels and the weight-streaming Dense_0 kernels stay a valid implementation of the same step."""
+    from idqn_b200 import _lib
+    run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 2, 2, 2, 3, 3e-4, 1.5e-4, u8=True, flags=_lib.F_NO_IMG)
+
+
+def test_nature_cnn_programmatic_dependent_launch():
+    """IDQN_F_PDL: the step's kernels launched with programmatic stream serialization (griddepcontrol) give the same step."""
+    from idqn_b200 import _lib
+    run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 3, 3, 2, 3, 3e-4, 1.5e-4, u8=True, flags=_lib.F_PDL,
+               check_grads=False)
+
+
+def test_nature_cnn_k5_production_path():
+    """K = 5 (the benchmark configuration: two head groups on the first layer, split-K Dense_0 summed in the head kernel)."""
+    run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 5, 2, 8, 2, 3e-4, 1.5e-4, u8=True, check_grads=False)
+
+
 def test_nature_cnn_simt_cross_check():
     """the exact-fp32 CUDA-core path (IDQN_F_SIMT_ONLY) stays a valid implementation of the same step."""
     from idqn_b200 import _lib
