@@ -145,6 +145,7 @@ struct idqn_handle {
   __nv_bfloat16 *wpl_hi, *wpl_lo;                    // the allocation behind won_*/wtg_*: [2K][stride], online first
   // image-resident conv path (conv_img.cuh); img_on == 0 -> the generic kernels of gemm_tc.cuh run instead
   int img_on;
+  int img_last;           // the most recent step ran the image path (conv activations live in planes only)
   int pdl;                // launch the step's kernels with programmatic stream serialization
   ImgLayerState il[IDQN_IMG_LAYERS];
   void* img_host;         // ImgHost (net.cu): geometry and kernel arguments of the three conv layers

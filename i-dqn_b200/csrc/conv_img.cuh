@@ -78,7 +78,7 @@ struct TapsArgs {
   // M
   int tiles, tpp, P, M_valid, W_valid;  // tiles per image, tiles per pass, pitch, valid rows, valid columns (ox < W_valid)
   // taps
-  int n_taps, kt;                        // kt = K=16 steps per tap
+  int n_taps, kt, tap_group;             // kt = K=16 steps per tap; taps per ring slot
   int a_shift[MAX_TAPS];                 // rows
   int w_c1[MAX_TAPS], w_c2[MAX_TAPS];    // TMA coordinates (dims 1, 2) of the tap's weight box
   // B tile
@@ -91,7 +91,8 @@ struct TapsArgs {
   NetPtr w;                              // fp32 arenas (bias), fwd
   int64_t b_off;
   float* out;                            // fwd: act (+act_off); dgrad: dact of the previous layer (+act_off)
-  const float* mask;                     // dgrad: act of the previous layer (relu' mask)
+  const bf16* mask_hi;                   // dgrad: X2 hi plane of this layer = its input (relu' mask), [net][img][rows][C2]
+  int64_t mask_net_stride, mask_img_rows;
   int64_t out_net_stride;
   PlaneDst dst;
   int debug;
@@ -107,13 +108,16 @@ __host__ __device__ inline TapsSmem taps_smem(const TapsArgs& p, int a_planes) {
   s.a_plane_bytes = (uint32_t)p.a_halves * p.a_buf_rows * 128;
   s.a_buf_bytes = a_planes * s.a_plane_bytes;
   s.ring_off = 2 * s.a_buf_bytes;
-  s.slot_bytes = round_up(2 * p.hpg * p.b_box_bytes, 1024);
+  s.slot_bytes = round_up(2 * p.hpg * p.b_box_bytes * p.tap_group, 1024);
   s.bar_off = s.ring_off + p.ring * s.slot_bytes;
   s.total = s.bar_off + 256 + 1024;  // barriers + alignment slack
   return s;
 }
 
 // KIND 0: forward (B = weights MN-major, epilogue bias/relu); KIND 1: dgrad (B = weights K-major, epilogue relu').
+// Work is cut into jobs = (unit, M tile); every CTA takes a contiguous, balanced range of jobs, so consecutive jobs
+// reuse the image already resident in shared memory.  Weight tiles arrive in groups of `tap_group` taps per ring
+// slot (one barrier round trip per group).
 // Split products: the hi and lo weight tiles of a tap sit next to each other in the ring slot, so ONE MMA of width
 // 2N computes A_hi*[B_hi | B_lo] (the A tile, the larger operand, is read from shared memory once for both), a
 // second MMA of width N adds A_lo*B_hi into the first N columns; the epilogue sums the two column sets.
@@ -136,10 +140,14 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int passes = (p.tiles + p.tpp - 1) / p.tpp;
-  const int N = p.N, N2 = 2 * p.N;   // accumulator columns per tile: [0,N) hi*hi + lo*hi, [N,2N) hi*lo
+  const int N = p.N, N2 = 2 * p.N;   // accumulator columns per job: [0,N) hi*hi + lo*hi, [N,2N) hi*lo
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.tpp * N2) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * N2) tmem_cols <<= 1;
+  const int n_groups = (p.n_taps + p.tap_group - 1) / p.tap_group;
+  const uint32_t tap_bytes = 2u * p.hpg * p.b_box_bytes;  // hi boxes then lo boxes of one tap
+  // this CTA's jobs
+  const int J = p.n_units * p.tiles;
+  const int j0 = (int)((int64_t)blockIdx.x * J / gridDim.x), j1 = (int)((int64_t)(blockIdx.x + 1) * J / gridDim.x);
 
   // rows of an M tile past the image read whatever follows in shared memory (the other buffer, the ring): they only
   // produce accumulator rows that the epilogue drops
@@ -160,14 +168,15 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   if (tid == 0) tl_stamp(p.debug, 1);
 
   if (warp == 0) {
-    // ===== image producer =====
+    // ===== image producer: one load per unit this CTA touches =====
     if (elect_one()) {
       pdl_wait();  // the image is produced by the preceding kernels (the weight tiles of warp 1 are not)
-      int i = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
-        const int xb = i & 1;
-        mbar_wait(&x_empty[xb], ((i >> 1) & 1) ^ 1);
-        tl_stamp(p.debug, 1000 + i);
+      int xi = 0;
+      for (int j = j0; j < j1; ++j) {
+        if (j != j0 && j % p.tiles != 0) continue;
+        const int u = j / p.tiles, xb = xi & 1;
+        mbar_wait(&x_empty[xb], ((xi >> 1) & 1) ^ 1);
+        tl_stamp(p.debug, 1000 + xi);
         const int gi = u / p.n_hg;  // (g, img) linear
         const uint32_t bytes = (uint32_t)A_PLANES * p.a_halves * p.a_chunks * p.a_chunk_rows * 128;
         tma::expect_tx(&x_full[xb], bytes);
@@ -179,189 +188,209 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                                    (uint32_t)ch * p.a_chunk_rows * 128;
               tma::load_3d(dst, pl ? &mapA_lo : &mapA_hi, &x_full[xb], 0, hf, row0 + ch * p.a_chunk_rows);
             }
+        ++xi;
       }
     }
   } else if (warp == 1) {
-    // ===== weight-tap producer =====
+    // ===== weight producer: groups of taps per ring slot =====
     if (elect_one()) {
-      int ws = 0, ui = 0;
+      int ws = 0;
       uint32_t wphase = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ui) {
+      for (int j = j0; j < j1; ++j) {
+        const int u = j / p.tiles;
         const int hg = u % p.n_hg, g = (u / p.n_hg) / p.imgs;
         const int net0 = g * p.nets_per_g + hg * p.hpg;
         const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
-        for (int ps = 0; ps < passes; ++ps)
-          for (int t = 0; t < p.n_taps; ++t) {
-            mbar_wait(&w_empty[ws], wphase ^ 1);
-            tl_stamp(p.debug, 2000 + (ui * passes + ps) * 16 + t);
-            tma::expect_tx(&w_full[ws], 2u * nb * p.b_box_bytes);
-            const uint32_t slot = base + L.ring_off + ws * L.slot_bytes;
-            for (int j = 0; j < nb; ++j) {
-              tma::load_4d(slot + j * p.b_box_bytes, &mapW_hi, &w_full[ws], 0, p.w_c1[t], p.w_c2[t], net0 + j);
-              tma::load_4d(slot + (p.hpg + j) * p.b_box_bytes, &mapW_lo, &w_full[ws], 0, p.w_c1[t], p.w_c2[t], net0 + j);
+        for (int grp = 0; grp < n_groups; ++grp) {
+          mbar_wait(&w_empty[ws], wphase ^ 1);
+          tl_stamp(p.debug, 2000 + (j - j0) * 16 + grp);
+          const int tg0 = grp * p.tap_group, tg1 = min(p.n_taps, tg0 + p.tap_group);
+          tma::expect_tx(&w_full[ws], 2u * nb * p.b_box_bytes * (tg1 - tg0));
+          for (int t = tg0; t < tg1; ++t) {
+            const uint32_t slot = base + L.ring_off + ws * L.slot_bytes + (uint32_t)(t - tg0) * tap_bytes;
+            for (int jn = 0; jn < nb; ++jn) {
+              tma::load_4d(slot + jn * p.b_box_bytes, &mapW_hi, &w_full[ws], 0, p.w_c1[t], p.w_c2[t], net0 + jn);
+              tma::load_4d(slot + (p.hpg + jn) * p.b_box_bytes, &mapW_lo, &w_full[ws], 0, p.w_c1[t], p.w_c2[t], net0 + jn);
             }
-            if (++ws == p.ring) ws = 0, wphase ^= 1;
           }
+          if (++ws == p.ring) ws = 0, wphase ^= 1;
+        }
       }
     }
   } else if (warp == 2) {
     // ===== MMA issuer: one elected lane walks the whole pipeline =====
-    if (elect_one()) {
+    if (elect_one() && j0 < j1) {
       const uint32_t idesc2 = make_idesc_bf16(128, N2, false, KIND == 0);  // A_hi * [B_hi | B_lo]
       const uint32_t idesc1 = make_idesc_bf16(128, N, false, KIND == 0);   // A_lo * B_hi
       const uint32_t b_lt = p.b_row_bytes == 128 ? tma::LT_SW128 : tma::LT_SW64;
       const uint32_t a_hi32 = tma::desc_hi32(1024, tma::LT_SW128), b_hi32 = tma::desc_hi32(8 * p.b_row_bytes, b_lt);
       const uint32_t half16 = (uint32_t)p.a_buf_rows * 8;                 // next 64-channel half of the image
       const uint32_t bstep = KIND == 0 ? p.b_row_bytes : 2u;              // K = 16 step of B: 16 rows (MN-major) or 32 bytes
-      int i = 0, ws = 0, ai = 0;
+      int xi = 0, ws = 0, ai = 0;
       uint32_t wphase = 0;
-      const bool any = blockIdx.x < p.n_units;
-      if (any) {  // waits of the very first step
-        mbar_wait(&x_full[0], 0);
-        mbar_wait(&w_full[0], 0);
-        tcgen05_after_sync();
-      }
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
-        const int xb = i & 1;
-        const bool last_unit = u + (int)gridDim.x >= p.n_units;
+      mbar_wait(&x_full[0], 0);  // waits of the very first group
+      mbar_wait(&w_full[0], 0);
+      tcgen05_after_sync();
+      for (int j = j0; j < j1; ++j, ++ai) {
+        const int tile = j % p.tiles, xb = xi & 1, ab = ai & 1;
+        const bool last_job = j == j1 - 1, unit_ends = last_job || tile == p.tiles - 1;
         const uint32_t a_hi = base + xb * L.a_buf_bytes, a_lo = a_hi + L.a_plane_bytes;
-        for (int ps = 0; ps < passes; ++ps, ++ai) {
-          const int ab = ai & 1;
-          const int t0 = ps * p.tpp, t1 = min(p.tiles, t0 + p.tpp);
-          for (int t = 0; t < p.n_taps; ++t) {
-            tl_stamp(p.debug, 3000 + ai * 32 + t);
-            const uint32_t b_hi = base + L.ring_off + ws * L.slot_bytes;
+        const uint32_t d = tmem + (uint32_t)ab * N2;
+        for (int grp = 0; grp < n_groups; ++grp) {
+          tl_stamp(p.debug, 3000 + ai * 32 + grp);
+          const int tg0 = grp * p.tap_group, tg1 = min(p.n_taps, tg0 + p.tap_group);
+          for (int t = tg0; t < tg1; ++t) {
+            const uint32_t b_hi = base + L.ring_off + ws * L.slot_bytes + (uint32_t)(t - tg0) * tap_bytes;
             // descriptor low words; offsets in 16-byte units.  B: N groups at LBO = box bytes (hi boxes then lo boxes)
-            const uint32_t bh0 = tma::desc_lo32(b_hi, p.b_box_bytes);
-            const uint32_t ah0 = tma::desc_lo32(a_hi, 16) + (uint32_t)p.a_shift[t] * 8;
-            const uint32_t al0 = tma::desc_lo32(a_lo, 16) + (uint32_t)p.a_shift[t] * 8;
-            for (int tile = t0; tile < t1; ++tile) {
-              const uint32_t d = tmem + (uint32_t)(ab * p.tpp + (tile - t0)) * N2;
-              uint32_t ah = ah0 + (uint32_t)tile * 1024, al = al0 + (uint32_t)tile * 1024, bh = bh0;
-              for (int j4 = 0; j4 < p.kt; j4 += 4) {
+            uint32_t bh = tma::desc_lo32(b_hi, p.b_box_bytes);
+            uint32_t ah = tma::desc_lo32(a_hi, 16) + (uint32_t)p.a_shift[t] * 8 + (uint32_t)tile * 1024;
+            uint32_t al = tma::desc_lo32(a_lo, 16) + (uint32_t)p.a_shift[t] * 8 + (uint32_t)tile * 1024;
+            for (int j4 = 0; j4 < p.kt; j4 += 4) {
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  if (t == 0 && j4 == 0 && jj == 0) tma::mma_bf16_split<false>(d, ah, a_hi32, bh, b_hi32, idesc2);
-                  else tma::mma_bf16_split<true>(d, ah + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc2);
-                  if (A_PLANES == 2) tma::mma_bf16_split<true>(d, al + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc1);
-                }
-                ah += half16, al += half16, bh += 4 * bstep;
+              for (int jj = 0; jj < 4; ++jj) {
+                if (t == 0 && j4 == 0 && jj == 0) tma::mma_bf16_split<false>(d, ah, a_hi32, bh, b_hi32, idesc2);
+                else tma::mma_bf16_split<true>(d, ah + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc2);
+                if (A_PLANES == 2) tma::mma_bf16_split<true>(d, al + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc1);
               }
-            }
-            mma_commit(&w_empty[ws]);
-            const bool last_tap = t == p.n_taps - 1, last_pass = ps == passes - 1;
-            if (last_tap) {
-              mma_commit(&acc_full[ab]);
-              if (last_pass) mma_commit(&x_empty[xb]);
-            }
-            tl_stamp(p.debug, 3000 + ai * 32 + 16 + t);
-            if (++ws == p.ring) ws = 0, wphase ^= 1;
-            // waits of the NEXT step, issued while the MMAs just queued drain
-            if (!(last_tap && last_pass && last_unit)) {
-              if (last_tap) {
-                const int an = ai + 1;
-                mbar_wait(&acc_empty[an & 1], ((an >> 1) & 1) ^ 1);
-                if (last_pass) mbar_wait(&x_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-              }
-              mbar_wait(&w_full[ws], wphase);
-              tcgen05_after_sync();
+              ah += half16, al += half16, bh += 4 * bstep;
             }
           }
+          mma_commit(&w_empty[ws]);
+          const bool last_grp = grp == n_groups - 1;
+          if (last_grp) {
+            mma_commit(&acc_full[ab]);
+            if (unit_ends) mma_commit(&x_empty[xb]);
+          }
+          tl_stamp(p.debug, 3000 + ai * 32 + 16 + grp);
+          if (++ws == p.ring) ws = 0, wphase ^= 1;
+          // waits of the NEXT group, issued while the MMAs just queued drain
+          if (!(last_grp && last_job)) {
+            if (last_grp) {
+              const int an = ai + 1;
+              mbar_wait(&acc_empty[an & 1], ((an >> 1) & 1) ^ 1);
+              if (unit_ends) {
+                const int xn = xi + 1;
+                mbar_wait(&x_full[xn & 1], (xn >> 1) & 1);
+              }
+            }
+            mbar_wait(&w_full[ws], wphase);
+            tcgen05_after_sync();
+          }
         }
+        if (unit_ends) ++xi;
       }
     }
     __syncwarp();
-    pdl_trigger();  // the bulk of this CTA's work is queued: let the next kernel's CTAs start their prologue
+    pdl_trigger();  // the bulk of this CTA's work is queued
   } else {
     // ===== epilogue warps 3..6: TMEM lane quadrant = warp % 4 =====
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row inside the tile
-    int ai = 0;
     pdl_wait();
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    int ai = 0;
+    for (int j = j0; j < j1; ++j, ++ai) {
+      const int u = j / p.tiles, tile = j - u * p.tiles;
       const int hg = u % p.n_hg, gi = u / p.n_hg, g = gi / p.imgs, im = gi - g * p.imgs;
       const int net0 = g * p.nets_per_g + hg * p.hpg;
       const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
-      for (int ps = 0; ps < passes; ++ps, ++ai) {
-        const int ab = ai & 1;
-        mbar_wait(&acc_full[ab], (ai >> 1) & 1);
-        tcgen05_after_sync();
-        if (warp == 3 && lane == 0) tl_stamp(p.debug, 1200 + 2 * ai);
-        const int t0 = ps * p.tpp, t1 = min(p.tiles, t0 + p.tpp);
-        for (int tile = t0; tile < t1; ++tile) {
-          const int m = tile * 128 + r;
-          const int my = m / p.P, mx = m - my * p.P;
-          const bool rowok = m < p.M_valid && mx < p.W_valid;
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tpp + (tile - t0)) * N2;
-          // per-row bases, computed once per tile
-          int64_t orow = 0, prow = 0;
-          if (KIND == 0) {
-            orow = (((int64_t)im * p.OH + my) * p.OW + mx) * p.OC;
-            prow = plane_index(p.dst, 0, im, my, mx);
+      const int ab = ai & 1;
+      mbar_wait(&acc_full[ab], (ai >> 1) & 1);
+      tcgen05_after_sync();
+      if (warp == 3 && lane == 0) tl_stamp(p.debug, 1200 + 2 * ai);
+      const int m = tile * 128 + r;
+      const int my = m / p.P, mx = m - my * p.P;
+      const bool rowok = m < p.M_valid && mx < p.W_valid;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * N2;
+      // per-row bases, computed once per tile
+      int64_t orow = 0, prow = 0;
+      if (KIND == 0) {
+        orow = (((int64_t)im * p.OH + my) * p.OW + mx) * p.OC;
+        prow = plane_index(p.dst, 0, im, my, mx);
+      }
+      // 32 columns per iteration; every load of the iteration (TMEM, bias / relu mask) is issued before the first
+      // use so the four epilogue warps expose one memory latency per iteration, not one per access
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32], v2[32];
+        tmem_ld16_nowait(taddr + c0, v);
+        tmem_ld16_nowait(taddr + c0 + 16, v + 16);
+        tmem_ld16_nowait(taddr + N + c0, v2);
+        tmem_ld16_nowait(taddr + N + c0 + 16, v2 + 16);
+        if (KIND == 0) {
+          const int hl = c0 / p.OC, oc = c0 - hl * p.OC;  // 32 | OC: the 32 columns stay inside one head
+          const bool ok = rowok && hl < nb;
+          const int net = net0 + (ok ? hl : 0);
+          const float4* bias = reinterpret_cast<const float4*>(p.w.get<float>(net) + p.b_off + oc);
+          float4 bb[8];
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) bb[k4] = __ldg(bias + k4);
+          tmem_ld_wait();
+          if (!ok) continue;
+          float o[32];
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            o[4 * k4] = fmaxf(fmaf(v[4 * k4] + v2[4 * k4], p.scale, bb[k4].x), 0.f);
+            o[4 * k4 + 1] = fmaxf(fmaf(v[4 * k4 + 1] + v2[4 * k4 + 1], p.scale, bb[k4].y), 0.f);
+            o[4 * k4 + 2] = fmaxf(fmaf(v[4 * k4 + 2] + v2[4 * k4 + 2], p.scale, bb[k4].z), 0.f);
+            o[4 * k4 + 3] = fmaxf(fmaf(v[4 * k4 + 3] + v2[4 * k4 + 3], p.scale, bb[k4].w), 0.f);
           }
-          for (int c0 = 0; c0 < N; c0 += 16) {
-            float v[16], v2[16];
-            tmem_ld16_nowait(taddr + c0, v);
-            tmem_ld16_nowait(taddr + N + c0, v2);
-            tmem_ld_wait();
-            if (!rowok) continue;
+          if (p.out) {  // fp32 copy only on request: the planes carry the activation (row-per-thread stores are costly)
+            float* dst = p.out + (int64_t)net * p.out_net_stride + orow + oc;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] += v2[e];
-            if (KIND == 0) {
-              const int hl = c0 / p.OC, oc = c0 - hl * p.OC;
-              if (hl >= nb) continue;
-              const int net = net0 + hl;
-              const float* bias = p.w.get<float>(net) + p.b_off + oc;
-              float o[16];
+            for (int k4 = 0; k4 < 8; ++k4)
+              reinterpret_cast<float4*>(dst)[k4] = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
+          }
+          const int64_t pi = (int64_t)net * p.dst.net_stride + prow + oc;
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + k4);
-                o[4 * k4] = fmaxf(fmaf(v[4 * k4], p.scale, bb.x), 0.f);
-                o[4 * k4 + 1] = fmaxf(fmaf(v[4 * k4 + 1], p.scale, bb.y), 0.f);
-                o[4 * k4 + 2] = fmaxf(fmaf(v[4 * k4 + 2], p.scale, bb.z), 0.f);
-                o[4 * k4 + 3] = fmaxf(fmaf(v[4 * k4 + 3], p.scale, bb.w), 0.f);
-              }
-              float* dst = p.out + (int64_t)net * p.out_net_stride + orow + oc;
+          for (int h8 = 0; h8 < 4; ++h8) {
+            uint4 hh, ll;
+            split8(o + 8 * h8, hh, ll);
+            reinterpret_cast<uint4*>(p.dst.hi + pi)[h8] = hh;
+            reinterpret_cast<uint4*>(p.dst.lo + pi)[h8] = ll;
+          }
+        } else {
+          // row = block (my, mx) of the layer input; columns (ry, rx, c): 32 channels of one input pixel (32 | IC)
+          const int blk = c0 / p.OC, c = c0 - blk * p.OC;
+          const int ry = blk / p.s, rx = blk - ry * p.s;
+          const int iy = my * p.s + ry - p.ph, ix = mx * p.s + rx - p.pw;
+          const bool ok = rowok && (unsigned)iy < (unsigned)p.IH && (unsigned)ix < (unsigned)p.IW;
+          // relu' mask: the layer input is this very row of the X2 hi plane (hi > 0 <=> x > 0), 32 contiguous bf16
+          const int64_t mi = ok ? (int64_t)g * p.mask_net_stride + (((int64_t)im * p.mask_img_rows) + m) * N + c0 : 0;
+          uint4 xa[4];
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                reinterpret_cast<float4*>(dst)[k4] = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
-              const int64_t pi = (int64_t)net * p.dst.net_stride + prow + oc;
-              uint4 h0, l0, h1, l1;
-              split8(o, h0, l0);
-              split8(o + 8, h1, l1);
-              reinterpret_cast<uint4*>(p.dst.hi + pi)[0] = h0, reinterpret_cast<uint4*>(p.dst.hi + pi)[1] = h1;
-              reinterpret_cast<uint4*>(p.dst.lo + pi)[0] = l0, reinterpret_cast<uint4*>(p.dst.lo + pi)[1] = l1;
-            } else {
-              // row = block (my, mx) of the layer input; columns (ry, rx, c): 16 channels of one input pixel
-              const int blk = c0 / p.OC, c = c0 - blk * p.OC;
-              const int ry = blk / p.s, rx = blk - ry * p.s;
-              const int iy = my * p.s + ry - p.ph, ix = mx * p.s + rx - p.pw;
-              if ((unsigned)iy >= (unsigned)p.IH || (unsigned)ix >= (unsigned)p.IW) continue;
-              const int64_t oi = (int64_t)g * p.out_net_stride + (((int64_t)im * p.IH + iy) * p.IW + ix) * p.OC + c;
-              float o[16];
+          for (int k4 = 0; k4 < 4; ++k4) xa[k4] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + mi) + k4);
+          tmem_ld_wait();
+          if (!ok) continue;
+          float o[32];
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                const float4 xa = __ldg(reinterpret_cast<const float4*>(p.mask + oi) + k4);
-                o[4 * k4] = xa.x > 0.f ? v[4 * k4] : 0.f, o[4 * k4 + 1] = xa.y > 0.f ? v[4 * k4 + 1] : 0.f;
-                o[4 * k4 + 2] = xa.z > 0.f ? v[4 * k4 + 2] : 0.f, o[4 * k4 + 3] = xa.w > 0.f ? v[4 * k4 + 3] : 0.f;
-              }
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t w[4] = {xa[k4].x, xa[k4].y, xa[k4].z, xa[k4].w};
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                reinterpret_cast<float4*>(p.out + oi)[k4] = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
-              const int64_t pi = plane_index(p.dst, g, im, iy, ix) + c;
-              uint4 h0, l0, h1, l1;
-              split8(o, h0, l0);
-              split8(o + 8, h1, l1);
-              reinterpret_cast<uint4*>(p.dst.hi + pi)[0] = h0, reinterpret_cast<uint4*>(p.dst.hi + pi)[1] = h1;
-              reinterpret_cast<uint4*>(p.dst.lo + pi)[0] = l0, reinterpret_cast<uint4*>(p.dst.lo + pi)[1] = l1;
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t bits = (w[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+              const bool pos = bits != 0 && !(bits & 0x8000u);  // bf16 > 0
+              o[8 * k4 + e] = pos ? v[8 * k4 + e] + v2[8 * k4 + e] : 0.f;
             }
           }
+          if (p.out) {
+            const int64_t oi = (int64_t)g * p.out_net_stride + (((int64_t)im * p.IH + iy) * p.IW + ix) * p.OC + c;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4)
+              reinterpret_cast<float4*>(p.out + oi)[k4] = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
+          }
+          const int64_t pi = plane_index(p.dst, g, im, iy, ix) + c;
+#pragma unroll
+          for (int h8 = 0; h8 < 4; ++h8) {
+            uint4 hh, ll;
+            split8(o + 8 * h8, hh, ll);
+            reinterpret_cast<uint4*>(p.dst.hi + pi)[h8] = hh;
+            reinterpret_cast<uint4*>(p.dst.lo + pi)[h8] = ll;
+          }
         }
-        tcgen05_before_sync();
-        __syncwarp();
-        if (warp == 3 && lane == 0) tl_stamp(p.debug, 1201 + 2 * ai);
-        if (lane == 0) tma::arrive(&acc_empty[ab]);
       }
+      tcgen05_before_sync();
+      __syncwarp();
+      if (warp == 3 && lane == 0) tl_stamp(p.debug, 1201 + 2 * ai);
+      if (lane == 0) tma::arrive(&acc_empty[ab]);
     }
   }
   tcgen05_before_sync();
@@ -625,6 +654,22 @@ __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
       *reinterpret_cast<uint4*>(a.hi + o + e) = h;
       if (!a.u8) *reinterpret_cast<uint4*>(a.lo + o + e) = l;
     }
+  }
+}
+
+// fp32 NHWC activation from the planes of its consumer layout (debug / parity: idqn_download_activation)
+__global__ void __launch_bounds__(256) planes_to_f32_kernel(const PlaneDst d, int net, int imgs, int H, int W, int C,
+                                                            float* __restrict__ out) {
+  const int64_t total = (int64_t)imgs * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int c = (int)(t % C);
+    t /= C;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y = (int)(t % H), im = (int)(t / H);
+    const int64_t pi = plane_index(d, net, im, y, x) + c;
+    out[i] = __bfloat162float(d.hi[pi]) + __bfloat162float(d.lo[pi]);
   }
 }
 

@@ -36,7 +36,8 @@ struct Args {
   float* y;             // [nets][ystride]  (fwd)  /  dx [heads][xstride] (dgrad)
   bf16 *yh, *yl;        // planes of the output
   int64_t ystride;
-  const float* xact;    // dgrad: layer input (relu output), same indexing as dx
+  const float* xact;    // dgrad: layer input (relu output), same indexing as dx; or
+  const bf16* xmask_hi; // its bf16 hi plane (hi > 0 <=> x > 0)
   float* part;          // fwd: [nets*tiles][splits][32][128]
   int* tickets;         // fwd: [nets*tiles]
   // dgrad planes destination: dyZ layout of the preceding conv layer (zP > 0) or plain
@@ -206,11 +207,25 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
             zrow = (int64_t)net * p.zstride + ((int64_t)(yy + p.zOff) * p.zP + xx + p.zOff) * p.zC + ch;
           }
           const int64_t x0 = (int64_t)net * p.ystride + row;
+          // relu' mask of all 32 samples first (independent loads in flight together), then the stores
+          uint32_t posmask = 0;
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
             const int64_t idx = x0 + (int64_t)b * p.I;
-            const float o = __ldg(p.xact + idx) > 0.f ? v[b] : 0.f;
-            p.y[idx] = o;
+            bool pos;
+            if (p.xmask_hi) {
+              const unsigned short bits = __ldg(reinterpret_cast<const unsigned short*>(p.xmask_hi) + idx);
+              pos = bits != 0 && !(bits & 0x8000u);  // bf16 > 0
+            } else {
+              pos = __ldg(p.xact + idx) > 0.f;
+            }
+            posmask |= (pos ? 1u : 0u) << b;
+          }
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const int64_t idx = x0 + (int64_t)b * p.I;
+            const float o = ((posmask >> b) & 1u) ? v[b] : 0.f;
+            if (p.y) p.y[idx] = o;
             const int64_t pi = p.zP > 0 ? zrow + (int64_t)b * p.zRows * p.zC : idx;
             st1_planes(p.yh + pi, p.yl + pi, o);
           }

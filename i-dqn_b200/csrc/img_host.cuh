@@ -32,7 +32,7 @@ static bool img_geom(const Layer& l, int layer_index, img::Geom& g) {
   g.IC = c.IC, g.OC = c.OC, g.C2 = c.S * c.S * c.IC;
   if (g.C2 != 64 && g.C2 != 128) return false;
   if (g.OC != 32 && g.OC != 64) return false;
-  if (layer_index > 0 && (g.OC != 64 || g.IC % 16)) return false;  // dgrad: 128-byte dy rows, 16-channel chunks
+  if (layer_index > 0 && (g.OC != 64 || g.IC % 32)) return false;  // dgrad: 128-byte dy rows, 32-channel epilogue chunks
   const int run = c.S * c.IC;
   if (run > 64 || 64 % run) return false;
   if (g.T * g.T > img::MAX_TAPS) return false;
@@ -160,7 +160,7 @@ static int img_setup(idqn_handle* h) {
       a.scale = li == 0 ? 1.0f / 255.0f : 1.0f;  // architectures/dqn.py:44
       a.w = NetPtr{h->online, h->target, h->stride, h->stride, K};
       a.b_off = l.b_off;
-      a.out = h->act + l.act_off, a.out_net_stride = h->act_stride, a.mask = nullptr;
+      a.out = nullptr, a.out_net_stride = h->act_stride, a.mask_hi = nullptr;  // fp32 copy: idqn_download_activation rebuilds it
       if (li + 1 < IDQN_IMG_LAYERS) {
         const img::Geom& n = H->g[li + 1];
         a.dst = img::PlaneDst{h->il[li + 1].x2_hi, h->il[li + 1].x2_lo, h->il[li + 1].x2_net_stride, n.XRa,
@@ -169,10 +169,12 @@ static int img_setup(idqn_handle* h) {
         a.dst = img::PlaneDst{h->act_hi + l.act_off, h->act_lo + l.act_off, h->act_stride, (int64_t)g.OH * g.OW,
                               1, 0, 0, g.OW, g.OC, g.OC};
       }
-      // ring depth: what fits next to the two image buffers
-      const uint32_t slot = img::round_up(2 * a.hpg * a.b_box_bytes, 1024);
+      // taps per ring slot (one ty row if two such slots fit next to the two image buffers), then the ring depth
       const uint32_t abuf2 = 2u * (li == 0 ? 1 : 2) * a.a_halves * a.a_buf_rows * 128;  // layer 0: uint8 frames, hi plane only
-      a.ring = (int)std::min<size_t>(4, (IMG_SMEM_MAX - 2048 - abuf2) / slot);
+      a.tap_group = g.T;
+      if (2 * img::round_up(2 * a.hpg * a.b_box_bytes * a.tap_group, 1024) + abuf2 + 2048 > IMG_SMEM_MAX) a.tap_group = 1;
+      const uint32_t slot = img::round_up(2 * a.hpg * a.b_box_bytes * a.tap_group, 1024);
+      a.ring = (int)std::min<size_t>(a.tap_group > 1 ? 2 : 4, (IMG_SMEM_MAX - 2048 - abuf2) / slot);
       const int over = a.tiles * 128 + a.a_shift[a.n_taps - 1] - a.a_buf_rows;
       if (a.ring < 2 || over * 128 > (int)(a.ring * slot)) {
         idqn_set_error("internal: image path does not fit shared memory (fwd L%d)", li);
@@ -204,12 +206,16 @@ static int img_setup(idqn_handle* h) {
       a.OC = g.IC, a.s = g.s, a.ph = g.ph, a.pw = g.pw, a.IH = g.IH, a.IW = g.IW;
       a.OH = g.OH, a.OW = g.OW;
       a.scale = 1.f;
-      a.out = h->dact + prev.act_off, a.mask = h->act + prev.act_off, a.out_net_stride = h->act_stride;
+      a.out = nullptr, a.out_net_stride = h->act_stride;  // the fp32 gradient is not needed: dyZ planes carry it
+      a.mask_hi = h->il[li].x2_hi, a.mask_net_stride = h->il[li].x2_net_stride, a.mask_img_rows = g.XRa;
+      (void)prev;
       a.dst = img::PlaneDst{h->il[li - 1].dz_hi, h->il[li - 1].dz_lo, h->il[li - 1].dz_net_stride, pg.ZRa,
                             1, pg.T - 1, pg.T - 1, pg.P, pg.OC, pg.OC};
-      const uint32_t slot = img::round_up(2 * a.b_box_bytes, 1024);
       const uint32_t abuf2 = 2u * 2 * a.a_buf_rows * 128;
-      a.ring = (int)std::min<size_t>(4, (IMG_SMEM_MAX - 2048 - abuf2) / slot);
+      a.tap_group = g.T;
+      if (2 * img::round_up(2 * a.b_box_bytes * a.tap_group, 1024) + abuf2 + 2048 > IMG_SMEM_MAX) a.tap_group = 1;
+      const uint32_t slot = img::round_up(2 * a.b_box_bytes * a.tap_group, 1024);
+      a.ring = (int)std::min<size_t>(a.tap_group > 1 ? 2 : 4, (IMG_SMEM_MAX - 2048 - abuf2) / slot);
       const int over = a.tiles * 128 + shmax - a.a_buf_rows;
       if (a.ring < 2 || over * 128 > (int)(a.ring * slot)) {
         idqn_set_error("internal: image path does not fit shared memory (dgrad L%d)", li);
@@ -321,7 +327,7 @@ static int img_setup(idqn_handle* h) {
         a.n_units = a.nets * a.tiles;
         a.stages = 5;
         a.I = I, a.O = O;
-        a.y = h->dact + prev.act_off, a.xact = h->act + prev.act_off, a.ystride = h->act_stride;
+        a.y = h->dact + prev.act_off, a.xact = nullptr, a.xmask_hi = h->act_hi + prev.act_off, a.ystride = h->act_stride;
         a.yh = h->dact_hi + prev.act_off, a.yl = h->dact_lo + prev.act_off;
         a.zP = 0;
       }
@@ -385,7 +391,7 @@ static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes) {
   a.debug = img_debug_on(dgrad ? "dgrad" : "fwd", li);
   const ImgLayerState& S = h->il[li];
   const img::TapsSmem L = img::taps_smem(a, a_planes);
-  const int grid = std::min(a.n_units, h->sm_count);
+  const int grid = std::min(a.n_units * a.tiles, h->sm_count);
   const CUtensorMap* mA = dgrad ? S.mapZ : S.mapX;
 #define IMG_TAPS_LAUNCH(KIND, PL)                                                                            \
   do {                                                                                                       \
@@ -448,5 +454,18 @@ static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst) {
   }
   CK(cudaGetLastError());
   mark(h, dgrad ? "dense_dgrad_L%d" : "dense_fwd_L%d", li);
+  return IDQN_OK;
+}
+
+// rebuild the fp32 activation of conv layer `layer` of net `net` from the planes the image path wrote
+static int img_rebuild_activation(idqn_handle* h, int net, int layer) {
+  ImgHost* H = (ImgHost*)h->img_host;
+  const img::Geom& g = H->g[layer];
+  img::PlaneDst d = H->fwd[layer].dst;
+  float* out = h->act + (int64_t)net * h->act_stride + h->layers[layer].act_off;
+  const int64_t total = (int64_t)h->B * g.OH * g.OW * g.OC;
+  img::planes_to_f32_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 4096), 256, 0, h->stream>>>(d, net, h->B, g.OH, g.OW,
+                                                                                                 g.OC, out);
+  CK(cudaGetLastError());
   return IDQN_OK;
 }

@@ -747,6 +747,7 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   // image-resident TMA conv kernels for the conv stack (uint8 frames); the generic kernels otherwise
   const bool use_img = h->img_on && x_u8 && !dry;
   const int n_img = use_img ? IDQN_IMG_LAYERS : 0;
+  if (!dry) h->img_last = use_img;
   // bf16 planes of the staged batch (operand of the first layer's tensor-core kernels)
   const bool in_planes = use_tc(h) && (tc_conv_ok(h->layers[0]) || tc_dense_ok(h, h->layers[0]));
   if (use_img) {
@@ -1106,6 +1107,10 @@ extern "C" int idqn_download_activation(idqn_handle* h, int net, int layer, floa
   REQUIRE(net >= 0 && net < 2 * h->K && layer >= 0 && layer < h->n_layers - 1, "bad net/layer");
   REQUIRE(n >= 0 && n <= h->layers[layer].act_size, "too many elements");
   CK(cudaSetDevice(h->cfg.device));
+  if (h->img_on && h->img_last && layer < IDQN_IMG_LAYERS) {  // the image path keeps conv activations as planes
+    int rc = img_rebuild_activation(h, net, layer);
+    if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(dst, h->act + (int64_t)net * h->act_stride + h->layers[layer].act_off, sizeof(float) * n,
                      cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
