@@ -401,8 +401,9 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 // ------------------------------------------------------------------------------------------------------
 // weight gradient.  CTA = (head z, image range); accumulators of all M tiles live in TMEM across the images.
 struct WgradArgs {
-  int heads, groups, imgs;          // grid = heads * groups; CTA handles images [gidx*ipg, min(imgs, +ipg))
+  int heads, groups, imgs;          // grid = heads * groups * tsplit; CTA handles images [gidx*ipg, min(imgs, +ipg))
   int ipg;
+  int tsplit, tps;                  // the layer's M tiles are split over tsplit CTAs, tps tiles each
   int x_shared;                     // 1: every head reads the same X2 images (first layer: the staged batch)
   // images
   int x_rows_alloc, x_chunks, x_chunk_rows, x_halves, x_buf_rows;
@@ -437,6 +438,9 @@ __host__ __device__ inline WgradSmem wgrad_smem(const WgradArgs& p, int a_planes
   return s;
 }
 
+// CTA = (head z, image range, tile split ts): tiles [ts*tps, (ts+1)*tps) of the layer, the last split also owns the
+// bias tile.  Per K = 16 step and tile: X_hi^T * [dy_hi | dy_lo] (one MMA, width 2N; the two dy planes are N groups
+// LBO = plane bytes apart) + X_lo^T * dy_hi (width N); the epilogue sums the two column sets.
 template <int A_PLANES>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
@@ -454,9 +458,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
 
   pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int z = blockIdx.x / p.groups, gidx = blockIdx.x - z * p.groups;
+  const int ts = blockIdx.x % p.tsplit, zg = blockIdx.x / p.tsplit;
+  const int z = zg / p.groups, gidx = zg - z * p.groups;
   const int im0 = gidx * p.ipg, im1 = min(p.imgs, im0 + p.ipg);
-  const int ncols = (p.n_tiles + 1) * p.N;  // + bias tile
+  const int t_lo = ts * p.tps, t_hi = min(p.n_tiles, t_lo + p.tps);
+  const int nt = t_hi - t_lo;                  // tiles of this CTA
+  const bool has_bias = ts == p.tsplit - 1;    // + the bias tile
+  const int N = p.N, N2 = 2 * p.N;
+  const int ncols = (nt + (has_bias ? 1 : 0)) * N2;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < ncols) tmem_cols <<= 1;
 
@@ -505,45 +514,46 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
     }
   } else if (warp == 1) {
     {
-      const uint32_t idesc = make_idesc_bf16(128, p.N, true, true);
+      const uint32_t idesc2 = make_idesc_bf16(128, N2, true, true), idesc1 = make_idesc_bf16(128, N, true, true);
       const uint32_t z_lt = p.z_row_bytes == 128 ? tma::LT_SW128 : tma::LT_SW64;
       const uint32_t x_hi32 = tma::desc_hi32(1024, tma::LT_SW128), z_hi32 = tma::desc_hi32(8 * p.z_row_bytes, z_lt);
       // per tile: descriptor low word of the hi plane at k = 0 (start address | LBO = distance to the second M group)
       uint32_t xlo[MAX_TAPS];
 #pragma unroll
       for (int t = 0; t < MAX_TAPS; ++t) {
-        if (t < p.n_tiles) {
-          const uint32_t o0 = (uint32_t)p.hf0[t] * p.x_buf_rows * 128 + (uint32_t)p.sh0[t] * 128;
-          const uint32_t o1 = (uint32_t)p.hf1[t] * p.x_buf_rows * 128 + (uint32_t)p.sh1[t] * 128;
+        if (t < nt) {
+          const int tt = t_lo + t;
+          const uint32_t o0 = (uint32_t)p.hf0[tt] * p.x_buf_rows * 128 + (uint32_t)p.sh0[tt] * 128;
+          const uint32_t o1 = (uint32_t)p.hf1[tt] * p.x_buf_rows * 128 + (uint32_t)p.sh1[tt] * 128;
           xlo[t] = tma::desc_lo32(xs + o0, o1 - o0);
         }
       }
       const uint32_t xpl16 = L.x_plane_bytes >> 4, ones_lo = tma::desc_lo32(base + L.ones_off, 16);
-      const uint32_t zh0 = tma::desc_lo32(zs + (uint32_t)p.z_start * p.z_row_bytes, 16), zpl16 = L.z_plane_bytes >> 4;
-      const uint32_t dbias = tmem + (uint32_t)p.n_tiles * p.N;
+      // B = [dy_hi | dy_lo]: the lo plane is the second N group, LBO = plane bytes
+      const uint32_t zh0 = tma::desc_lo32(zs + (uint32_t)p.z_start * p.z_row_bytes, L.z_plane_bytes);
+      const uint32_t dbias = tmem + (uint32_t)nt * N2;
       for (int im = im0, i = 0; im < im1; ++im, ++i) {
         mbar_wait(full, i & 1);
         tcgen05_after_sync();
         if (elect_one()) {
         tl_stamp(p.debug, 3000 + 2 * i);
         for (int j = 0; j < p.k16; ++j) {
-          const uint32_t zh = zh0 + (uint32_t)j * p.z_row_bytes, zl = zh + zpl16;  // 16 rows = row_bytes 16-byte units
-          const uint32_t xk = (uint32_t)j * 128;                                      // 16 rows of 128 bytes
+          const uint32_t zh = zh0 + (uint32_t)j * p.z_row_bytes;  // 16 rows = row_bytes 16-byte units
+          const uint32_t xk = (uint32_t)j * 128;                  // 16 rows of 128 bytes
           const bool first = i == 0 && j == 0;
 #pragma unroll
           for (int t = 0; t < MAX_TAPS; ++t) {
-            if (t < p.n_tiles) {
-              const uint32_t d = tmem + (uint32_t)t * p.N;
-              if (first) tma::mma_bf16_split<false>(d, xlo[t] + xk, x_hi32, zh, z_hi32, idesc);
-              else tma::mma_bf16_split<true>(d, xlo[t] + xk, x_hi32, zh, z_hi32, idesc);
-              tma::mma_bf16_split<true>(d, xlo[t] + xk, x_hi32, zl, z_hi32, idesc);
-              if (A_PLANES == 2) tma::mma_bf16_split<true>(d, xlo[t] + xk + xpl16, x_hi32, zh, z_hi32, idesc);
+            if (t < nt) {
+              const uint32_t d = tmem + (uint32_t)t * N2;
+              if (first) tma::mma_bf16_split<false>(d, xlo[t] + xk, x_hi32, zh, z_hi32, idesc2);
+              else tma::mma_bf16_split<true>(d, xlo[t] + xk, x_hi32, zh, z_hi32, idesc2);
+              if (A_PLANES == 2) tma::mma_bf16_split<true>(d, xlo[t] + xk + xpl16, x_hi32, zh, z_hi32, idesc1);
             }
           }
-          // bias gradient: ones^T dy (lo part of dy included)
-          if (first) tma::mma_bf16_split<false>(dbias, ones_lo, x_hi32, zh, z_hi32, idesc);
-          else tma::mma_bf16_split<true>(dbias, ones_lo, x_hi32, zh, z_hi32, idesc);
-          tma::mma_bf16_split<true>(dbias, ones_lo, x_hi32, zl, z_hi32, idesc);
+          if (has_bias) {  // bias gradient: ones^T [dy_hi | dy_lo]
+            if (first) tma::mma_bf16_split<false>(dbias, ones_lo, x_hi32, zh, z_hi32, idesc2);
+            else tma::mma_bf16_split<true>(dbias, ones_lo, x_hi32, zh, z_hi32, idesc2);
+          }
         }
         mma_commit(empty);
         tl_stamp(p.debug, 3001 + 2 * i);
@@ -561,25 +571,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
     tcgen05_after_sync();
     if (warp == 2 && lane == 0) tl_stamp(p.debug, 1200);
     float* part = p.part + ((int64_t)z * p.groups + gidx) * p.span;
-    for (int t = 0; t <= p.n_tiles; ++t) {
+    const int ntot = nt + (has_bias ? 1 : 0);
+    for (int t = 0; t < ntot; ++t) {
       int64_t arow = -1;
       float sc = p.scale;
-      if (t < p.n_tiles) {
+      if (t < nt) {
+        const int tt = t_lo + t;
         const int grp = r >> 6, j = r & 63;
-        const int r0 = grp ? p.row1[t] : p.row0[t];
-        if (r0 >= 0 && j < p.grp_rows) arow = p.w_off + ((int64_t)r0 + (j / p.run) * p.run_stride + j % p.run) * p.N;
+        const int r0 = grp ? p.row1[tt] : p.row0[tt];
+        if (r0 >= 0 && j < p.grp_rows) arow = p.w_off + ((int64_t)r0 + (j / p.run) * p.run_stride + j % p.run) * N;
       } else if (r == 0) {
         arow = p.b_off, sc = 1.f;
       }
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)t * p.N;
-      for (int c0 = 0; c0 < p.N; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)t * N2;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16], v2[16];
+        tmem_ld16_nowait(taddr + c0, v);
+        tmem_ld16_nowait(taddr + N + c0, v2);
+        tmem_ld_wait();
         if (arow < 0) continue;
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
           reinterpret_cast<float4*>(part + arow + c0)[k4] =
-              make_float4(v[4 * k4] * sc, v[4 * k4 + 1] * sc, v[4 * k4 + 2] * sc, v[4 * k4 + 3] * sc);
+              make_float4((v[4 * k4] + v2[4 * k4]) * sc, (v[4 * k4 + 1] + v2[4 * k4 + 1]) * sc,
+                          (v[4 * k4 + 2] + v2[4 * k4 + 2]) * sc, (v[4 * k4 + 3] + v2[4 * k4 + 3]) * sc);
       }
     }
   }

@@ -549,9 +549,9 @@ struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused o
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (ok[u]) {
-            Pv[u] = *reinterpret_cast<const float4*>(Wp + off[u]);
-            Mv[u] = *reinterpret_cast<const float4*>(Mp + off[u]);
-            Vv[u] = *reinterpret_cast<const float4*>(Vp + off[u]);
+            Pv[u] = __ldcs(reinterpret_cast<const float4*>(Wp + off[u]));  // touched once per step: streaming
+            Mv[u] = __ldcs(reinterpret_cast<const float4*>(Mp + off[u]));
+            Vv[u] = __ldcs(reinterpret_cast<const float4*>(Vp + off[u]));
           }
         }
 #pragma unroll
@@ -561,9 +561,9 @@ struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused o
             adam_elem(ac, Gv[u].y, Pv[u].y, Mv[u].y, Vv[u].y);
             adam_elem(ac, Gv[u].z, Pv[u].z, Mv[u].z, Vv[u].z);
             adam_elem(ac, Gv[u].w, Pv[u].w, Mv[u].w, Vv[u].w);
-            *reinterpret_cast<float4*>(Wp + off[u]) = Pv[u];
-            *reinterpret_cast<float4*>(Mp + off[u]) = Mv[u];
-            *reinterpret_cast<float4*>(Vp + off[u]) = Vv[u];
+            __stcs(reinterpret_cast<float4*>(Wp + off[u]), Pv[u]);
+            __stcs(reinterpret_cast<float4*>(Mp + off[u]), Mv[u]);
+            __stcs(reinterpret_cast<float4*>(Vp + off[u]), Vv[u]);
             uint2 h2, l2;
             split4(Pv[u], h2, l2);
             *reinterpret_cast<uint2*>(Wh + hb + off[u]) = h2;

@@ -118,7 +118,7 @@ static int img_setup(idqn_handle* h) {
   // ---- partial weight gradients ----
   h->wspan = dense.w_off;  // the conv layers occupy the arena range [0, Dense_0.w_off)
   {
-    const int want = std::max(1, h->sm_count / K);
+    const int want = std::max(1, h->sm_count / (2 * K));  // x 2 tile splits per (head, image range)
     const int ipg = (B + want - 1) / std::min(want, B);
     h->wgroups = (B + ipg - 1) / ipg;
     const size_t pb = sizeof(float) * h->wspan * h->wgroups * K;
@@ -248,7 +248,8 @@ static int img_setup(idqn_handle* h) {
             ++ng;
           }
       a.n_tiles = (ng + 1) / 2;
-      if (a.n_tiles > img::MAX_TAPS || (a.n_tiles + 1) * g.OC > 512) {
+      a.tsplit = 2, a.tps = (a.n_tiles + 1) / 2;
+      if (a.n_tiles > img::MAX_TAPS || (a.tps + 1) * 2 * g.OC > 512) {
         idqn_set_error("internal: wgrad L%d needs too many accumulator tiles", li);
         return IDQN_EINVAL;
       }
@@ -414,7 +415,7 @@ static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
   a.debug = img_debug_on("wgrad", li);
   const ImgLayerState& S = h->il[li];
   const img::WgradSmem L = img::wgrad_smem(a, a_planes);
-  const int grid = a.heads * a.groups;
+  const int grid = a.heads * a.groups * a.tsplit;
   if (a_planes == 1) {
     CK(img_set_smem(img::conv_wgrad_kernel<1>, L.total));
     CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<1>, dim3(grid), dim3(192), L.total, h->stream, S.mapX[0], S.mapX[1],
