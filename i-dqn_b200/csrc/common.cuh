@@ -120,6 +120,12 @@ struct idqn_handle {
   int64_t in_elems;     // elements of one input sample
   int K, B, A;
   cudaStream_t stream;
+  // SM partitions of the backward pass (sm_partition.cuh): conv chain | HBM-bound Dense_0 wgrad+Adam
+  void* partition;      // smpart::Partition, null when green contexts are unavailable or disabled
+  cudaEvent_t ev_fork, ev_join[2];
+  float part_frac;      // share of the Dense_0 wgrad+Adam tiles that run inside the partition
+  int wg_tile0, wg_tiles;  // tile range of the next Dense wgrad+Adam launch (wg_tiles == 0: all)
+  int sm_avail;         // SMs of the stream the next launches go to
   // arenas [K][stride]
   float *online, *target, *mu, *nu, *grad;
   int32_t* count;       // [K]

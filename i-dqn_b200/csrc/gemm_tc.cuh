@@ -487,6 +487,7 @@ struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused o
   float lr, b1, b2, eps;
   int I, O, B, NT, nstage;
   int adam;                // 0: only write the gradient
+  int bx0;                 // first 128-row tile of this launch (the step may split the layer over two launches)
 
   struct Ctx {
     int m0, n0, kbeg, kend, z;
@@ -495,7 +496,7 @@ struct TcWgradDenseAdam {  // dW[i][o] = sum_b x[b][i] dy[b][o] (K = B), fused o
   __device__ __forceinline__ Ctx ctx(int bx, int by, int bz) const {
     Ctx c;
     c.z = bz;
-    c.m0 = bx * 128;
+    c.m0 = (bx + bx0) * 128;
     c.n0 = by * NT;
     c.kbeg = 0, c.kend = B;
     c.ah = xh.get<bf16>(bz), c.al = xl.get<bf16>(bz);

@@ -3,6 +3,7 @@
 #pragma once
 #include "conv_img.cuh"
 #include "dense_stream.cuh"
+#include "dense_wgrad_tma.cuh"
 
 struct ImgHost {
   img::Geom g[IDQN_IMG_LAYERS];
@@ -12,6 +13,8 @@ struct ImgHost {
   // weight-streaming kernels of the big Dense layer (dense_stream.cuh)
   int dense_on;
   alignas(64) CUtensorMap dmapWf[2], dmapWd[2], dmapX[2], dmapDy[2];
+  alignas(64) CUtensorMap wmapX[2], wmapP[3];  // dense_wgrad_tma.cuh: x planes {32 i, 32 b}; fp32 W / mu / nu {256 o, 8 i}
+  int wgrad_tma_on;
   dense::Args dfwd, ddg;
   float* dpart;
   int* dtickets;
@@ -118,7 +121,9 @@ static int img_setup(idqn_handle* h) {
   // ---- partial weight gradients ----
   h->wspan = dense.w_off;  // the conv layers occupy the arena range [0, Dense_0.w_off)
   {
-    const int want = std::max(1, h->sm_count / (2 * K));  // x 2 tile splits per (head, image range)
+    // x 2 tile splits per (head, image range); the conv backward chain owns one SM partition when there is one
+    const int conv_sms = h->partition ? ((smpart::Partition*)h->partition)->sms[0] : h->sm_count;
+    const int want = std::max(1, conv_sms / (2 * K));
     const int ipg = (B + want - 1) / std::min(want, B);
     h->wgroups = (B + ipg - 1) / ipg;
     const size_t pb = sizeof(float) * h->wspan * h->wgroups * K;
@@ -297,6 +302,25 @@ static int img_setup(idqn_handle* h) {
         const uint64_t ystr[2] = {(uint64_t)O * 2, (uint64_t)h->act_stride * 2};
         REQUIRE(tma::encode_bf16(&H->dmapDy[pl], yb, 3, ydims, ystr, boxx, 128), "tensor map dense dy");
       }
+      // fused wgrad + Adam pipeline (dense_wgrad_tma.cuh)
+      H->wgrad_tma_on = O == dwt::CB * dwt::TO && I % dwt::TM == 0 && dense.b_off == dense.w_off + (int64_t)I * O;
+      if (H->wgrad_tma_on) {
+        for (int pl = 0; pl < 2; ++pl) {
+          // x planes as the N-side operand: boxes {32 i, 32 b} (64-byte rows); dy planes as the M side: dmapDy {64 o, 32 b}
+          const __nv_bfloat16* xb = (pl ? h->act_lo : h->act_hi) + prev.act_off;
+          const uint64_t xdims[3] = {(uint64_t)I, (uint64_t)B, (uint64_t)2 * K};
+          const uint64_t xstr[2] = {(uint64_t)I * 2, (uint64_t)h->act_stride * 2};
+          const uint32_t xbox[3] = {(uint32_t)dwt::TN, (uint32_t)B, 1};
+          REQUIRE(tma::encode_bf16(&H->wmapX[pl], xb, 3, xdims, xstr, xbox, 64), "tensor map dense x (wgrad)");
+        }
+        float* arenas[3] = {h->online, h->mu, h->nu};
+        for (int a = 0; a < 3; ++a) {
+          const uint64_t pdims[3] = {(uint64_t)O, (uint64_t)I, (uint64_t)K};
+          const uint64_t pstr[2] = {(uint64_t)O * 4, (uint64_t)h->stride * 4};
+          const uint32_t pbox[3] = {256, (uint32_t)dwt::TM, 1};
+          REQUIRE(tma::encode_f32(&H->wmapP[a], arenas[a] + dense.w_off, 3, pdims, pstr, pbox), "tensor map dense W/mu/nu");
+        }
+      }
       const int kblocks = (I + 63) / 64;
       {
         dense::Args& a = H->dfwd;
@@ -392,7 +416,7 @@ static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes) {
   a.debug = img_debug_on(dgrad ? "dgrad" : "fwd", li);
   const ImgLayerState& S = h->il[li];
   const img::TapsSmem L = img::taps_smem(a, a_planes);
-  const int grid = std::min(a.n_units * a.tiles, h->sm_count);
+  const int grid = std::min(a.n_units * a.tiles, h->sm_avail);
   const CUtensorMap* mA = dgrad ? S.mapZ : S.mapX;
 #define IMG_TAPS_LAUNCH(KIND, PL)                                                                            \
   do {                                                                                                       \
@@ -455,6 +479,27 @@ static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst) {
   }
   CK(cudaGetLastError());
   mark(h, dgrad ? "dense_dgrad_L%d" : "dense_fwd_L%d", li);
+  return IDQN_OK;
+}
+
+// Dense_0 wgrad + Adam over the 8-row tiles [tile0, tile0 + ntiles) of every head (dense_wgrad_tma.cuh)
+static int dense_wgrad_launch(idqn_handle* h, int tile0, int ntiles, bool keep_grads) {
+  ImgHost* H = (ImgHost*)h->img_host;
+  const Layer& l = h->layers[IDQN_IMG_LAYERS];
+  dwt::Args a;
+  a.heads = h->K, a.tile0 = tile0, a.ntiles = ntiles;
+  a.I = l.g.Kd, a.O = l.g.OC;
+  a.count = h->count;
+  a.lr = h->cfg.learning_rate, a.b1 = 0.9f, a.b2 = 0.999f, a.eps = h->cfg.adam_eps;
+  a.Wh = h->won_hi, a.Wl = h->won_lo;
+  a.grad = keep_grads ? h->grad : nullptr;
+  a.stride = h->stride, a.w_off = l.w_off;
+  const int grid = std::min(a.heads * a.ntiles, h->sm_avail);
+  CK(img_set_smem(dwt::dense_wgrad_adam_kernel, dwt::SMEM_TOTAL));
+  CK(launch_pdl(0, dwt::dense_wgrad_adam_kernel, dim3(grid), dim3(dwt::NTHREADS), dwt::SMEM_TOTAL, h->stream, H->wmapX[0],
+                H->wmapX[1], H->dmapDy[0], H->dmapDy[1], H->wmapP[0], H->wmapP[1], H->wmapP[2], a));
+  CK(cudaGetLastError());
+  mark(h, "dense_wgrad_adam_L%d", IDQN_IMG_LAYERS);
   return IDQN_OK;
 }
 

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "sm_partition.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -158,6 +159,7 @@ struct HeadArgs {
   const float* part;
   int ptiles, psplits;
   int64_t pb_off;  // arena offset of that layer's bias
+  int64_t hbias_off;  // >= 0: also write the bias gradient of the hidden layer (sum_b dhid) at this arena offset
 };
 #define HEAD_MAXA 32
 
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
   float* coef = sm;        // [B]
   float* lterm = sm + B;   // [B]
   int* act_s = reinterpret_cast<int*>(sm + 2 * B);  // [B]
+  float* dtile = sm + 3 * B;                        // [B][32] dL/dhidden of this CTA's units (hbias_off >= 0)
   const float* qo = a.q + (int64_t)k * B * A;
   const float* qt = a.q + (int64_t)(a.K + k) * B * A;
   for (int b = tid; b < B; b += blockDim.x) {
@@ -275,12 +278,23 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = j0 + jj + u;
+        float v = 0.f;
         if (j < H) {
-          float v = cb * __ldg(Wk + (int64_t)j * A + ab);
+          v = cb * __ldg(Wk + (int64_t)j * A + ab);
           if (a.relu_mask && !(hid[(int64_t)b * H + j] > 0.f)) v = 0.f;
           dh[(int64_t)b * H + j] = v;
           tc::st1_planes(dhh + (int64_t)b * H + j, dhl + (int64_t)b * H + j, v);
         }
+        if (a.hbias_off >= 0) dtile[b * 32 + jj + u] = v;
+      }
+    }
+    if (a.hbias_off >= 0) {
+      // bias gradient of the hidden layer = sum_b dL/dhidden[b][j], fixed order (dense_wgrad_tma.cuh leaves it to us)
+      __syncthreads();
+      if (tid < 32 && j0 + tid < H) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += dtile[b * 32 + tid];
+        a.grad[(int64_t)k * a.stride + a.hbias_off + j0 + tid] = s;
       }
     }
   }
@@ -391,6 +405,13 @@ static int check_ws(idqn_handle* h, int64_t part, int tickets, const char* what,
 }
 
 #include "img_host.cuh"
+
+// the TMA-pipelined wgrad+Adam kernel (dense_wgrad_tma.cuh) covers the big Dense layer of the image path
+static bool dense_wgrad_tma_ok(const idqn_handle* h, int li) {
+  if (!h->img_on || !h->img_host || (h->cfg.flags & (IDQN_F_OLD_WGRAD | IDQN_F_SIMT_ONLY))) return false;
+  const ImgHost* H = (const ImgHost*)h->img_host;
+  return li == IDQN_IMG_LAYERS && H->dense_on && H->wgrad_tma_on;
+}
 
 // ---- planes -----------------------------------------------------------------------------------------------
 // bf16 planes of the input batch (first layer operand of the tensor-core path); part of the captured step
@@ -542,9 +563,17 @@ static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_
   const int xu = (li == 0) ? x_u8 : 0;
   const float scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;
   const bool keep = (h->cfg.flags & IDQN_F_KEEP_GRADS) != 0;
+  if (dense_wgrad_tma_ok(h, li)) {
+    if (dry) return IDQN_OK;
+    const int mt = l.g.Kd / dwt::TM;
+    const int t0 = h->wg_tiles > 0 ? h->wg_tile0 : 0;
+    const int nt = h->wg_tiles > 0 ? std::min(h->wg_tiles, mt - t0) : mt;
+    return nt > 0 ? dense_wgrad_launch(h, t0, nt, keep) : IDQN_OK;
+  }
   if (use_tc(h) && tc_dense_ok(h, l)) {
     // dW = x^T dy with K = batch: the tile is final after one k-block, so Adam runs in the epilogue and the
-    // gradient of the (98%-of-all-parameters) Dense_0 kernel never goes to HBM
+    // gradient of the (98%-of-all-parameters) Dense_0 kernel never goes to HBM.  h->wg_tile0 / wg_tiles select a
+    // range of 128-row tiles (the step splits this HBM-bound kernel over an SM partition and the whole machine)
     tcg::TcWgradDenseAdam p;
     p.xh = xh, p.xl = xl;
     p.dyh = h->dact_hi + l.act_off, p.dyl = h->dact_lo + l.act_off, p.dystride = h->act_stride;
@@ -559,7 +588,11 @@ static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_
     p.nstage = 2;
     p.adam = 1;
     if (dry) return IDQN_OK;
-    dim3 grid((p.I + 1 + 127) / 128, (p.O + p.NT - 1) / p.NT, K);
+    const int mt = (p.I + 1 + 127) / 128;
+    p.bx0 = h->wg_tiles > 0 ? h->wg_tile0 : 0;
+    const int nt = h->wg_tiles > 0 ? std::min(h->wg_tiles, mt - p.bx0) : mt;
+    if (nt <= 0) return IDQN_OK;
+    dim3 grid(nt, (p.O + p.NT - 1) / p.NT, K);
     CK((tcg::launch_tc<true, true, 2, false, false, false>(p, grid, h->part, h->tickets, h->stream, h->pdl != 0)));
     mark(h, "tc_wgrad_adam_L%d", li);
     return IDQN_OK;
@@ -824,12 +857,16 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     }
     CK(launch_pdl(h->pdl, head_q_kernel, dim3(2 * K * B), dim3(128), 0, h->stream, a));
     mark(h, "head_q_L%d", L - 1);
-    const size_t smem = (size_t)(3 * B) * sizeof(float);
+    a.hbias_off = -1;
+    if (L >= 2 && dense_wgrad_tma_ok(h, L - 2)) a.hbias_off = h->layers[L - 2].b_off;
+    const size_t smem = (size_t)(3 * B + (a.hbias_off >= 0 ? 32 * B : 0)) * sizeof(float);
     CK(launch_pdl(h->pdl, head_bwd_kernel, dim3((a.H + 31) / 32, K), dim3(256), smem, h->stream, a));
     mark(h, "head_bwd_L%d", L - 1);
   }
   // backward through the hidden layers
   int64_t fused_lo = -1, fused_hi = -1;  // arena range whose Adam update was fused into a wgrad epilogue
+  smpart::Partition* part = (smpart::Partition*)h->partition;
+  const bool split = part && use_img && n_img == L - 2 && !h->prof_on && !dry && use_dense;
   for (int li = L - 2; li >= 0; --li) {
     // the dgrad of this layer reads the weights the fused wgrad+Adam kernel overwrites: dgrad first
     if (li < n_img) {
@@ -844,13 +881,45 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
                                                    : launch_dgrad_layer(h, li, li == n_img && n_img > 0);
       if (rc) return rc;
     }
-    int rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
-    if (rc) return rc;
-    if (use_tc(h) && tc_dense_ok(h, h->layers[li])) {
+    const bool fused = use_tc(h) && tc_dense_ok(h, h->layers[li]);
+    if (fused) {
       REQUIRE(fused_lo < 0, "internal: at most one fused wgrad+Adam layer is supported");
       fused_lo = h->layers[li].w_off;
-      fused_hi = h->layers[li].b_off + h->layers[li].g.OC;
+      fused_hi = h->layers[li].b_off + (dense_wgrad_tma_ok(h, li) ? 0 : h->layers[li].g.OC);  // the TMA kernel leaves the bias to Adam
     }
+    if (fused && split) {
+      // Two SM partitions (sm_partition.cuh): the conv backward chain below this layer on part->stream[0], the first
+      // part_frac of this layer's HBM-bound wgrad+Adam tiles on part->stream[1]; the rest of the tiles run on the
+      // whole machine after the join.
+      cudaStream_t main_stream = h->stream;
+      const int mt = dense_wgrad_tma_ok(h, li) ? h->layers[li].g.Kd / dwt::TM : (h->layers[li].g.Kd + 1 + 127) / 128;
+      const int t1 = std::min(mt, std::max(0, (int)(mt * h->part_frac + 0.5f)));
+      CK(cudaEventRecord(h->ev_fork, main_stream));
+      CK(cudaStreamWaitEvent(part->stream[0], h->ev_fork, 0));
+      CK(cudaStreamWaitEvent(part->stream[1], h->ev_fork, 0));
+      int rc = IDQN_OK;
+      h->stream = part->stream[1], h->sm_avail = part->sms[1];
+      h->wg_tile0 = 0, h->wg_tiles = t1;
+      if (t1 > 0) rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
+      h->stream = part->stream[0], h->sm_avail = part->sms[0];
+      for (int lj = li - 1; lj >= 0 && !rc; --lj) {
+        if (lj > 0) rc = img_launch_taps(h, lj, true, 2);
+        if (!rc) rc = img_launch_wgrad(h, lj, lj == 0 ? 1 : 2);
+      }
+      h->stream = main_stream, h->sm_avail = h->sm_count;
+      if (rc) return rc;
+      CK(cudaEventRecord(h->ev_join[0], part->stream[0]));
+      CK(cudaEventRecord(h->ev_join[1], part->stream[1]));
+      CK(cudaStreamWaitEvent(main_stream, h->ev_join[0], 0));
+      CK(cudaStreamWaitEvent(main_stream, h->ev_join[1], 0));
+      h->wg_tile0 = t1, h->wg_tiles = mt - t1;
+      if (mt - t1 > 0) rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
+      h->wg_tile0 = h->wg_tiles = 0;
+      if (rc) return rc;
+      break;
+    }
+    int rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
+    if (rc) return rc;
   }
   if (dry) return IDQN_OK;
   // Adam over the rest of the arena of every head
@@ -938,6 +1007,23 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   REQUIRE(prop.major == 10, "libidqn_b200 is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
   h->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->sm_avail = h->sm_count;
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming));
+  if ((cfg->flags & IDQN_F_PARTITION) && !(cfg->flags & (IDQN_F_SIMT_ONLY | IDQN_F_NO_IMG)) && cfg->arch == IDQN_ARCH_CNN) {
+    // conv chain on 112 of the 148 SMs (its grids are <= 110 CTAs at K = 5), the HBM stream on the other 36
+    const char* e_sms = getenv("IDQN_PART_SMS");
+    const char* e_frac = getenv("IDQN_PART_FRAC");
+    const int conv_sms = e_sms ? atoi(e_sms) : (h->sm_count * 3 / 4 + 7) / 8 * 8;
+    h->part_frac = e_frac ? (float)atof(e_frac) : 0.6f;
+    smpart::Partition* P = new smpart::Partition();
+    if (smpart::create(cfg->device, conv_sms, P)) h->partition = P;
+    else {
+      smpart::destroy(P);
+      delete P;
+    }
+  }
   const int K = h->K, B = h->B;
   const size_t arena = sizeof(float) * h->stride * K;
   float** arenas[5] = {&h->online, &h->target, &h->mu, &h->nu, &h->grad};
@@ -1035,6 +1121,13 @@ extern "C" int idqn_destroy(idqn_handle* h) {
     if (p) cudaFree(p);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->h_i32) cudaFreeHost(h->h_i32);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  if (h->partition) {
+    smpart::destroy((smpart::Partition*)h->partition);
+    delete (smpart::Partition*)h->partition;
+  }
   cudaStreamDestroy(h->stream);
   delete h;
   return IDQN_OK;

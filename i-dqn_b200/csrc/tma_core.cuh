@@ -115,6 +115,19 @@ static inline EncodeTiledFn encode_fn() {
   }
   return fn;
 }
+// fp32 tensor, no swizzle (row-major box in shared memory), rank <= 4, dims/box innermost first
+static inline bool encode_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                              const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) gd[i] = dims[i], bx[i] = box[i], es[i] = 1;
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // bf16 tensor, rank <= 4, dims/box innermost first, strides (bytes) for dims 1..rank-1; sw_bytes = 128 or 64
 static inline bool encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                                const uint32_t* box, int sw_bytes) {
