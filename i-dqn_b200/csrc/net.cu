@@ -180,22 +180,53 @@ __global__ void __launch_bounds__(128) head_q_kernel(const HeadArgs a) {
   float acc[HEAD_MAXA];
 #pragma unroll
   for (int i = 0; i < HEAD_MAXA; ++i) acc[i] = 0.f;
-  for (int j = tid; j < a.H; j += 128) {
-    float h;
-    if (a.part) {
-      const float* src = a.part + ((int64_t)(net * a.ptiles + (j >> 7)) * a.psplits) * (32 * 128) + b * 128 + (j & 127);
-      h = __ldg(base + a.pb_off + j);
-#pragma unroll 4
-      for (int sp = 0; sp < a.psplits; ++sp) h += __ldcg(src + (int64_t)sp * (32 * 128));  // fixed order
-      h = fmaxf(h, 0.f);
-      hv[j] = h;
-    } else {
-      h = hv[j];
-    }
-    const float* wr = W + (int64_t)j * a.A;
+  if (a.part && a.H <= 4 * 128 && (a.H & 127) == 0 && a.psplits <= 16) {
+    // latency path (Dense_0 of the NatureCNN: H = 512, 11 splits): every load of the thread -- bias, split partials,
+    // final-layer weights -- is issued before the first use, so the CTA pays ONE memory round trip
+    const int JT = a.H >> 7;
+    float hb[4], pv[4][16];
 #pragma unroll
-    for (int i = 0; i < HEAD_MAXA; ++i)
-      if (i < a.A) acc[i] = fmaf(h, __ldg(wr + i), acc[i]);
+    for (int t = 0; t < 4; ++t) {
+      const int j = t * 128 + tid;
+      hb[t] = t < JT ? __ldg(base + a.pb_off + j) : 0.f;
+      const float* src = a.part + ((int64_t)(net * a.ptiles + t) * a.psplits) * (32 * 128) + b * 128 + tid;
+#pragma unroll
+      for (int sp = 0; sp < 16; ++sp) pv[t][sp] = (t < JT && sp < a.psplits) ? __ldcg(src + (int64_t)sp * (32 * 128)) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t < JT) {
+        const int j = t * 128 + tid;
+        float h = hb[t];
+#pragma unroll
+        for (int sp = 0; sp < 16; ++sp)
+          if (sp < a.psplits) h += pv[t][sp];  // fixed order
+        h = fmaxf(h, 0.f);
+        hv[j] = h;
+        const float* wr = W + (int64_t)j * a.A;
+#pragma unroll
+        for (int i = 0; i < HEAD_MAXA; ++i)
+          if (i < a.A) acc[i] = fmaf(h, __ldg(wr + i), acc[i]);
+      }
+    }
+  } else {
+    for (int j = tid; j < a.H; j += 128) {
+      float h;
+      if (a.part) {
+        const float* src = a.part + ((int64_t)(net * a.ptiles + (j >> 7)) * a.psplits) * (32 * 128) + b * 128 + (j & 127);
+        h = __ldg(base + a.pb_off + j);
+#pragma unroll 4
+        for (int sp = 0; sp < a.psplits; ++sp) h += __ldcg(src + (int64_t)sp * (32 * 128));  // fixed order
+        h = fmaxf(h, 0.f);
+        hv[j] = h;
+      } else {
+        h = hv[j];
+      }
+      const float* wr = W + (int64_t)j * a.A;
+#pragma unroll
+      for (int i = 0; i < HEAD_MAXA; ++i)
+        if (i < a.A) acc[i] = fmaf(h, __ldg(wr + i), acc[i]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < HEAD_MAXA; ++i) {
@@ -221,7 +252,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
   float* coef = sm;        // [B]
   float* lterm = sm + B;   // [B]
   int* act_s = reinterpret_cast<int*>(sm + 2 * B);  // [B]
-  float* dtile = sm + 3 * B;                        // [B][32] dL/dhidden of this CTA's units (hbias_off >= 0)
+  float* htile = sm + 3 * B;                        // [B][32] hidden activations of this CTA's units
+  float* wtile = htile + 32 * B;                    // [32][A] final-layer weights of this CTA's units
+  float* dtile = wtile + 32 * A;                    // [B][32] dL/dhidden of this CTA's units (hbias_off >= 0)
+  const int j0 = blockIdx.x * 32;
+  const float* hid = a.hid.get<float>(k);
+  const float* Wk = a.online + (int64_t)k * a.stride + a.w_off;
+  // every global load of the CTA is issued here, before the first use: one memory round trip
+  for (int e = tid; e < 32 * B; e += blockDim.x) {
+    const int b = e >> 5, j = j0 + (e & 31);
+    htile[e] = j < H ? __ldg(hid + (int64_t)b * H + j) : 0.f;
+  }
+  for (int e = tid; e < 32 * A; e += blockDim.x) wtile[e] = j0 + e / A < H ? __ldg(Wk + (int64_t)j0 * A + e) : 0.f;
   const float* qo = a.q + (int64_t)k * B * A;
   const float* qt = a.q + (int64_t)(a.K + k) * B * A;
   for (int b = tid; b < B; b += blockDim.x) {
@@ -253,17 +295,14 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
       gb[i] = s;
     }
   }
-  const int j0 = blockIdx.x * 32;
-  const float* hid = a.hid.get<float>(k);
-  const float* Wk = a.online + (int64_t)k * a.stride + a.w_off;
   // kernel gradient: 32 units x A actions
   for (int e = tid; e < 32 * A; e += blockDim.x) {
-    const int j = j0 + e / A, i = e - (e / A) * A;
-    if (j < H) {
+    const int u = e / A, i = e - u * A;
+    if (j0 + u < H) {
       float s = 0.f;
       for (int b = 0; b < B; ++b)
-        if (act_s[b] == i) s = fmaf(coef[b], hid[(int64_t)b * H + j], s);
-      a.grad[(int64_t)k * a.stride + a.w_off + (int64_t)j * A + i] = s;
+        if (act_s[b] == i) s = fmaf(coef[b], htile[b * 32 + u], s);
+      a.grad[(int64_t)k * a.stride + a.w_off + (int64_t)(j0 + u) * A + i] = s;
     }
   }
   if (a.dhid) {
@@ -272,20 +311,32 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
     __nv_bfloat16* dhh = a.dhid_hi + (int64_t)k * a.dstride;
     __nv_bfloat16* dhl = a.dhid_lo + (int64_t)k * a.dstride;
     const int jj = (tid & 7) * 4;
+    const bool vec = (H & 3) == 0 && (a.dstride & 3) == 0;  // 4 units of a thread: one float4 + two 8-byte plane stores
     for (int b = tid >> 3; b < B; b += blockDim.x >> 3) {
       const float cb = coef[b];
       const int ab = act_s[b];
+      float v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int j = j0 + jj + u;
-        float v = 0.f;
-        if (j < H) {
-          v = cb * __ldg(Wk + (int64_t)j * A + ab);
-          if (a.relu_mask && !(hid[(int64_t)b * H + j] > 0.f)) v = 0.f;
-          dh[(int64_t)b * H + j] = v;
-          tc::st1_planes(dhh + (int64_t)b * H + j, dhl + (int64_t)b * H + j, v);
-        }
-        if (a.hbias_off >= 0) dtile[b * 32 + jj + u] = v;
+        v[u] = cb * wtile[(jj + u) * A + ab];
+        if ((a.relu_mask && !(htile[b * 32 + jj + u] > 0.f)) || j0 + jj + u >= H) v[u] = 0.f;
+        if (a.hbias_off >= 0) dtile[b * 32 + jj + u] = v[u];
+      }
+      const int64_t o = (int64_t)b * H + j0 + jj;
+      if (vec && j0 + jj + 3 < H) {
+        const float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dh + o) = v4;
+        uint2 h2, l2;
+        tc::split4(v4, h2, l2);
+        *reinterpret_cast<uint2*>(dhh + o) = h2;
+        *reinterpret_cast<uint2*>(dhl + o) = l2;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + jj + u < H) {
+            dh[o + u] = v[u];
+            tc::st1_planes(dhh + o + u, dhl + o + u, v[u]);
+          }
       }
     }
     if (a.hbias_off >= 0) {
@@ -859,7 +910,8 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     mark(h, "head_q_L%d", L - 1);
     a.hbias_off = -1;
     if (L >= 2 && dense_wgrad_tma_ok(h, L - 2)) a.hbias_off = h->layers[L - 2].b_off;
-    const size_t smem = (size_t)(3 * B + (a.hbias_off >= 0 ? 32 * B : 0)) * sizeof(float);
+    const size_t smem = (size_t)(3 * B + 32 * B + 32 * a.A + 32 * B) * sizeof(float);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(launch_pdl(h->pdl, head_bwd_kernel, dim3((a.H + 31) / 32, K), dim3(256), smem, h->stream, a));
     mark(h, "head_bwd_L%d", L - 1);
   }
