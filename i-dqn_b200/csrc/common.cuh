@@ -123,6 +123,9 @@ struct idqn_handle {
   // SM partitions of the backward pass (sm_partition.cuh): conv chain | HBM-bound Dense_0 wgrad+Adam
   void* partition;      // smpart::Partition, null when green contexts are unavailable or disabled
   cudaEvent_t ev_fork, ev_join[2];
+  // second branch of the step graph: the conv weight-gradient kernels run next to the conv data-gradient chain
+  cudaStream_t side;
+  cudaEvent_t ev_conv[IDQN_IMG_LAYERS], ev_side_done;
   float part_frac;      // share of the Dense_0 wgrad+Adam tiles that run inside the partition
   int wg_tile0, wg_tiles;  // tile range of the next Dense wgrad+Adam launch (wg_tiles == 0: all)
   int sm_avail;         // SMs of the stream the next launches go to

@@ -919,13 +919,28 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   int64_t fused_lo = -1, fused_hi = -1;  // arena range whose Adam update was fused into a wgrad epilogue
   smpart::Partition* part = (smpart::Partition*)h->partition;
   const bool split = part && use_img && n_img == L - 2 && !h->prof_on && !dry && use_dense;
+  const bool fork_conv = n_img > 0 && !split && !h->prof_on && !dry && !(h->cfg.flags & IDQN_F_NO_FORK);
   for (int li = L - 2; li >= 0; --li) {
     // the dgrad of this layer reads the weights the fused wgrad+Adam kernel overwrites: dgrad first
     if (li < n_img) {
+      // dyZ of this layer is complete at this point of the main stream: its weight gradient goes to the side branch
+      // and runs next to the data-gradient chain (both are one-CTA-per-SM kernels with 25-30% of the SMs idle in
+      // their last wave; as independent graph branches they fill each other's tails)
+      if (fork_conv) {
+        CK(cudaEventRecord(h->ev_conv[li], h->stream));
+        CK(cudaStreamWaitEvent(h->side, h->ev_conv[li], 0));
+      }
       int rc = li > 0 ? img_launch_taps(h, li, true, 2) : IDQN_OK;
       if (rc) return rc;
+      cudaStream_t main_stream = h->stream;
+      if (fork_conv) h->stream = h->side;
       rc = img_launch_wgrad(h, li, li == 0 ? 1 : 2);
+      h->stream = main_stream;
       if (rc) return rc;
+      if (fork_conv && li == 0) {
+        CK(cudaEventRecord(h->ev_side_done, h->side));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_side_done, 0));
+      }
       continue;
     }
     if (li > 0 && !dry) {
@@ -1063,6 +1078,9 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_side_done, cudaEventDisableTiming));
+  for (int i = 0; i < IDQN_IMG_LAYERS; ++i) CK(cudaEventCreateWithFlags(&h->ev_conv[i], cudaEventDisableTiming));
   if ((cfg->flags & IDQN_F_PARTITION) && !(cfg->flags & (IDQN_F_SIMT_ONLY | IDQN_F_NO_IMG)) && cfg->arch == IDQN_ARCH_CNN) {
     // conv chain on 112 of the 148 SMs (its grids are <= 110 CTAs at K = 5), the HBM stream on the other 36
     const char* e_sms = getenv("IDQN_PART_SMS");
@@ -1176,6 +1194,10 @@ extern "C" int idqn_destroy(idqn_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int i = 0; i < 2; ++i)
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  if (h->ev_side_done) cudaEventDestroy(h->ev_side_done);
+  for (int i = 0; i < IDQN_IMG_LAYERS; ++i)
+    if (h->ev_conv[i]) cudaEventDestroy(h->ev_conv[i]);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->partition) {
     smpart::destroy((smpart::Partition*)h->partition);
     delete (smpart::Partition*)h->partition;
