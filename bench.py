@@ -175,11 +175,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, first_step):
+    def timed(fn, steps, warmup, first_step, drain=None):
         step = first_step
         for _ in range(warmup):
             fn(step)
             step += 1
+        if drain:
+            drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(local)
@@ -189,6 +191,8 @@ def run_ours(args):
         for _ in range(steps):
             fn(step)
             step += 1
+        if drain:
+            drain()  # the last step's losses are read inside the timed region
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -217,14 +221,36 @@ def run_ours(args):
                   for k, v in b.items()}
         pool.append({k: t.numpy() for k, t in pinned.items()} | {"_keep": pinned})
 
+    # (2a) pipelined the way the reference's own call is (async dispatch): submit enqueues the pinned H2D copies of
+    # this step on the copy stream + the step, the losses of the previous step are read back (D2H) right after
+    pending = [None]
+    loss_log = []
+
     def e2e_step(step):
         b = pool[step % len(pool)]
-        eng.learn_host(b, want_losses=True)
+        t = eng.submit_host(b)
+        if pending[0] is not None:
+            loss_log.append(eng.wait_losses(pending[0]))
+        pending[0] = t
         agent.update_target_params(step)
 
+    def e2e_drain():
+        if pending[0] is not None:
+            loss_log.append(eng.wait_losses(pending[0]))
+            pending[0] = None
+
     e2e_steps = max(args.steps // 2, 5)
-    ms_e2e, _, _, nxt = timed(e2e_step, e2e_steps, max(3, args.warmup // 2), nxt)
+    ms_e2e, _, _, nxt = timed(e2e_step, e2e_steps, max(3, args.warmup // 2), nxt, drain=e2e_drain)
     e2e_rate = e2e_steps / (ms_e2e / 1e3)
+    assert len(loss_log) >= e2e_steps and all(np.isfinite(l).all() for l in loss_log)
+
+    # (2b) the blocking call: H2D, step and D2H of the losses strictly one after the other
+    def e2e_sync_step(step):
+        eng.learn_host(pool[step % len(pool)], want_losses=True)
+        agent.update_target_params(step)
+
+    ms_sync, _, _, nxt = timed(e2e_sync_step, e2e_steps, 3, nxt)
+    e2e_sync_rate = e2e_steps / (ms_sync / 1e3)
 
     # (3) live per-kernel timing (CUDA events after every launch, un-graphed) for the roofline of the top kernel
     names_buf = (np.zeros(64 * 32, np.uint8))
@@ -245,6 +271,14 @@ def run_ours(args):
     pk = peaks()
     rl = kernel_roofline(top, acc[top], eng.K, pk)
     rl["traffic"] = None
+    try:  # per-launch DRAM bytes of this kernel from the committed ncu --set full capture (K = 5 per GPU)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f).get(top)
+        if tr and eng.K == HEADS_PER_GPU:
+            rl["traffic"] = tr
+            rl["algorithmic_bytes"] = int(round(rl["achieved"] * acc[top] * 1e6)) if rl.get("achieved") else None
+    except Exception:
+        pass
     rl["kernel"] = top
     rl["peak_source"] = pk["src"]
 
@@ -271,7 +305,10 @@ def run_ours(args):
             "step_tflops": FLOP_PER_HEAD_STEP * eng.K / (ms / args.steps * 1e-3) / 1e12,
             "wall_s": wall, "clocks": clocks,
             "e2e": {"value": e2e_rate * world, "unit": "steps/s", "h2d_bytes_per_step": BATCH_BYTES,
-                    "d2h_bytes_per_step": 4 * eng.K},
+                    "d2h_bytes_per_step": 4 * eng.K,
+                    "how": "idqn_submit_batch_host / idqn_wait_losses: pinned H2D of step t+1 on a copy stream while "
+                           "step t computes, losses of every step read back one step behind (two steps in flight)",
+                    "blocking_call_value": e2e_sync_rate * world},
             "gpu_launches": kernels_per_step * args.steps,
             "roofline": rl, "kernel_ms": {k: round(v, 5) for k, v in acc.items()},
         }

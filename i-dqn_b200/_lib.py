@@ -47,6 +47,8 @@ SYMBOLS = {
     "idqn_stream": (_P, [_P]),
     "idqn_learn_on_batch_host": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
     "idqn_learn_on_batch_dev": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
+    "idqn_submit_batch_host": (_I, [_P, _P, _P, _I, _P, _P, _P, C.POINTER(_I64)]),
+    "idqn_wait_losses": (_I, [_P, _I64, _P]),
     "idqn_read_cumulated_losses": (_I, [_P, _P, _I]),
     "idqn_kernels_per_step": (_I, [_P]),
     "idqn_profile_step": (_I, [_P, _I, _I, _P, _P, C.POINTER(_I)]),

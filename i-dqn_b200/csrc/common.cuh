@@ -166,6 +166,15 @@ struct idqn_handle {
   int64_t part_floats;
   int* tickets;
   int n_tickets;
+  // pipelined host path (idqn_submit_batch_host / idqn_wait_losses): two staging slots filled by the copy stream
+  cudaStream_t copy_stream;
+  void *alt_s[2], *alt_s2[2];
+  int32_t* alt_action[2];
+  float* alt_reward[2];
+  uint8_t* alt_terminal[2];
+  float* h_loss_ring;   // pinned [2][K]
+  cudaEvent_t ev_h2d[2], ev_consumed[2], ev_done[2];
+  int64_t next_ticket;
   // pinned host scratch
   float* h_loss;
   int32_t* h_i32;

@@ -1194,6 +1194,16 @@ extern "C" int idqn_destroy(idqn_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int i = 0; i < 2; ++i)
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  if (h->copy_stream) {
+    for (int i = 0; i < 2; ++i) {
+      void* ptrs[] = {h->alt_s[i], h->alt_s2[i], h->alt_action[i], h->alt_reward[i], h->alt_terminal[i]};
+      for (void* q : ptrs)
+        if (q) cudaFree(q);
+      cudaEventDestroy(h->ev_h2d[i]), cudaEventDestroy(h->ev_consumed[i]), cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->h_loss_ring) cudaFreeHost(h->h_loss_ring);
+    cudaStreamDestroy(h->copy_stream);
+  }
   if (h->ev_side_done) cudaEventDestroy(h->ev_side_done);
   for (int i = 0; i < IDQN_IMG_LAYERS; ++i)
     if (h->ev_conv[i]) cudaEventDestroy(h->ev_conv[i]);
@@ -1320,6 +1330,74 @@ extern "C" int idqn_learn_on_batch_dev(idqn_handle* h, const void* s, const void
   int rc = stage_batch(h, s, s2, u8, a, r, d, cudaMemcpyDeviceToDevice);
   if (rc) return rc;
   return idqn_learn_step_resident(h, u8, losses);
+}
+
+// ---- pipelined host path --------------------------------------------------------------------------------------
+// submit: the H2D copies of this batch go to the copy stream and land in one of two staging slots while the previous
+// step still computes; the main stream picks the slot up with device-to-device copies, runs the step and sends the
+// losses to a pinned ring.  wait: blocks on that step's completion event only.
+static int pipeline_setup(idqn_handle* h) {
+  if (h->copy_stream) return IDQN_OK;
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  const size_t sb = (size_t)h->in_elems * h->B * 4;
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&h->alt_s[i], sb));
+    CK(cudaMalloc(&h->alt_s2[i], sb));
+    CK(cudaMalloc(&h->alt_action[i], sizeof(int32_t) * h->B));
+    CK(cudaMalloc(&h->alt_reward[i], sizeof(float) * h->B));
+    CK(cudaMalloc(&h->alt_terminal[i], h->B));
+    CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+  }
+  CK(cudaMallocHost(&h->h_loss_ring, sizeof(float) * 2 * h->K));
+  h->next_ticket = 0;
+  return IDQN_OK;
+}
+
+extern "C" int idqn_submit_batch_host(idqn_handle* h, const void* s, const void* s2, int u8, const int32_t* a,
+                                      const float* r, const uint8_t* d, int64_t* ticket) {
+  REQUIRE(h && s && s2 && a && r && d && ticket, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  u8 = u8 ? 1 : 0;
+  int rc = pipeline_setup(h);
+  if (rc) return rc;
+  rc = refresh_planes(h);
+  if (rc) return rc;
+  const int64_t t = h->next_ticket;
+  const int slot = (int)(t & 1);
+  if (t >= 2) CK(cudaEventSynchronize(h->ev_done[slot]));  // at most two steps in flight: the slot's loss entry is free
+  const size_t sb = (size_t)h->in_elems * h->B * (u8 ? 1 : 4);
+  if (t >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
+  CK(cudaMemcpyAsync(h->alt_s[slot], s, sb, cudaMemcpyHostToDevice, h->copy_stream));
+  CK(cudaMemcpyAsync(h->alt_s2[slot], s2, sb, cudaMemcpyHostToDevice, h->copy_stream));
+  CK(cudaMemcpyAsync(h->alt_action[slot], a, sizeof(int32_t) * h->B, cudaMemcpyHostToDevice, h->copy_stream));
+  CK(cudaMemcpyAsync(h->alt_reward[slot], r, sizeof(float) * h->B, cudaMemcpyHostToDevice, h->copy_stream));
+  CK(cudaMemcpyAsync(h->alt_terminal[slot], d, h->B, cudaMemcpyHostToDevice, h->copy_stream));
+  CK(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+  rc = stage_batch(h, h->alt_s[slot], h->alt_s2[slot], u8, h->alt_action[slot], h->alt_reward[slot], h->alt_terminal[slot],
+                   cudaMemcpyDeviceToDevice);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev_consumed[slot], h->stream));
+  rc = idqn_learn_step_resident(h, u8, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_loss_ring + (size_t)slot * h->K, h->loss, sizeof(float) * h->K, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->ev_done[slot], h->stream));
+  *ticket = t;
+  h->next_ticket = t + 1;
+  return IDQN_OK;
+}
+
+extern "C" int idqn_wait_losses(idqn_handle* h, int64_t ticket, float* losses) {
+  REQUIRE(h && h->copy_stream, "no batch was submitted");
+  REQUIRE(ticket >= 0 && ticket < h->next_ticket && ticket + 2 >= h->next_ticket, "ticket %lld is not one of the two most recent submissions",
+          (long long)ticket);
+  CK(cudaSetDevice(h->cfg.device));
+  const int slot = (int)(ticket & 1);
+  CK(cudaEventSynchronize(h->ev_done[slot]));
+  if (losses) memcpy(losses, h->h_loss_ring + (size_t)slot * h->K, sizeof(float) * h->K);
+  return IDQN_OK;
 }
 
 extern "C" int idqn_read_cumulated_losses(idqn_handle* h, double* sums, int reset) {

@@ -130,6 +130,7 @@ class Engine:
         self.h = h
         self._finalizer = weakref.finalize(self, self.lib.idqn_destroy, h)
         self.stride = int(self.lib.idqn_arena_stride(h))
+        self._inflight = [None, None]  # host arrays of the two most recent submit_host calls
         self.leaves: List[Dict[str, Any]] = []
         for i in range(self.lib.idqn_leaf_count(h)):
             off, size, ndim = C.c_int64(), C.c_int64(), C.c_int32()
@@ -239,6 +240,21 @@ class Engine:
         losses = np.zeros(self.K, np.float32) if want_losses else None
         L.check(self.lib.idqn_learn_on_batch_host(self.h, L.ptr(s), L.ptr(s2), u8, L.ptr(a), L.ptr(r), L.ptr(d),
                                                   L.ptr(losses) if want_losses else None))
+        return losses
+
+    def submit_host(self, batch) -> int:
+        """Pipelined host path: enqueue the H2D copies (copy stream) and the step; returns a ticket.  The arrays of
+        ``batch`` must stay alive and unmodified until ``wait_losses(ticket)``."""
+        s, s2, u8, a, r, d = self.pack_batch(batch)
+        ticket = C.c_int64(0)
+        L.check(self.lib.idqn_submit_batch_host(self.h, L.ptr(s), L.ptr(s2), u8, L.ptr(a), L.ptr(r), L.ptr(d),
+                                                C.byref(ticket)))
+        self._inflight[ticket.value & 1] = (s, s2, a, r, d)  # keep converted copies alive
+        return ticket.value
+
+    def wait_losses(self, ticket: int) -> np.ndarray:
+        losses = np.zeros(self.K, np.float32)
+        L.check(self.lib.idqn_wait_losses(self.h, C.c_int64(ticket), L.ptr(losses)))
         return losses
 
     def learn_dev(self, s_ptr: int, s2_ptr: int, u8: int, a_ptr: int, r_ptr: int, d_ptr: int,

@@ -87,6 +87,25 @@ def exchange_for_shift(online, rank: int, parts, dist, group=None) -> None:
         online[k_local - 1].copy_(recv)
 
 
+def warm_up_links(like, rank: int, parts, dist, group=None) -> None:
+    """Run both neighbour-exchange patterns once on scratch tensors.  NCCL sets up its point-to-point connections
+    lazily, per peer and direction, on first use (~100 ms): without this the first D-sync and the first T-shift of a
+    run pay for it inside the training loop."""
+    import torch
+
+    if parts[rank][1] == 0:
+        return
+    prev, nxt = _neighbours(rank, parts)
+    for send_to, recv_from in ((nxt, prev), (prev, nxt)):  # D-sync direction, then T-shift direction
+        ops = []
+        if send_to is not None:
+            ops.append(dist.P2POp(dist.isend, torch.zeros_like(like), send_to, group))
+        if recv_from is not None:
+            ops.append(dist.P2POp(dist.irecv, torch.empty_like(like), recv_from, group))
+        for r in (dist.batch_isend_irecv(ops) if ops else []):
+            r.wait()
+
+
 class _CudaView:
     def __init__(self, ptr: int, shape):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
@@ -160,4 +179,7 @@ def make_sharded_idqn(key, observation_dim, n_actions, n_networks_total: int, fe
     agent._target = arena_tensor(agent._engine, L.TARGET)
     agent._stream = engine_stream(agent._engine)
     agent.head_offset, agent.n_networks_total = start, n_networks_total
+    with torch.cuda.stream(agent._stream):
+        warm_up_links(agent._online[0], rank, parts, dist, group)
+    torch.cuda.synchronize()
     return agent

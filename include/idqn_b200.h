@@ -112,6 +112,16 @@ int idqn_learn_on_batch_host(idqn_handle* h, const void* state_host, const void*
 int idqn_learn_on_batch_dev(idqn_handle* h, const void* state_dev, const void* next_state_dev, int state_is_u8,
                             const int32_t* action_dev, const float* reward_dev, const uint8_t* is_terminal_dev,
                             float* losses_host);
+/* The same step as idqn_learn_on_batch_host, pipelined the way the reference's own call is (jax dispatches
+ * learn_on_batch asynchronously and idqn.py:72 only accumulates device futures): submit returns as soon as the copies
+ * and the step are enqueued -- the H2D copies of batch t+1 run on a copy stream while step t computes -- and
+ * idqn_wait_losses blocks until the step of `ticket` has finished and returns its K losses.  At most two steps are in
+ * flight (submit waits for ticket-2); host buffers must stay valid until idqn_wait_losses(ticket) returns (pinned
+ * buffers make the copies truly asynchronous). */
+int idqn_submit_batch_host(idqn_handle* h, const void* state_host, const void* next_state_host, int state_is_u8,
+                           const int32_t* action_host, const float* reward_host, const uint8_t* is_terminal_host,
+                           int64_t* ticket);
+int idqn_wait_losses(idqn_handle* h, int64_t ticket, float* losses_host);
 /* idqn.py:72,82-87: device-side sum of the per-head losses since the last reset */
 int idqn_read_cumulated_losses(idqn_handle* h, double* sums_host, int reset);
 

@@ -270,3 +270,34 @@ def test_loss_logging_and_cumulated_losses():
     np.testing.assert_allclose(logs["loss"], tot.mean() / 4, rtol=1e-6)
     np.testing.assert_allclose(logs["networks/2_loss"], tot[2] / 4, rtol=1e-6)
     assert (agent.cumulated_losses == 0).all()
+
+
+def test_pipelined_host_submission_equals_blocking_calls():
+    """idqn_submit_batch_host / idqn_wait_losses (H2D of batch t+1 on the copy stream while step t computes, losses
+    read one step behind) give bit-identical losses and parameters to the blocking idqn_learn_on_batch_host."""
+    from idqn_b200.networks.idqn import iDQN
+    obs, feats, A, K, B = (84, 84, 4), [32, 64, 64, 512], 6, 2, 32
+    rng = np.random.default_rng(3)
+    params = O.init_params(rng, obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    target = O.init_params(np.random.default_rng(1003), obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    batches = [make_batch(rng, B, obs, A, True) for _ in range(5)]
+    out = []
+    for pipelined in (False, True):
+        agent = iDQN(0, obs, A, K, feats, "cnn", 3e-4, 0.99, 1, 1, 8, 4, 1.5e-4)
+        agent.params, agent.target_params = params, target
+        eng, losses, pending = agent._engine, [], None
+        for b in batches:
+            if pipelined:
+                t = eng.submit_host(b)
+                if pending is not None:
+                    losses.append(eng.wait_losses(pending))
+                pending = t
+            else:
+                losses.append(eng.learn_host(b, want_losses=True))
+        if pipelined:
+            losses.append(eng.wait_losses(pending))
+            with pytest.raises(Exception):
+                eng.wait_losses(0)  # only the two most recent tickets can be waited on
+        out.append((np.stack(losses), agent.params.to_host()))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    assert_tree_close(out[0][1], out[1][1], 0.0, "params after pipelined steps")

@@ -32,6 +32,8 @@ def _worker(rank, world, port, k_total, stride, events, q):
     target_g = rng.standard_normal((k_total, stride)).astype(np.float32)
     online = torch.from_numpy(online_g[start:start + cnt].copy())
     target = torch.from_numpy(target_g[start:start + cnt].copy())
+    if cnt:
+        parallel.warm_up_links(online[0], rank, parts, dist)  # scratch tensors only: must not change any head
     for ev in events:
         if ev == "T":
             target.copy_(online)
