@@ -35,7 +35,8 @@ void idqn_set_error(const char* fmt, ...);
 // kernel of the stream / graph may then be scheduled as SM resources free up and run its prologue: barrier init,
 // TMEM allocation, tensor-map prefetch, weight tiles) and pdl_wait() before it touches anything the step produces
 // (full completion + visibility of all earlier kernels).  Without the launch attribute both are no-ops.
-// Measured on B200 (K = 5 step, CUDA graph): 0.481 ms with the attribute, 0.458 ms without -- opt-in (IDQN_F_PDL).
+// Measured on B200 (K = 5 step, CUDA graph): 0.353 ms with the attribute, 0.358 ms without -- on unless IDQN_F_NO_PDL
+// (an earlier generation of the conv kernels measured 0.481 vs 0.458 ms the other way round).
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -179,7 +180,8 @@ struct idqn_handle {
   float* h_loss;
   int32_t* h_i32;
   // CUDA graph of one learn step, per input dtype (0: f32, 1: u8)
-  cudaGraphExec_t graph[2];
+  cudaGraphExec_t graph[6];  // [staging set: 0 = s/s2/..., 1 + i = pipelined slot i][input dtype]
+  int graph_set;             // staging set the next step reads (idqn_submit_batch_host points the step at its slot)
   int sm_count;
   // launch accounting / live per-kernel timing (idqn_profile_step)
   int n_launch;          // kernels enqueued by the last enqueue_learn_step

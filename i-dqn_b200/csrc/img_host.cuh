@@ -404,8 +404,12 @@ static int img_launch_s2d(idqn_handle* h, int x_u8) {
   ImgHost* H = (ImgHost*)h->img_host;
   img::S2dArgs a = H->s2d;
   a.u8 = x_u8;
+  a.src[0] = h->s, a.src[1] = h->s2;  // the staging set of this step (idqn_submit_batch_host points it at its slot)
   const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
-  CK(launch_pdl(h->pdl, img::s2d_input_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, h->stream, a));
+  // first kernel of the step: launched WITHOUT the programmatic attribute, so everything enqueued before the step (the
+  // previous step's Adam kernels when the step is not graph-replayed) has completed before any kernel of this step --
+  // several of which prefetch weight tiles ahead of their griddepcontrol.wait -- can start
+  CK(launch_pdl(false, img::s2d_input_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, h->stream, a));
   mark(h, "s2d_input_L%d", 0);
   return IDQN_OK;
 }

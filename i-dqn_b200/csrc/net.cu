@@ -1005,17 +1005,18 @@ int idqn_learn_step_resident(idqn_handle* h, int x_u8, float* losses_host) {
     int rc = enqueue_learn_step(h, x_u8);
     if (rc) return rc;
   } else {
-    if (!h->graph[x_u8]) {
+    cudaGraphExec_t& gexec = h->graph[2 * h->graph_set + x_u8];
+    if (!gexec) {
       cudaGraph_t g;
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       int rc = enqueue_learn_step(h, x_u8);
       cudaError_t e = cudaStreamEndCapture(h->stream, &g);
       if (rc) return rc;
       CK(e);
-      CK(cudaGraphInstantiate(&h->graph[x_u8], g, 0));
+      CK(cudaGraphInstantiate(&gexec, g, 0));
       CK(cudaGraphDestroy(g));
     }
-    CK(cudaGraphLaunch(h->graph[x_u8], h->stream));
+    CK(cudaGraphLaunch(gexec, h->stream));
   }
   if (losses_host) {
     CK(cudaMemcpyAsync(h->h_loss, h->loss, sizeof(float) * h->K, cudaMemcpyDeviceToHost, h->stream));
@@ -1145,7 +1146,7 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
     CK(cudaMemcpyAsync(h->ones, &one_bits, 2, cudaMemcpyHostToDevice, h->stream));
     h->planes_dirty[0] = h->planes_dirty[1] = 0;  // all-zero weights have all-zero planes
   }
-  h->pdl = (cfg->flags & IDQN_F_PDL) ? 1 : 0;  // measured: 0.481 ms/step with PDL vs 0.458 without (B200, K=5)
+  h->pdl = (cfg->flags & IDQN_F_NO_PDL) ? 0 : 1;  // measured: 0.353 ms/step with PDL vs 0.358 without (B200, K=5)
   rc = img_setup(h);
   if (rc) return rc;
   // split-K workspace: maximum over every launch the step (and a stand-alone apply) will make
@@ -1177,7 +1178,7 @@ extern "C" int idqn_destroy(idqn_handle* h) {
   if (!h) return IDQN_OK;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 6; ++i)
     if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
   for (int i = 0; i <= IDQN_PROF_MAX; ++i)
     if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
@@ -1376,12 +1377,21 @@ extern "C" int idqn_submit_batch_host(idqn_handle* h, const void* s, const void*
   CK(cudaMemcpyAsync(h->alt_terminal[slot], d, h->B, cudaMemcpyHostToDevice, h->copy_stream));
   CK(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
-  rc = stage_batch(h, h->alt_s[slot], h->alt_s2[slot], u8, h->alt_action[slot], h->alt_reward[slot], h->alt_terminal[slot],
-                   cudaMemcpyDeviceToDevice);
+  {
+    // the step reads the slot in place: one captured graph per slot, no device-to-device staging copies
+    void *s0 = h->s, *s20 = h->s2;
+    int32_t* a0 = h->action;
+    float* r0 = h->reward;
+    uint8_t* d0 = h->terminal;
+    h->s = h->alt_s[slot], h->s2 = h->alt_s2[slot], h->action = h->alt_action[slot], h->reward = h->alt_reward[slot];
+    h->terminal = h->alt_terminal[slot];
+    h->graph_set = 1 + slot;
+    rc = idqn_learn_step_resident(h, u8, nullptr);
+    h->graph_set = 0;
+    h->s = s0, h->s2 = s20, h->action = a0, h->reward = r0, h->terminal = d0;
+  }
   if (rc) return rc;
   CK(cudaEventRecord(h->ev_consumed[slot], h->stream));
-  rc = idqn_learn_step_resident(h, u8, nullptr);
-  if (rc) return rc;
   CK(cudaMemcpyAsync(h->h_loss_ring + (size_t)slot * h->K, h->loss, sizeof(float) * h->K, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev_done[slot], h->stream));
   *ticket = t;

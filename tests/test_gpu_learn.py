@@ -143,10 +143,11 @@ def test_nature_cnn_generic_tensor_path():
     run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 2, 2, 2, 3, 3e-4, 1.5e-4, u8=True, flags=_lib.F_NO_IMG)
 
 
-def test_nature_cnn_programmatic_dependent_launch():
-    """IDQN_F_PDL: the step's kernels launched with programmatic stream serialization (griddepcontrol) give the same step."""
+def test_nature_cnn_without_programmatic_dependent_launch():
+    """IDQN_F_NO_PDL: the step's kernels launched without programmatic stream serialization (griddepcontrol is the
+    default) give the same step."""
     from idqn_b200 import _lib
-    run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 3, 3, 2, 3, 3e-4, 1.5e-4, u8=True, flags=_lib.F_PDL,
+    run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 3, 3, 2, 3, 3e-4, 1.5e-4, u8=True, flags=_lib.F_NO_PDL,
                check_grads=False)
 
 
