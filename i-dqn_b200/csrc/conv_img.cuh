@@ -17,7 +17,7 @@
 // ("bf16x3", fp32-faithful to ~2^-17); uint8 frames are exact in bf16 (two MMAs).
 //
 // conv_taps_kernel (fwd, dgrad): persistent CTAs walk (net, image) units.  Warp roles: 0 = TMA of the image
-// (double-buffered), 1 = TMA of the per-tap weight tiles (ring), 2 = MMA issue, 3..6 = epilogue (TMEM -> bias/relu
+// (double-buffered), 1 = TMA of the per-tap weight tiles (ring), 2 = MMA issue, 3..10 = epilogue (TMEM -> bias/relu
 // or relu' -> fp32 + the bf16 planes of the consumer's layout); accumulators double-buffered in TMEM so the
 // epilogue of unit u overlaps the MMAs of unit u+1.
 // conv_wgrad_kernel: CTA = (head, image range); M tiles = tap pairs (the second 64-row group aliases the image at
@@ -34,7 +34,8 @@ using namespace tc;
 typedef __nv_bfloat16 bf16;
 
 constexpr int MAX_TAPS = 16;
-constexpr int NTHREADS = 224;  // 7 warps
+constexpr int WG_THREADS = 320;  // wgrad: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int NTHREADS = 352;  // 11 warps: TMA image, TMA weights, MMA issue, 8 epilogue warps
 
 // debug timeline (IDQN_TL=<kernel tag> in the environment): lane 0 of every role of CTA 0 stamps clock64 at its
 // pipeline events; read back with idqn_debug_timeline.  Costs one predictable branch when off.
@@ -154,7 +155,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 1);
-      mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
     }
     for (int i = 0; i < p.ring; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
     fence_mbar_init();
@@ -283,8 +284,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     __syncwarp();
     pdl_trigger();  // the bulk of this CTA's work is queued
   } else {
-    // ===== epilogue warps 3..6: TMEM lane quadrant = warp % 4 =====
-    const int q = warp & 3;
+    // ===== epilogue warps 3..10: TMEM lane quadrant = warp % 4, 32-column chunks of parity (warp - 3) / 4 =====
+    const int q = warp & 3, chalf = (warp - 3) >> 2;
     const int r = q * 32 + lane;  // row inside the tile
     pdl_wait();
     int ai = 0;
@@ -309,7 +310,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       }
       // 32 columns per iteration; every load of the iteration (TMEM, bias / relu mask) is issued before the first
       // use so the four epilogue warps expose one memory latency per iteration, not one per access
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      for (int c0 = chalf * 32; c0 < N; c0 += 64) {
         float v[32], v2[32];
         tmem_ld16_nowait(taddr + c0, v);
         tmem_ld16_nowait(taddr + c0 + 16, v + 16);
@@ -442,7 +443,7 @@ __host__ __device__ inline WgradSmem wgrad_smem(const WgradArgs& p, int a_planes
 // bias tile.  Per K = 16 step and tile: X_hi^T * [dy_hi | dy_lo] (one MMA, width 2N; the two dy planes are N groups
 // LBO = plane bytes apart) + X_lo^T * dy_hi (width N); the epilogue sums the two column sets.
 template <int A_PLANES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
                   const __grid_constant__ CUtensorMap mapZ_hi, const __grid_constant__ CUtensorMap mapZ_lo,
                   const WgradArgs p) {
@@ -469,7 +470,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < ncols) tmem_cols <<= 1;
 
-  for (uint32_t i = tid; i < L.bar_off / 16; i += 192) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid; i < L.bar_off / 16; i += WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   // ones tile (MN-major SW128, 16 k-rows x 64 m): element (k, m = 0) = 1 -> accumulator row 0 = sum_k dy[k][:]
   if (tid < 16) {
@@ -563,9 +564,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
       }
     }
   }
-  // ===== epilogue: warps 2..5 (quadrant = warp % 4) write the partial gradient =====
+  // ===== epilogue: warps 2..9 (quadrant = warp % 4, 16-column chunks of parity (warp - 2) / 4) write the partial gradient =====
   if (warp >= 2) {
-    const int q = warp & 3, r = q * 32 + lane;
+    const int q = warp & 3, r = q * 32 + lane, chalf = (warp - 2) >> 2;
     pdl_wait();
     mbar_wait(done, 0);
     tcgen05_after_sync();
@@ -584,7 +585,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
         arow = p.b_off, sc = 1.f;
       }
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)t * N2;
-      for (int c0 = 0; c0 < N; c0 += 16) {
+      for (int c0 = chalf * 16; c0 < N; c0 += 32) {
         float v[16], v2[16];
         tmem_ld16_nowait(taddr + c0, v);
         tmem_ld16_nowait(taddr + N + c0, v2);

@@ -446,11 +446,11 @@ static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
   const int grid = a.heads * a.groups * a.tsplit;
   if (a_planes == 1) {
     CK(img_set_smem(img::conv_wgrad_kernel<1>, L.total));
-    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<1>, dim3(grid), dim3(192), L.total, h->stream, S.mapX[0], S.mapX[1],
+    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<1>, dim3(grid), dim3(img::WG_THREADS), L.total, h->stream, S.mapX[0], S.mapX[1],
                   S.mapZ[0], S.mapZ[1], a));
   } else {
     CK(img_set_smem(img::conv_wgrad_kernel<2>, L.total));
-    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<2>, dim3(grid), dim3(192), L.total, h->stream, S.mapX[0], S.mapX[1],
+    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<2>, dim3(grid), dim3(img::WG_THREADS), L.total, h->stream, S.mapX[0], S.mapX[1],
                   S.mapZ[0], S.mapZ[1], a));
   }
   CK(cudaGetLastError());

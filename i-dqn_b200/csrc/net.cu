@@ -375,19 +375,30 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
   const int64_t base = (int64_t)k * stride4 + off4;
   for (int64_t i = (int64_t)bx * blockDim.x + threadIdx.x; i < n4; i += (int64_t)nbx * blockDim.x) {
     float4 G;
+    const float4 P0 = p[base + i], M0 = m[base + i], V0 = v[base + i];  // requested before the partial sums are needed
     if (part) {
       G = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4* src = part + (int64_t)k * groups * span4 + off4 + i;
+      if (groups <= 16) {
+        // every partial of this quad is requested before the first add: one memory round trip; fixed summation order
+        float4 t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = u < groups ? __ldcs(src + (int64_t)u * span4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (u < groups) G.x += t[u].x, G.y += t[u].y, G.z += t[u].z, G.w += t[u].w;
+      } else {
 #pragma unroll 4
-      for (int u = 0; u < groups; ++u) {
-        const float4 t = __ldcs(src + (int64_t)u * span4);
-        G.x += t.x, G.y += t.y, G.z += t.z, G.w += t.w;
+        for (int u = 0; u < groups; ++u) {
+          const float4 t = __ldcs(src + (int64_t)u * span4);
+          G.x += t.x, G.y += t.y, G.z += t.z, G.w += t.w;
+        }
       }
       if (gout) gout[base + i] = G;
     } else {
       G = __ldcs(g + base + i);
     }
-    float4 P = p[base + i], M = m[base + i], V = v[base + i];
+    float4 P = P0, M = M0, V = V0;
     tc::adam_elem(ac, G.x, P.x, M.x, V.x);
     tc::adam_elem(ac, G.y, P.y, M.y, V.y);
     tc::adam_elem(ac, G.z, P.z, M.z, V.z);
