@@ -180,7 +180,18 @@ struct idqn_handle {
   float* h_loss;
   int32_t* h_i32;
   // CUDA graph of one learn step, per input dtype (0: f32, 1: u8)
-  cudaGraphExec_t graph[6];  // [staging set: 0 = s/s2/..., 1 + i = pipelined slot i][input dtype]
+  cudaGraphExec_t graph[8];  // [staging set: 0 = s/s2/..., 1 + i = pipelined slot i, 3 = replay slots in place][input dtype]
+  // replay-direct input (idqn_learn_from_replay on the image path): the first kernel of the step reads the frames
+  // straight from the replay slots and gathers the scalars -- no gather kernel, no staging copy
+  struct {
+    const uint8_t *state, *next_state;
+    const int64_t* slots;
+    int64_t state_bytes;
+    const int32_t* action;
+    const double* reward;
+    const uint8_t* terminal;
+  } rsrc;
+  int rsrc_on;
   int graph_set;             // staging set the next step reads (idqn_submit_batch_host points the step at its slot)
   int sm_count;
   // launch accounting / live per-kernel timing (idqn_profile_step)

@@ -609,6 +609,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
 // staged batch (uint8 or fp32 NHWC) -> X2 planes of the first conv layer (space-to-depth, padded, pitched)
 struct S2dArgs {
   const void* src[2];  // state, next_state
+  // slots != nullptr: image im of source g lives at src[g] + slots[im] * src_stride (replay slots read in place) and
+  // thread b < imgs of block 0 also gathers the scalars of sample b into the learner's staging
+  const int64_t* slots;
+  int64_t src_stride;
+  const int32_t* g_action;
+  const double* g_reward;
+  const uint8_t* g_terminal;
+  int32_t* o_action;
+  float* o_reward;
+  uint8_t* o_terminal;
   int u8, imgs, IH, IW, IC, s, ph, pw, BH, BW, P, C2;
   int64_t img_rows;    // allocated rows per image
   bf16 *hi, *lo;       // [2][imgs][img_rows][C2]
@@ -619,6 +629,13 @@ __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
   pdl_wait();
   const int run = a.s * a.IC;
   const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
+  const int64_t img_elems = (int64_t)a.IH * a.IW * a.IC;
+  if (a.slots && blockIdx.x == 0 && (int)threadIdx.x < a.imgs) {
+    const int64_t slot = a.slots[threadIdx.x];
+    a.o_action[threadIdx.x] = a.g_action[slot];
+    a.o_reward[threadIdx.x] = __double2float_rn(a.g_reward[slot]);
+    a.o_terminal[threadIdx.x] = a.g_terminal[slot];
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = i;
     const int ry = (int)(t % a.s);
@@ -632,14 +649,14 @@ __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
     const int64_t o = (((int64_t)g * a.imgs + im) * a.img_rows + (int64_t)by * a.P + bx) * a.C2 + (int64_t)ry * run;
     if (a.u8 && a.IC == 4 && a.s == 4 && (a.pw & 1) == 0 && (a.IW & 1) == 0) {
       // Atari frames: the run is 4 pixels x 4 stacked frames = 16 source bytes, 8-byte aligned pixel pairs
-      const uint8_t* src = (const uint8_t*)(g ? a.src[1] : a.src[0]);
+      const uint8_t* src = (const uint8_t*)(g ? a.src[1] : a.src[0]) + (a.slots ? a.slots[im] * a.src_stride : (int64_t)im * img_elems);
       const int ix0 = bx * 4 - a.pw;
       uint2 raw[2];
 #pragma unroll
       for (int hp = 0; hp < 2; ++hp) {
         const int ix = ix0 + 2 * hp;
         const bool ok = (unsigned)iy < (unsigned)a.IH && ix >= 0 && ix + 1 < a.IW;
-        raw[hp] = ok ? __ldg(reinterpret_cast<const uint2*>(src + (((int64_t)im * a.IH + iy) * a.IW + ix) * 4)) : make_uint2(0, 0);
+        raw[hp] = ok ? __ldg(reinterpret_cast<const uint2*>(src + ((int64_t)iy * a.IW + ix) * 4)) : make_uint2(0, 0);
       }
       const uint32_t w[4] = {raw[0].x, raw[0].y, raw[1].x, raw[1].y};
 #pragma unroll
@@ -659,9 +676,10 @@ __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
         const int ix = bx * a.s + rx - a.pw;
         float v = 0.f;
         if ((unsigned)iy < (unsigned)a.IH && (unsigned)ix < (unsigned)a.IW) {
-          const int64_t si = (((int64_t)im * a.IH + iy) * a.IW + ix) * a.IC + c;
+          const int64_t si = ((int64_t)iy * a.IW + ix) * a.IC + c;
           const void* src = g ? a.src[1] : a.src[0];
-          v = a.u8 ? (float)__ldg((const uint8_t*)src + si) : __ldg((const float*)src + si);
+          if (a.slots) v = (float)__ldg((const uint8_t*)src + a.slots[im] * a.src_stride + si);  // replay slots hold uint8 frames here
+          else v = a.u8 ? (float)__ldg((const uint8_t*)src + (int64_t)im * img_elems + si) : __ldg((const float*)src + (int64_t)im * img_elems + si);
         }
         x[k] = v;
       }

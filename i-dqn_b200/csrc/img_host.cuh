@@ -405,6 +405,13 @@ static int img_launch_s2d(idqn_handle* h, int x_u8) {
   img::S2dArgs a = H->s2d;
   a.u8 = x_u8;
   a.src[0] = h->s, a.src[1] = h->s2;  // the staging set of this step (idqn_submit_batch_host points it at its slot)
+  a.slots = nullptr;
+  if (h->rsrc_on) {  // idqn_learn_from_replay: frames read from the replay slots in place, scalars gathered here
+    a.src[0] = h->rsrc.state, a.src[1] = h->rsrc.next_state;
+    a.slots = h->rsrc.slots, a.src_stride = h->rsrc.state_bytes;
+    a.g_action = h->rsrc.action, a.g_reward = h->rsrc.reward, a.g_terminal = h->rsrc.terminal;
+    a.o_action = h->action, a.o_reward = h->reward, a.o_terminal = h->terminal;
+  }
   const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
   // first kernel of the step: launched WITHOUT the programmatic attribute, so everything enqueued before the step (the
   // previous step's Adam kernels when the step is not graph-replayed) has completed before any kernel of this step --

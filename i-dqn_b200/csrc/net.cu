@@ -1189,7 +1189,7 @@ extern "C" int idqn_destroy(idqn_handle* h) {
   if (!h) return IDQN_OK;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 8; ++i)
     if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
   for (int i = 0; i <= IDQN_PROF_MAX; ++i)
     if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);

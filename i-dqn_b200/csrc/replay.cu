@@ -175,6 +175,23 @@ extern "C" int idqn_learn_from_replay(idqn_handle* h, idqn_replay* r, const int6
   int rc = ensure_slots(r, n);
   if (rc) return rc;
   CK(cudaMemcpyAsync(r->d_slots, slots, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->stream));
+  if (h->img_on && u8) {
+    // image path: its first kernel (space-to-depth) reads the frames from the replay slots in place and gathers the
+    // scalars; the graph of this staging set is re-captured if the store or its index buffer changed
+    if (h->rsrc.state != r->state || h->rsrc.slots != r->d_slots) {
+      for (int i = 6; i < 8; ++i)
+        if (h->graph[i]) {
+          CK(cudaGraphExecDestroy(h->graph[i]));
+          h->graph[i] = nullptr;
+        }
+    }
+    h->rsrc.state = r->state, h->rsrc.next_state = r->next_state, h->rsrc.slots = r->d_slots;
+    h->rsrc.state_bytes = r->state_bytes, h->rsrc.action = r->action, h->rsrc.reward = r->reward, h->rsrc.terminal = r->terminal;
+    h->rsrc_on = 1, h->graph_set = 3;
+    rc = idqn_learn_step_resident(h, u8, losses);
+    h->rsrc_on = 0, h->graph_set = 0;
+    return rc;
+  }
   GatherArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n;
