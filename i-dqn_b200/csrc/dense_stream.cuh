@@ -41,6 +41,9 @@ struct Args {
   float* part;          // fwd: [nets*tiles][splits][32][128]
   int* tickets;         // fwd: [nets*tiles]
   // dgrad planes destination: dyZ layout of the preceding conv layer (zP > 0) or plain
+  // L2 policy of the weight-plane loads: nets < keep_heads (online heads whose planes dense_wgrad_tma wrote evict_last)
+  // are kept, every other net's planes are streamed evict_first
+  int keep_heads;
   int zP, zW, zC, zOff;
   int64_t zRows, zstride;
   int debug;
@@ -102,16 +105,17 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
           tma::expect_tx(&full[st], L.stage_bytes);
           const uint32_t s0 = base + st * L.stage_bytes;
           const int k0 = (sp * p.kb_per_unit + kb) * BKD;
+          const uint64_t pol = net < p.keep_heads ? tma::L2_EVICT_LAST : tma::L2_EVICT_FIRST;
           if (MODE == 0) {
             // A = W^T: two 64-wide o groups x 64 i rows per plane
             for (int g = 0; g < 2; ++g) {
-              tma::load_3d(s0 + g * 8192, &mapA_hi, &full[st], tile * 128 + g * 64, k0, net);
-              tma::load_3d(s0 + L.a_bytes + g * 8192, &mapA_lo, &full[st], tile * 128 + g * 64, k0, net);
+              tma::load_3d_hint(s0 + g * 8192, &mapA_hi, &full[st], tile * 128 + g * 64, k0, net, pol);
+              tma::load_3d_hint(s0 + L.a_bytes + g * 8192, &mapA_lo, &full[st], tile * 128 + g * 64, k0, net, pol);
             }
           } else {
             // A = W: 128 i rows x 64 o
-            tma::load_3d(s0, &mapA_hi, &full[st], k0, tile * 128, net);
-            tma::load_3d(s0 + L.a_bytes, &mapA_lo, &full[st], k0, tile * 128, net);
+            tma::load_3d_hint(s0, &mapA_hi, &full[st], k0, tile * 128, net, pol);
+            tma::load_3d_hint(s0 + L.a_bytes, &mapA_lo, &full[st], k0, tile * 128, net, pol);
           }
           tma::load_3d(s0 + 2 * L.a_bytes, &mapB_hi, &full[st], k0, 0, net);
           tma::load_3d(s0 + 2 * L.a_bytes + L.b_bytes, &mapB_lo, &full[st], k0, 0, net);

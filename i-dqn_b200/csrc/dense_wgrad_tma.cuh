@@ -49,6 +49,8 @@ struct Args {
   float lr, b1, b2, eps;
   bf16 *Wh, *Wl;              // weight planes, refreshed with the new W
   float* grad;                // optional: materialised gradient (IDQN_F_KEEP_GRADS)
+  int keep_heads;             // planes of heads < keep_heads are written L2 evict_last: the next step's Dense_0 forward
+                              // and data gradient find them in L2; everything else this kernel touches is evict_first
   int64_t stride, w_off;
 };
 
@@ -122,10 +124,10 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
         const uint32_t s0 = base + st * STAGE_BYTES;
         tma::load_3d(s0 + 3 * TILE_F32, &mapX_hi, &full[st], row0, 0, z);
         tma::load_3d(s0 + 3 * TILE_F32 + X_PLANE, &mapX_lo, &full[st], row0, 0, z);
-        for (int hb = 0; hb < 2; ++hb) {  // two boxes of 256 columns per array
-          tma::load_3d(s0 + hb * (TILE_F32 / 2), &mapW, &full[st], hb * 256, row0, z);
-          tma::load_3d(s0 + TILE_F32 + hb * (TILE_F32 / 2), &mapM, &full[st], hb * 256, row0, z);
-          tma::load_3d(s0 + 2 * TILE_F32 + hb * (TILE_F32 / 2), &mapV, &full[st], hb * 256, row0, z);
+        for (int hb = 0; hb < 2; ++hb) {  // two boxes of 256 columns per array; touched once per step: evict_first
+          tma::load_3d_hint(s0 + hb * (TILE_F32 / 2), &mapW, &full[st], hb * 256, row0, z, tma::L2_EVICT_FIRST);
+          tma::load_3d_hint(s0 + TILE_F32 + hb * (TILE_F32 / 2), &mapM, &full[st], hb * 256, row0, z, tma::L2_EVICT_FIRST);
+          tma::load_3d_hint(s0 + 2 * TILE_F32 + hb * (TILE_F32 / 2), &mapV, &full[st], hb * 256, row0, z, tma::L2_EVICT_FIRST);
         }
         if (++st == STAGES) st = 0, ph ^= 1;
       }
@@ -177,6 +179,7 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
         last_z = z;
         ac = adam_coef(p.b1, p.b2, p.lr, p.eps, p.count[z]);  // count already incremented for this step
       }
+      const uint64_t plane_policy = z < p.keep_heads ? tma::L2_EVICT_LAST : tma::L2_EVICT_FIRST;
       const int ab = ti & 1;
       mbar_wait(&acc_full[ab], (ti >> 1) & 1);
       mbar_wait(&full[st], ph);  // the stage's W / mu / nu tiles (async-proxy writes) are visible after this wait
@@ -212,9 +215,9 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
       if (storer) {
         const uint32_t src = base + st * STAGE_BYTES;
         for (int hb = 0; hb < 2; ++hb) {
-          tma_store_3d(&mapW, src + hb * (TILE_F32 / 2), hb * 256, row0, z);
-          tma_store_3d(&mapM, src + TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z);
-          tma_store_3d(&mapV, src + 2 * TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z);
+          tma::store_3d_hint(&mapW, src + hb * (TILE_F32 / 2), hb * 256, row0, z, tma::L2_EVICT_FIRST);
+          tma::store_3d_hint(&mapM, src + TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, tma::L2_EVICT_FIRST);
+          tma::store_3d_hint(&mapV, src + 2 * TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, tma::L2_EVICT_FIRST);
         }
         bulk_commit();
         if (prev_st >= 0) {
@@ -226,7 +229,7 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
 #pragma unroll
       for (int e = 0; e < TM; ++e) {  // planes (and the optional gradient) after the barrier: off the stores' critical path
         const int64_t go = gb + (int64_t)e * p.O;
-        st1_planes(p.Wh + go, p.Wl + go, P[e]);
+        tma::st1_planes_hint(p.Wh + go, p.Wl + go, P[e], plane_policy);
         if (p.grad) p.grad[go] = g[e];
       }
       if (++st == STAGES) st = 0, ph ^= 1;

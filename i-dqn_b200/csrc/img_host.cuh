@@ -395,6 +395,16 @@ extern "C" int idqn_debug_timeline(unsigned long long* out, int max_entries) {
   return n;
 }
 
+// L2 eviction priorities of the Dense_0 streams: the weight planes of the first `keep` online heads are loaded / stored
+// evict_last, every other plane (target heads) and the fp32 W / mu / nu streams evict_first.  Measured (K = 5): the data
+// gradient, which re-reads the online planes ~20 us after the forward, drops from 28.7 to 22.6 us with keep = 2; the
+// planes do NOT survive from the wgrad+Adam of one step to the forward of the next (250 us, ~250 MB of other traffic),
+// and a persisting-L2 set-aside (cudaLimitPersistingL2CacheSize) makes the streaming kernels 35-100% slower.
+static int l2_keep_heads(const idqn_handle* h) {
+  static const int env = getenv("IDQN_L2_KEEP_HEADS") ? atoi(getenv("IDQN_L2_KEEP_HEADS")) : 2;
+  return std::min(env, h->K);
+}
+
 template <class Kern>
 static cudaError_t img_set_smem(Kern kern, size_t bytes) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -477,6 +487,7 @@ static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst) {
     a.yh = h->il[li - 1].dz_hi, a.yl = h->il[li - 1].dz_lo;
     a.zP = pg.P, a.zW = pg.OW, a.zC = pg.OC, a.zOff = pg.T - 1, a.zRows = pg.ZRa, a.zstride = h->il[li - 1].dz_net_stride;
   }
+  a.keep_heads = l2_keep_heads(h);
   const dense::Smem L = dense::smem_layout(a);
   const int grid = std::min(a.n_units, h->sm_count);
   if (dgrad) {
@@ -504,6 +515,7 @@ static int dense_wgrad_launch(idqn_handle* h, int tile0, int ntiles, bool keep_g
   a.lr = h->cfg.learning_rate, a.b1 = 0.9f, a.b2 = 0.999f, a.eps = h->cfg.adam_eps;
   a.Wh = h->won_hi, a.Wl = h->won_lo;
   a.grad = keep_grads ? h->grad : nullptr;
+  a.keep_heads = l2_keep_heads(h);
   a.stride = h->stride, a.w_off = l.w_off;
   const int grid = std::min(a.heads * a.ntiles, h->sm_avail);
   CK(img_set_smem(dwt::dense_wgrad_adam_kernel, dwt::SMEM_TOTAL));

@@ -50,6 +50,30 @@ __device__ __forceinline__ void load_4d(uint32_t dst, const CUtensorMap* map, ui
       : "memory");
 }
 
+// L2 eviction-priority policies for the cache_hint operand (the pre-encoded descriptors createpolicy would return)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull,
+                   L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void load_3d_hint(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                             uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], "
+      "[%2], %6;" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void store_3d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+               : "memory");
+}
+// bf16 hi/lo planes of one value, stored with an L2 eviction priority
+__device__ __forceinline__ void st1_planes_hint(__nv_bfloat16* hi, __nv_bfloat16* lo, float v, uint64_t policy) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  asm volatile("st.global.L2::cache_hint.b16 [%0], %1, %2;" ::"l"(hi), "h"(*reinterpret_cast<const unsigned short*>(&h)), "l"(policy) : "memory");
+  asm volatile("st.global.L2::cache_hint.b16 [%0], %1, %2;" ::"l"(lo), "h"(*reinterpret_cast<const unsigned short*>(&l)), "l"(policy) : "memory");
+}
+
 // UMMA layout types (cute/arch/mma_sm100_desc.hpp: UMMA::LayoutType)
 constexpr uint32_t LT_SW128 = 2, LT_SW64 = 4;
 // swizzled shared-memory matrix descriptor; saddr may be any 16-byte aligned address inside a 1024-byte aligned tile
