@@ -295,12 +295,36 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       const int net0 = g * p.nets_per_g + hg * p.hpg;
       const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
       const int ab = ai & 1;
-      mbar_wait(&acc_full[ab], (ai >> 1) & 1);
-      tcgen05_after_sync();
-      if (warp == 3 && lane == 0) tl_stamp(p.debug, 1200 + 2 * ai);
       const int m = tile * 128 + r;
       const int my = m / p.P, mx = m - my * p.P;
       const bool rowok = m < p.M_valid && mx < p.W_valid;
+      // dgrad: the relu' masks of this thread's (at most two) 32-column chunks do not depend on the accumulator:
+      // they are requested BEFORE the wait for the MMAs, so their L2 latency hides behind the MMA phase of the job
+      uint4 xa[2][4];
+      if (KIND == 1) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const int c0 = chalf * 32 + kk * 64;
+          const int blk = c0 / p.OC, ry = blk / p.s, rx = blk - ry * p.s;
+          const int iy = my * p.s + ry - p.ph, ix = mx * p.s + rx - p.pw;
+          const bool ok = c0 < N && rowok && (unsigned)iy < (unsigned)p.IH && (unsigned)ix < (unsigned)p.IW;
+          const int64_t mi = ok ? (int64_t)g * p.mask_net_stride + (((int64_t)im * p.mask_img_rows) + m) * N + c0 : 0;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) xa[kk][k4] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + mi) + k4);
+        }
+      }
+      // forward: likewise the bias of this thread's first chunk
+      float4 bb0[8];
+      if (KIND == 0) {
+        const int c0 = chalf * 32, hl = c0 / p.OC, oc = c0 - hl * p.OC;
+        const int net = net0 + ((rowok && hl < nb) ? hl : 0);
+        const float4* bias = reinterpret_cast<const float4*>(p.w.get<float>(net) + p.b_off + oc);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) bb0[k4] = __ldg(bias + k4);
+      }
+      mbar_wait(&acc_full[ab], (ai >> 1) & 1);
+      tcgen05_after_sync();
+      if (warp == 3 && lane == 0) tl_stamp(p.debug, 1200 + 2 * ai);
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * N2;
       // per-row bases, computed once per tile
       int64_t orow = 0, prow = 0;
@@ -323,7 +347,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           const float4* bias = reinterpret_cast<const float4*>(p.w.get<float>(net) + p.b_off + oc);
           float4 bb[8];
 #pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4) bb[k4] = __ldg(bias + k4);
+          for (int k4 = 0; k4 < 8; ++k4) bb[k4] = c0 < 64 ? bb0[k4] : __ldg(bias + k4);
           tmem_ld_wait();
           if (!ok) continue;
           float o[32];
@@ -355,16 +379,14 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           const int iy = my * p.s + ry - p.ph, ix = mx * p.s + rx - p.pw;
           const bool ok = rowok && (unsigned)iy < (unsigned)p.IH && (unsigned)ix < (unsigned)p.IW;
           // relu' mask: the layer input is this very row of the X2 hi plane (hi > 0 <=> x > 0), 32 contiguous bf16
-          const int64_t mi = ok ? (int64_t)g * p.mask_net_stride + (((int64_t)im * p.mask_img_rows) + m) * N + c0 : 0;
-          uint4 xa[4];
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) xa[k4] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + mi) + k4);
+          const int kk = c0 >> 6;  // this thread's chunk index (N <= 128: at most two chunks per thread)
           tmem_ld_wait();
           if (!ok) continue;
           float o[32];
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            const uint32_t w[4] = {xa[k4].x, xa[k4].y, xa[k4].z, xa[k4].w};
+            const uint4 xv = kk ? xa[1][k4] : xa[0][k4];
+            const uint32_t w[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const uint32_t bits = (w[e >> 1] >> (16 * (e & 1))) & 0xffffu;

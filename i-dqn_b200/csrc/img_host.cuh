@@ -196,7 +196,7 @@ static int img_setup(idqn_handle* h) {
       a.a_buf_rows = g.ZRa;
       a.P = g.P, a.M_valid = g.BH * g.P, a.W_valid = g.BW;
       a.tiles = (a.M_valid + 127) / 128;
-      a.N = g.C2;
+      a.N = g.C2;  // <= 128 (img_geom): the epilogue prefetches the relu' masks of at most two 32-column chunks per thread
       a.tpp = std::max(1, std::min(a.tiles, 128 / a.N));
       a.n_taps = g.T * g.T, a.kt = g.OC / 16;
       int shmax = 0;
