@@ -44,6 +44,7 @@ SYMBOLS = {
     "idqn_get_count": (_I, [_P, _P]),
     "idqn_arena_ptr": (_P, [_P, _I]),
     "idqn_mark_planes_dirty": (_I, [_P, _I]),
+    "idqn_mark_head_planes_dirty": (_I, [_P, _I, _I]),
     "idqn_stream": (_P, [_P]),
     "idqn_learn_on_batch_host": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
     "idqn_learn_on_batch_dev": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),

@@ -151,7 +151,7 @@ struct idqn_handle {
   __nv_bfloat16 *dact_hi, *dact_lo;                  // [K][act_stride]
   __nv_bfloat16 *in_hi, *in_lo;                      // [2][B*in_elems]  state, next_state
   __nv_bfloat16* ones;                               // {1,0 x7 | 0 x8}: bias-gradient row of the wgrad GEMMs
-  int planes_dirty[2];                               // online / target planes stale (host upload)
+  unsigned long long planes_dirty[2];                // online / target planes stale: bit k = head k (bit 63: every head)
   __nv_bfloat16 *wpl_hi, *wpl_lo;                    // the allocation behind won_*/wtg_*: [2K][stride], online first
   // image-resident conv path (conv_img.cuh); img_on == 0 -> the generic kernels of gemm_tc.cuh run instead
   int img_on;

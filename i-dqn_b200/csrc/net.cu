@@ -501,11 +501,21 @@ static int launch_input_planes(idqn_handle* h, int x_u8, int nsamples, int two) 
 // weights uploaded from the host: rebuild their planes (outside the captured step)
 static int refresh_planes(idqn_handle* h) {
   for (int w = 0; w < 2; ++w) {
-    if (!h->planes_dirty[w]) continue;
-    const int64_t n8 = (int64_t)h->K * h->stride / 8;
+    unsigned long long dirty = h->planes_dirty[w];
+    if (!dirty) continue;
+    const float* src = w ? h->target : h->online;
+    __nv_bfloat16 *hi = w ? h->wtg_hi : h->won_hi, *lo = w ? h->wtg_lo : h->won_lo;
+    int first = 0, count = h->K;  // one launch over a contiguous run of heads
+    if (!(dirty >> 63)) {
+      while (!((dirty >> first) & 1ull)) ++first;
+      int last = first;
+      for (int k = first; k < h->K && k < 63; ++k)
+        if ((dirty >> k) & 1ull) last = k;
+      count = last - first + 1;
+    }
+    const int64_t n8 = (int64_t)count * h->stride / 8, o = (int64_t)first * h->stride;
     const int blocks = (int)std::min<int64_t>((n8 + 255) / 256, 8192);
-    tcg::to_planes_kernel<<<blocks, 256, 0, h->stream>>>(w ? h->target : h->online, w ? h->wtg_hi : h->won_hi,
-                                                       w ? h->wtg_lo : h->won_lo, n8);
+    tcg::to_planes_kernel<<<blocks, 256, 0, h->stream>>>(src + o, hi + o, lo + o, n8);
     CK(cudaGetLastError());
     h->planes_dirty[w] = 0;
   }
@@ -1277,8 +1287,8 @@ extern "C" int idqn_upload(idqn_handle* h, int which, int head, int64_t offset, 
   CK(cudaMemcpyAsync(a + (int64_t)head * h->stride + offset, src, sizeof(float) * n, cudaMemcpyHostToDevice,
                      h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (which == IDQN_ONLINE) h->planes_dirty[0] = 1;
-  if (which == IDQN_TARGET) h->planes_dirty[1] = 1;
+  if (which == IDQN_ONLINE) h->planes_dirty[0] |= head < 63 ? 1ull << head : 1ull << 63;
+  if (which == IDQN_TARGET) h->planes_dirty[1] |= head < 63 ? 1ull << head : 1ull << 63;
   return IDQN_OK;
 }
 extern "C" int idqn_download(idqn_handle* h, int which, int head, int64_t offset, float* dst, int64_t n) {
@@ -1465,7 +1475,13 @@ extern "C" int idqn_copy_online_to_target(idqn_handle* h) {  // idqn.py:78, dqn.
 // planes of externally modified arenas (NCCL / peer copies into idqn_arena_ptr memory) must be rebuilt
 extern "C" int idqn_mark_planes_dirty(idqn_handle* h, int which) {
   REQUIRE(h && (which == IDQN_ONLINE || which == IDQN_TARGET), "bad argument");
-  h->planes_dirty[which == IDQN_TARGET] = 1;
+  h->planes_dirty[which == IDQN_TARGET] = 1ull << 63;
+  return IDQN_OK;
+}
+// the same for ONE head (the neighbour exchange of the sharded agent rewrites a single boundary head)
+extern "C" int idqn_mark_head_planes_dirty(idqn_handle* h, int which, int head) {
+  REQUIRE(h && (which == IDQN_ONLINE || which == IDQN_TARGET) && head >= 0 && head < h->K, "bad argument");
+  h->planes_dirty[which == IDQN_TARGET] |= head < 63 ? 1ull << head : 1ull << 63;
   return IDQN_OK;
 }
 

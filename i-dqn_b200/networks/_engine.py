@@ -300,6 +300,10 @@ class Engine:
         L.check(self.lib.idqn_best_action(self.h, which, head, L.ptr(x), int(u8), C.byref(out)))
         return int(out.value)
 
+    def mark_head_planes_dirty(self, which: int, head: int) -> None:
+        """One head of an arena was rewritten behind the library's back (neighbour exchange): rebuild its planes."""
+        L.check(self.lib.idqn_mark_head_planes_dirty(self.h, which, int(head)))
+
     def mark_planes_dirty(self, which: int) -> None:
         """An arena was written through its raw pointer (NCCL recv / peer copy): rebuild its bf16 operand planes."""
         L.check(self.lib.idqn_mark_planes_dirty(self.h, which))

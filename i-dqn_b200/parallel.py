@@ -37,8 +37,10 @@ def _neighbours(rank: int, parts: List[Tuple[int, int]]):
     return prev, nxt
 
 
-def exchange_for_sync(online, target, rank: int, parts, dist, group=None) -> None:
-    """sync_target_params (idqn.py:20-24) across shards.  ``online``/``target``: [K_local, stride] tensors."""
+def exchange_for_sync(online, target, rank: int, parts, dist, group=None, local_sync=None) -> None:
+    """sync_target_params (idqn.py:20-24) across shards.  ``online``/``target``: [K_local, stride] tensors.
+    ``local_sync``: callable that performs the in-shard part ``target[1:] <- online[:-1]`` (the engine's own
+    ``sync_target``, which also moves the bf16 planes); default: a tensor copy."""
     import torch
 
     k_local = parts[rank][1]
@@ -53,7 +55,9 @@ def exchange_for_sync(online, target, rank: int, parts, dist, group=None) -> Non
         recv = torch.empty_like(target[0])
         ops.append(dist.P2POp(dist.irecv, recv, prev, group))
     reqs = dist.batch_isend_irecv(ops) if ops else []
-    if k_local > 1:
+    if local_sync is not None:
+        local_sync()
+    elif k_local > 1:
         target[1:].copy_(online[:-1])
     for r in reqs:
         r.wait()
@@ -61,8 +65,9 @@ def exchange_for_sync(online, target, rank: int, parts, dist, group=None) -> Non
         target[0].copy_(recv)
 
 
-def exchange_for_shift(online, rank: int, parts, dist, group=None) -> None:
-    """shift_params (idqn.py:13-17) across shards: online[k] <- online[k+1] over the GLOBAL head index."""
+def exchange_for_shift(online, rank: int, parts, dist, group=None, local_shift=None) -> None:
+    """shift_params (idqn.py:13-17) across shards: online[k] <- online[k+1] over the GLOBAL head index.
+    ``local_shift``: callable for the in-shard part (the engine's ``shift_params``); default: tensor copies."""
     import torch
 
     k_local = parts[rank][1]
@@ -79,8 +84,11 @@ def exchange_for_shift(online, rank: int, parts, dist, group=None) -> None:
         recv = torch.empty_like(online[0])
         ops.append(dist.P2POp(dist.irecv, recv, nxt, group))
     reqs = dist.batch_isend_irecv(ops) if ops else []
-    for k in range(k_local - 1):
-        online[k].copy_(online[k + 1])
+    if local_shift is not None:
+        local_shift()
+    else:
+        for k in range(k_local - 1):
+            online[k].copy_(online[k + 1])
     for r in reqs:
         r.wait()
     if recv is not None:
@@ -150,8 +158,9 @@ def make_sharded_idqn(key, observation_dim, n_actions, n_networks_total: int, fe
             if step % self.target_update_frequency == 0:
                 eng.copy_online_to_target()
                 with torch.cuda.stream(self._stream):
-                    exchange_for_shift(self._online, rank, parts, dist, group)
-                eng.mark_planes_dirty(L.ONLINE)  # the arena was rewritten behind the library's back
+                    exchange_for_shift(self._online, rank, parts, dist, group, local_shift=eng.shift_params)
+                if _neighbours(rank, parts)[1] is not None:  # the last slot was rewritten behind the library's back
+                    eng.mark_head_planes_dirty(L.ONLINE, k_local - 1)
                 cumulated = eng.cumulated_losses(reset=True)
                 denom = self.target_update_frequency / self.update_to_data
                 logs = {"loss": np.mean(cumulated) / denom}
@@ -160,8 +169,9 @@ def make_sharded_idqn(key, observation_dim, n_actions, n_networks_total: int, fe
                 return True, logs
             if step % self.target_sync_frequency == 0:
                 with torch.cuda.stream(self._stream):
-                    exchange_for_sync(self._online, self._target, rank, parts, dist, group)
-                eng.mark_planes_dirty(L.TARGET)
+                    exchange_for_sync(self._online, self._target, rank, parts, dist, group, local_sync=eng.sync_target)
+                if _neighbours(rank, parts)[0] is not None:
+                    eng.mark_head_planes_dirty(L.TARGET, 0)
             return False, {}
 
     torch.cuda.set_device(device)

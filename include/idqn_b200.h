@@ -99,6 +99,7 @@ void* idqn_arena_ptr(idqn_handle* h, int which);
 /* after writing an online/target arena through idqn_arena_ptr (NCCL recv, peer copy): its bf16 operand planes are
  * rebuilt before the next step */
 int idqn_mark_planes_dirty(idqn_handle* h, int which);
+int idqn_mark_head_planes_dirty(idqn_handle* h, int which, int head);  /* one head only (neighbour exchange of the sharded agent) */
 void* idqn_stream(idqn_handle* h);
 
 /* iDQN.learn_on_batch (idqn.py:96-109) / DQN.learn_on_batch (dqn.py:60-72) on the handle's resident state:
