@@ -49,8 +49,9 @@ struct Args {
   float lr, b1, b2, eps;
   bf16 *Wh, *Wl;              // weight planes, refreshed with the new W
   float* grad;                // optional: materialised gradient (IDQN_F_KEEP_GRADS)
+  unsigned long long stream_policy;  // L2 policy of the W / mu / nu loads and stores
   int keep_heads;             // planes of heads < keep_heads are written L2 evict_last: the next step's Dense_0 forward
-                              // and data gradient find them in L2; everything else this kernel touches is evict_first
+                              // and data gradient find them in L2; the other planes are evict_first
   int64_t stride, w_off;
 };
 
@@ -124,10 +125,10 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
         const uint32_t s0 = base + st * STAGE_BYTES;
         tma::load_3d(s0 + 3 * TILE_F32, &mapX_hi, &full[st], row0, 0, z);
         tma::load_3d(s0 + 3 * TILE_F32 + X_PLANE, &mapX_lo, &full[st], row0, 0, z);
-        for (int hb = 0; hb < 2; ++hb) {  // two boxes of 256 columns per array; touched once per step: evict_first
-          tma::load_3d_hint(s0 + hb * (TILE_F32 / 2), &mapW, &full[st], hb * 256, row0, z, tma::L2_EVICT_FIRST);
-          tma::load_3d_hint(s0 + TILE_F32 + hb * (TILE_F32 / 2), &mapM, &full[st], hb * 256, row0, z, tma::L2_EVICT_FIRST);
-          tma::load_3d_hint(s0 + 2 * TILE_F32 + hb * (TILE_F32 / 2), &mapV, &full[st], hb * 256, row0, z, tma::L2_EVICT_FIRST);
+        for (int hb = 0; hb < 2; ++hb) {  // two boxes of 256 columns per array
+          tma::load_3d_hint(s0 + hb * (TILE_F32 / 2), &mapW, &full[st], hb * 256, row0, z, p.stream_policy);
+          tma::load_3d_hint(s0 + TILE_F32 + hb * (TILE_F32 / 2), &mapM, &full[st], hb * 256, row0, z, p.stream_policy);
+          tma::load_3d_hint(s0 + 2 * TILE_F32 + hb * (TILE_F32 / 2), &mapV, &full[st], hb * 256, row0, z, p.stream_policy);
         }
         if (++st == STAGES) st = 0, ph ^= 1;
       }
@@ -215,9 +216,9 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
       if (storer) {
         const uint32_t src = base + st * STAGE_BYTES;
         for (int hb = 0; hb < 2; ++hb) {
-          tma::store_3d_hint(&mapW, src + hb * (TILE_F32 / 2), hb * 256, row0, z, tma::L2_EVICT_FIRST);
-          tma::store_3d_hint(&mapM, src + TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, tma::L2_EVICT_FIRST);
-          tma::store_3d_hint(&mapV, src + 2 * TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, tma::L2_EVICT_FIRST);
+          tma::store_3d_hint(&mapW, src + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
+          tma::store_3d_hint(&mapM, src + TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
+          tma::store_3d_hint(&mapV, src + 2 * TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
         }
         bulk_commit();
         if (prev_st >= 0) {

@@ -516,6 +516,9 @@ static int dense_wgrad_launch(idqn_handle* h, int tile0, int ntiles, bool keep_g
   a.Wh = h->won_hi, a.Wl = h->won_lo;
   a.grad = keep_grads ? h->grad : nullptr;
   a.keep_heads = l2_keep_heads(h);
+  // measured: 98.6 us with the default policy for the fp32 streams, 100.8 us with evict_first
+  static const int sp = getenv("IDQN_L2_STREAM") ? atoi(getenv("IDQN_L2_STREAM")) : 0;
+  a.stream_policy = sp == 0 ? tma::L2_EVICT_NORMAL : (sp == 2 ? tma::L2_EVICT_LAST : tma::L2_EVICT_FIRST);
   a.stride = h->stride, a.w_off = l.w_off;
   const int grid = std::min(a.heads * a.ntiles, h->sm_avail);
   CK(img_set_smem(dwt::dense_wgrad_adam_kernel, dwt::SMEM_TOTAL));
