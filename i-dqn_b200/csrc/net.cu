@@ -824,17 +824,27 @@ static int launch_dgrad_layer(idqn_handle* h, int li, bool img_dst = false) {
 }
 
 // Adam over the arena ranges [off_a, off_a + len_a) and [off_b, off_b + len_b) of every head, one launch
+// coresident: 128-thread CTAs (one 64-register warp per SM sub-partition) with the shared-memory carve-out of the big
+// kernels, so that the launch runs NEXT to the persistent Dense_0 wgrad+Adam CTAs instead of after them
 static int launch_adam_ranges(idqn_handle* h, int64_t off_a, int64_t len_a, bool a_from_partials, int64_t off_b,
-                              int64_t len_b) {
+                              int64_t len_b, bool coresident = false) {
   len_a = std::max<int64_t>(len_a, 0), len_b = std::max<int64_t>(len_b, 0);
   if (len_a + len_b <= 0) return IDQN_OK;
   const int64_t n4a = len_a / 4, n4b = len_b / 4;
   const int cap = h->sm_count * 8;
-  const int ba = n4a ? (int)std::min<int64_t>((n4a + 255) / 256, cap) : 0;
-  const int bb = n4b ? (int)std::min<int64_t>((n4b + 255) / 256, cap) : 0;
+  const int bt = coresident ? 128 : 256;
+  const int ba = n4a ? (int)std::min<int64_t>((n4a + bt - 1) / bt, cap) : 0;
+  const int bb = n4b ? (int)std::min<int64_t>((n4b + bt - 1) / bt, cap) : 0;
+  if (coresident) {
+    static bool carve_set = false;
+    if (!carve_set) {
+      CK(cudaFuncSetAttribute(adam_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carve_set = true;
+    }
+  }
   dim3 grid(std::max(ba + bb, 1), h->K);
   const bool keep = (h->cfg.flags & IDQN_F_KEEP_GRADS) != 0;
-  CK(launch_pdl(h->pdl, adam_kernel, grid, dim3(256), 0, h->stream, (float4*)h->online, (const float4*)h->grad, (float4*)h->mu, (float4*)h->nu,
+  CK(launch_pdl(h->pdl && !coresident, adam_kernel, grid, dim3(bt), 0, h->stream, (float4*)h->online, (const float4*)h->grad, (float4*)h->mu, (float4*)h->nu,
                                            (uint2*)h->won_hi, (uint2*)h->won_lo, h->count, h->stride / 4, off_a / 4, n4a, ba,
                                            off_b / 4, n4b, h->cfg.learning_rate, 0.9f, 0.999f, h->cfg.adam_eps,
                                            a_from_partials ? (const float4*)h->wpart : nullptr, h->wgroups, h->wspan / 4,
@@ -941,6 +951,10 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   smpart::Partition* part = (smpart::Partition*)h->partition;
   const bool split = part && use_img && n_img == L - 2 && !h->prof_on && !dry && use_dense;
   const bool fork_conv = n_img > 0 && !split && !h->prof_on && !dry && !(h->cfg.flags & IDQN_F_NO_FORK);
+  // With the two-branch graph the HBM-bound Dense_0 wgrad+Adam (TMA pipeline, one persistent CTA per SM) is deferred to
+  // the END of the backward pass: the conv chain (main: dgrads, side: wgrads) runs first, then the final Adam launch
+  // -- small CTAs that fit next to the persistent ones -- hides under the 97 us of the HBM kernel.
+  int deferred_li = -1;
   for (int li = L - 2; li >= 0; --li) {
     // the dgrad of this layer reads the weights the fused wgrad+Adam kernel overwrites: dgrad first
     if (li < n_img) {
@@ -961,6 +975,20 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
       if (fork_conv && li == 0) {
         CK(cudaEventRecord(h->ev_side_done, h->side));
         CK(cudaStreamWaitEvent(h->stream, h->ev_side_done, 0));
+        if (deferred_li >= 0) {
+          // main: the HBM kernel (after the last conv weight gradient, so it does not take the SMs from it);
+          // side: the final Adam next to it; join
+          rc = launch_wgrad_layer(h, deferred_li, x_u8, dry, ws_part, ws_tick);
+          if (rc) return rc;
+          h->stream = h->side;
+          const int64_t hi = (fused_hi + 3) / 4 * 4;
+          rc = launch_adam_ranges(h, 0, fused_lo, fused_lo == h->wspan, hi, h->stride - hi, true);
+          h->stream = main_stream;
+          if (rc) return rc;
+          CK(cudaEventRecord(h->ev_join[0], h->side));
+          CK(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+          return IDQN_OK;
+        }
       }
       continue;
     }
@@ -1005,6 +1033,10 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
       h->wg_tile0 = h->wg_tiles = 0;
       if (rc) return rc;
       break;
+    }
+    if (fused && fork_conv && li == n_img && dense_wgrad_tma_ok(h, li) && !(h->cfg.flags & IDQN_F_NO_DEFER)) {
+      deferred_li = li;
+      continue;
     }
     int rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
     if (rc) return rc;

@@ -156,7 +156,7 @@ def test_nature_cnn_backward_variants():
     Adam in its epilogue (IDQN_F_OLD_WGRAD), the un-graphed order, the single-branch graph (IDQN_F_NO_FORK), and the backward pass split over two SM partitions
     (green contexts, IDQN_F_PARTITION, graphed and un-graphed) are the same step."""
     from idqn_b200 import _lib
-    for flags in (_lib.F_NO_GRAPH, _lib.F_OLD_WGRAD, _lib.F_NO_FORK, _lib.F_PARTITION, _lib.F_PARTITION | _lib.F_NO_GRAPH,
+    for flags in (_lib.F_NO_GRAPH, _lib.F_OLD_WGRAD, _lib.F_NO_FORK, _lib.F_NO_DEFER, _lib.F_PARTITION, _lib.F_PARTITION | _lib.F_NO_GRAPH,
                   _lib.F_PARTITION | _lib.F_OLD_WGRAD):
         run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 2, 2, 2, 3, 3e-4, 1.5e-4, u8=True, flags=flags)
 
