@@ -166,6 +166,11 @@ def test_nature_cnn_k5_production_path():
     run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 5, 2, 8, 2, 3e-4, 1.5e-4, u8=True, check_grads=False)
 
 
+def test_nature_cnn_k8_production_path():
+    """configs[3] on one GPU: K = 8 heads (three head groups on the first layer, 16 Dense_0 nets)."""
+    run_parity("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 8, 1, 8, 2, 3e-4, 1.5e-4, u8=True, check_grads=False)
+
+
 def test_nature_cnn_simt_cross_check():
     """the exact-fp32 CUDA-core path (IDQN_F_SIMT_ONLY) stays a valid implementation of the same step."""
     from idqn_b200 import _lib
