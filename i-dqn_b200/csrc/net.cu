@@ -1473,9 +1473,16 @@ extern "C" int idqn_read_cumulated_losses(idqn_handle* h, double* sums, int rese
 }
 
 // the target events move the bf16 planes together with their fp32 masters
+// The three target events move the bf16 planes together with the fp32 arenas: planes that are still stale (arena
+// uploaded or rewritten since the last step) are rebuilt FIRST, otherwise the copy would propagate stale planes into
+// an arena whose dirty bit is clear (a freshly constructed agent does upload(ONLINE) + copy_online_to_target()).
 extern "C" int idqn_shift_params(idqn_handle* h) {  // idqn.py:13-17
   REQUIRE(h, "null handle");
   CK(cudaSetDevice(h->cfg.device));
+  {
+    int rc = refresh_planes(h);
+    if (rc) return rc;
+  }
   for (int k = 0; k + 1 < h->K; ++k) {
     const int64_t d = (int64_t)k * h->stride, s = (int64_t)(k + 1) * h->stride;
     CK(cudaMemcpyAsync(h->online + d, h->online + s, sizeof(float) * h->stride, cudaMemcpyDeviceToDevice, h->stream));
@@ -1487,6 +1494,10 @@ extern "C" int idqn_shift_params(idqn_handle* h) {  // idqn.py:13-17
 extern "C" int idqn_sync_target(idqn_handle* h) {  // idqn.py:20-24
   REQUIRE(h, "null handle");
   CK(cudaSetDevice(h->cfg.device));
+  {
+    int rc = refresh_planes(h);
+    if (rc) return rc;
+  }
   if (h->K > 1) {
     const int64_t n = h->stride * (h->K - 1);
     CK(cudaMemcpyAsync(h->target + h->stride, h->online, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->stream));
@@ -1498,6 +1509,10 @@ extern "C" int idqn_sync_target(idqn_handle* h) {  // idqn.py:20-24
 extern "C" int idqn_copy_online_to_target(idqn_handle* h) {  // idqn.py:78, dqn.py:52
   REQUIRE(h, "null handle");
   CK(cudaSetDevice(h->cfg.device));
+  {
+    int rc = refresh_planes(h);
+    if (rc) return rc;
+  }
   const int64_t n = h->stride * h->K;
   CK(cudaMemcpyAsync(h->target, h->online, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->wtg_hi, h->won_hi, 2 * n, cudaMemcpyDeviceToDevice, h->stream));

@@ -333,3 +333,24 @@ def test_k5_steps_are_bit_reproducible():
     np.testing.assert_array_equal(runs[0][0], runs[1][0])
     for i, what in ((1, "params"), (2, "mu"), (3, "nu")):
         assert_tree_close(runs[0][i], runs[1][i], 0.0, f"{what} after 60 steps")
+
+
+def test_freshly_constructed_agent_bootstraps_from_its_own_init():
+    """idqn.py:56 ``target_params = params``: an agent used straight from its constructor (no explicit assignment of
+    target_params) must bootstrap every head from its own initial parameters -- the bf16 planes of the target arena have
+    to follow the constructor's upload(ONLINE) + copy_online_to_target(), and stay right across a D-sync."""
+    from idqn_b200.networks.idqn import iDQN
+    obs, feats, A, K, B = (84, 84, 4), [32, 64, 64, 512], 6, 3, 32
+    rng = np.random.default_rng(21)
+    agent = iDQN(7, obs, A, K, feats, "cnn", 3e-4, 0.99, 1, 1, 100, 2, 1.5e-4)
+    for step in (1, 2, 3):
+        p0, t0 = agent.params.to_host(), agent.target_params.to_host()
+        if step == 1:
+            assert_tree_close(t0, p0, 0.0, "target == online after construction")
+        st = agent.optimizer_state[0]
+        s_o = {"count": np.asarray(st.count).copy(), "mu": st.mu.to_host(), "nu": st.nu.to_host()}
+        batch = make_batch(rng, B, obs, A, True)
+        _, _, g_l = agent.learn_on_batch(agent.params, agent.target_params, agent.optimizer_state, batch)
+        _, _, o_l = O.learn_on_batch(p0, t0, s_o, batch, "cnn", 0.99, 1, 3e-4, 1.5e-4, torch.float32)
+        np.testing.assert_allclose(g_l, o_l, rtol=RTOL, err_msg=f"losses step {step}")
+        agent.update_target_params(step)  # D-sync at step 2
