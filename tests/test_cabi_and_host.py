@@ -133,3 +133,16 @@ def test_layer_shapes_match_survey():
     assert shapes[3][1] == (7744, 512)
     assert sum(int(np.prod(k)) + int(np.prod(b)) for _, k, b in shapes) == 4_046_502
     assert [s[1] for s in layer_shapes((8,), [100, 100], "fc", 4)] == [(8, 100), (100, 100), (100, 4)]
+
+
+def test_engine_flag_constants_match_the_header():
+    """The F_* constants of the ctypes binding are the IDQN_F_* bits of include/idqn_b200.h."""
+    import re
+    from idqn_b200 import _lib
+    with open(os.path.join(ROOT, "include", "idqn_b200.h")) as f:
+        header = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"#define IDQN_F_(\w+)\s+(\d+)", f.read()))
+    assert header, "no IDQN_F_* flags found in the header"
+    bits = sorted(header.values())
+    assert len(set(bits)) == len(bits) and all(b & (b - 1) == 0 for b in bits), "flags must be distinct single bits"
+    for name, value in header.items():
+        assert getattr(_lib, "F_" + name) == value, f"F_{name} != IDQN_F_{name}"
