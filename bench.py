@@ -97,7 +97,8 @@ def cpu_reference_rate(n_heads: int, min_seconds: float, max_steps: int, warmup:
         learner.step(batch)
     times = []
     t_start = time.perf_counter()
-    while len(times) < max_steps and (time.perf_counter() - t_start < min_seconds or len(times) < 3):
+    # min_seconds > 0: a time-bounded sample (cpu_baseline leg); otherwise exactly max_steps steps (reference arm)
+    while len(times) < max_steps and (min_seconds <= 0 or time.perf_counter() - t_start < min_seconds or len(times) < 3):
         t0 = time.perf_counter()
         learner.step(batch)
         times.append(time.perf_counter() - t0)
@@ -109,12 +110,13 @@ def run_reference(args):
     if rank != 0:
         return
     n_heads = HEADS_PER_GPU * args.gpus
-    steps = max(1, min(args.steps, 40))
-    rate, n, threads = cpu_reference_rate(n_heads, min_seconds=0.0, max_steps=steps, warmup=min(max(args.warmup, 1), 2))
+    steps = max(1, min(args.steps, 40))  # bounded sample: at most 40 CPU steps (~1.5-4 s each at N = 1..8)
+    warm = min(max(args.warmup, 1), 3)
+    rate, n, threads = cpu_reference_rate(n_heads, min_seconds=0.0, max_steps=steps, warmup=warm)
     value = rate * args.gpus  # same head-normalised unit as our arm (steps/s of a K=5 agent)
     print(json.dumps({
         "impl": "reference", "metric": "i-DQN grad steps/sec (NatureCNN K=5, batch 32)", "value": value,
-        "unit": "steps/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": 1e3 / rate,
+        "unit": "steps/s", "n_gpus": args.gpus, "steps": n, "warmup": warm, "ms_per_step": 1e3 / rate,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"Atari NatureCNN i-DQN, {HEADS_PER_GPU} heads per GPU ({n_heads} total), batch 32, "
                                "84x84x4 uint8, A=6", "heads_total": n_heads},
