@@ -34,12 +34,23 @@ def _worker(rank, world, port, k_total, stride, events, q):
     target = torch.from_numpy(target_g[start:start + cnt].copy())
     if cnt:
         parallel.warm_up_links(online[0], rank, parts, dist)  # scratch tensors only: must not change any head
+    # odd ranks hand the in-shard part to callbacks, the way the CUDA agent hands it to the engine's own
+    # shift_params / sync_target (which also move the bf16 planes); even ranks use the default tensor copies
+    def local_shift():
+        for k in range(cnt - 1):
+            online[k].copy_(online[k + 1])
+
+    def local_sync():
+        if cnt > 1:
+            target[1:].copy_(online[:-1])
+
+    cb = rank % 2 == 1
     for ev in events:
         if ev == "T":
             target.copy_(online)
-            parallel.exchange_for_shift(online, rank, parts, dist)
+            parallel.exchange_for_shift(online, rank, parts, dist, local_shift=local_shift if cb else None)
         elif ev == "D":
-            parallel.exchange_for_sync(online, target, rank, parts, dist)
+            parallel.exchange_for_sync(online, target, rank, parts, dist, local_sync=local_sync if cb else None)
         else:  # "grad": heads drift independently
             online += (rank + 1) * 0.5 + torch.arange(cnt, dtype=torch.float32)[:, None]
     q.put((rank, start, online.numpy().copy(), target.numpy().copy()))
