@@ -30,6 +30,22 @@ def threefry2x32(key, x0, x1):
     return x0.astype(np.uint32), x1.astype(np.uint32)
 
 
+def _threefry_scalar(k0: int, k1: int, x0: int, x1: int):
+    """The same 20 rounds on Python ints -- the acting path draws ONE head per environment step, and numpy's
+    per-call overhead on one-element arrays (3 block evaluations per draw) costs more than the forward pass."""
+    M = 0xFFFFFFFF
+    ks = (k0, k1, k0 ^ k1 ^ 0x1BD11BDA)
+    x0 = (x0 + ks[0]) & M
+    x1 = (x1 + ks[1]) & M
+    for i in range(5):
+        for r in _ROT[i % 2]:
+            x0 = (x0 + x1) & M
+            x1 = (((x1 << r) | (x1 >> (32 - r))) & M) ^ x0
+        x0 = (x0 + ks[(i + 1) % 3]) & M
+        x1 = (x1 + ks[(i + 2) % 3] + i + 1) & M
+    return x0, x1
+
+
 def as_key(key) -> np.ndarray:
     """jax.random.PRNGKey(seed) -> uint32[2] = [seed >> 32, seed & 0xffffffff]; uint32[2] arrays pass through."""
     if isinstance(key, (int, np.integer)):
@@ -48,15 +64,27 @@ def split(key, num: int = 2) -> np.ndarray:
     return np.concatenate([y0, y1]).reshape(num, 2)
 
 
+def _key_ints(key):
+    if isinstance(key, (int, np.integer)):
+        s = int(key) & 0xFFFFFFFFFFFFFFFF
+        return s >> 32, s & 0xFFFFFFFF
+    a = as_key(key)
+    return int(a[0]), int(a[1])
+
+
 def _bits32(key) -> int:
-    y0, _ = threefry2x32(as_key(key), np.zeros(1, np.uint32), np.zeros(1, np.uint32))
-    return int(y0[0])
+    k0, k1 = _key_ints(key)
+    return _threefry_scalar(k0, k1, 0, 0)[0]
 
 
 def randint(key, minval: int, maxval: int) -> int:
     """jax.random.randint(key, (), minval, maxval) for int32."""
-    k1, k2 = split(key)
-    hi, lo = _bits32(k1), _bits32(k2)
+    k0, k1 = _key_ints(key)
+    # split(key, 2): counters [0, 1 | 2, 3] -> blocks (0, 2) and (1, 3); keys = rows of [y0_0, y0_1, y1_0, y1_1].reshape(2, 2)
+    a0, b0 = _threefry_scalar(k0, k1, 0, 2)
+    a1, b1 = _threefry_scalar(k0, k1, 1, 3)
+    hi = _threefry_scalar(a0, a1, 0, 0)[0]
+    lo = _threefry_scalar(b0, b1, 0, 0)[0]
     span = max(int(maxval) - int(minval), 1) if maxval > minval else 1
     mult = (2 ** 16) % span
     mult = (mult * mult) % span

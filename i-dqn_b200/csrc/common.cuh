@@ -176,6 +176,7 @@ struct idqn_handle {
   float* h_loss_ring;   // pinned [2][K]
   cudaEvent_t ev_h2d[2], ev_consumed[2], ev_done[2];
   int64_t next_ticket;
+  int32_t* best_idx;     // device word receiving the argmax of best_action
   // pinned host scratch
   float* h_loss;
   int32_t* h_i32;

@@ -74,6 +74,7 @@ __device__ __forceinline__ int64_t plane_index(const PlaneDst& d, int net, int i
 
 struct TapsArgs {
   int n_units, imgs, nets_per_g, hpg, n_hg;
+  int unit0;  // first unit of this launch (best_action runs a single (net, image) unit of the training layout)
   // A image
   int a_rows_alloc, a_chunks, a_chunk_rows, a_halves, a_buf_rows;
   // M
@@ -175,7 +176,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       int xi = 0;
       for (int j = j0; j < j1; ++j) {
         if (j != j0 && j % p.tiles != 0) continue;
-        const int u = j / p.tiles, xb = xi & 1;
+        const int u = p.unit0 + j / p.tiles, xb = xi & 1;
         mbar_wait(&x_empty[xb], ((xi >> 1) & 1) ^ 1);
         tl_stamp(p.debug, 1000 + xi);
         const int gi = u / p.n_hg;  // (g, img) linear
@@ -198,7 +199,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       int ws = 0;
       uint32_t wphase = 0;
       for (int j = j0; j < j1; ++j) {
-        const int u = j / p.tiles;
+        const int u = p.unit0 + j / p.tiles;
         const int hg = u % p.n_hg, g = (u / p.n_hg) / p.imgs;
         const int net0 = g * p.nets_per_g + hg * p.hpg;
         const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
@@ -290,7 +291,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     pdl_wait();
     int ai = 0;
     for (int j = j0; j < j1; ++j, ++ai) {
-      const int u = j / p.tiles, tile = j - u * p.tiles;
+      const int tile = j % p.tiles, u = p.unit0 + j / p.tiles;
       const int hg = u % p.n_hg, gi = u / p.n_hg, g = gi / p.imgs, im = gi - g * p.imgs;
       const int net0 = g * p.nets_per_g + hg * p.hpg;
       const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
@@ -642,6 +643,7 @@ struct S2dArgs {
   float* o_reward;
   uint8_t* o_terminal;
   int u8, imgs, IH, IW, IC, s, ph, pw, BH, BW, P, C2;
+  int n_src;           // 2: state and next_state (learning step); 1: state only (best_action)
   int64_t img_rows;    // allocated rows per image
   bf16 *hi, *lo;       // [2][imgs][img_rows][C2]
 };
@@ -650,7 +652,7 @@ __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
   pdl_trigger();
   pdl_wait();
   const int run = a.s * a.IC;
-  const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
+  const int64_t total = (int64_t)a.n_src * a.imgs * a.BH * a.BW * a.s;
   const int64_t img_elems = (int64_t)a.IH * a.IW * a.IC;
   if (a.slots && blockIdx.x == 0 && (int)threadIdx.x < a.imgs) {
     const int64_t slot = a.slots[threadIdx.x];

@@ -27,6 +27,7 @@ constexpr int NB = 32;         // batch columns
 
 struct Args {
   int n_units, tiles, splits, kb_per_unit;  // unit = (net, tile, split); kb_per_unit K blocks each
+  int unit0;                                // first unit of this launch (best_action: the units of one net)
   int nets;
   int stages;
   // forward
@@ -98,7 +99,8 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
       int st = 0, ui = 0;
       uint32_t ph = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ui) {
-        const int sp = u % p.splits, nt = u / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
+        const int uu = u + p.unit0;
+        const int sp = uu % p.splits, nt = uu / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
         for (int kb = 0; kb < p.kb_per_unit; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
           tl_stamp(p.debug, 2000 + ui * 16 + kb);
@@ -164,7 +166,8 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
     pdl_wait();
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ai) {
       const int ab = ai & 1;
-      const int sp = u % p.splits, nt = u / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
+      const int uu = u + p.unit0;
+      const int sp = uu % p.splits, nt = uu / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
       mbar_wait(&acc_full[ab], (ai >> 1) & 1);
       tcgen05_after_sync();
       if (et == 0) tl_stamp(p.debug, 1200 + 2 * ai);

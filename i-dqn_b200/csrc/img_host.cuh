@@ -277,6 +277,7 @@ static int img_setup(idqn_handle* h) {
     a.imgs = B, a.IH = g.IH, a.IW = g.IW, a.IC = g.IC, a.s = g.s, a.ph = g.ph, a.pw = g.pw;
     a.BH = g.BH, a.BW = g.BW, a.P = g.P, a.C2 = g.C2, a.img_rows = g.XRa;
     a.hi = h->il[0].x2_hi, a.lo = h->il[0].x2_lo;
+    a.n_src = 2;
   }
   // ---- big Dense layer: weight-streaming kernels ----
   {
@@ -410,10 +411,12 @@ static cudaError_t img_set_smem(Kern kern, size_t bytes) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-static int img_launch_s2d(idqn_handle* h, int x_u8) {
+// single_state: only the first image of `state` (best_action); otherwise the whole batch of state and next_state
+static int img_launch_s2d(idqn_handle* h, int x_u8, bool single_state = false) {
   ImgHost* H = (ImgHost*)h->img_host;
   img::S2dArgs a = H->s2d;
   a.u8 = x_u8;
+  if (single_state) a.imgs = 1, a.n_src = 1;
   a.src[0] = h->s, a.src[1] = h->s2;  // the staging set of this step (idqn_submit_batch_host points it at its slot)
   a.slots = nullptr;
   if (h->rsrc_on) {  // idqn_learn_from_replay: frames read from the replay slots in place, scalars gathered here
@@ -422,7 +425,7 @@ static int img_launch_s2d(idqn_handle* h, int x_u8) {
     a.g_action = h->rsrc.action, a.g_reward = h->rsrc.reward, a.g_terminal = h->rsrc.terminal;
     a.o_action = h->action, a.o_reward = h->reward, a.o_terminal = h->terminal;
   }
-  const int64_t total = (int64_t)2 * a.imgs * a.BH * a.BW * a.s;
+  const int64_t total = (int64_t)a.n_src * a.imgs * a.BH * a.BW * a.s;
   // first kernel of the step: launched WITHOUT the programmatic attribute, so everything enqueued before the step (the
   // previous step's Adam kernels when the step is not graph-replayed) has completed before any kernel of this step --
   // several of which prefetch weight tiles ahead of their griddepcontrol.wait -- can start
@@ -431,9 +434,11 @@ static int img_launch_s2d(idqn_handle* h, int x_u8) {
   return IDQN_OK;
 }
 
-static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes) {
+// unit0 / n_units >= 0: run only that window of the layer's units (best_action: one (net, image) of the training layout)
+static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes, int unit0 = -1, int n_units = -1) {
   ImgHost* H = (ImgHost*)h->img_host;
   img::TapsArgs a = dgrad ? H->dg[li] : H->fwd[li];
+  if (unit0 >= 0) a.unit0 = unit0, a.n_units = n_units;
   a.debug = img_debug_on(dgrad ? "dgrad" : "fwd", li);
   const ImgLayerState& S = h->il[li];
   const img::TapsSmem L = img::taps_smem(a, a_planes);
@@ -477,9 +482,10 @@ static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
 
 // forward (dgrad == false) or data gradient of the big Dense layer; z_dst: dgrad planes go to the dyZ layout of the
 // preceding conv layer
-static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst) {
+static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst, int unit0 = -1, int n_units = -1) {
   ImgHost* H = (ImgHost*)h->img_host;
   dense::Args a = dgrad ? H->ddg : H->dfwd;
+  if (unit0 >= 0) a.unit0 = unit0, a.n_units = n_units;
   const int li = IDQN_IMG_LAYERS;
   a.debug = img_debug_on(dgrad ? "ddgrad" : "dfwd", li);
   if (dgrad && z_dst) {

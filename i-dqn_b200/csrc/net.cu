@@ -160,6 +160,7 @@ struct HeadArgs {
   int ptiles, psplits;
   int64_t pb_off;  // arena offset of that layer's bias
   int64_t hbias_off;  // >= 0: also write the bias gradient of the hidden layer (sum_b dhid) at this arena offset
+  int cta0;           // head_q: first (net, sample) pair of this launch (best_action runs a single one)
 };
 #define HEAD_MAXA 32
 
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(128) head_q_kernel(const HeadArgs a) {
   pdl_trigger();
   pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int net = blockIdx.x / a.B, b = blockIdx.x - net * a.B;
+  const int pair = blockIdx.x + a.cta0;
+  const int net = pair / a.B, b = pair - net * a.B;
   const int k = net < a.K ? net : net - a.K;
   const float* base = (net < a.K ? a.online : a.target) + (int64_t)k * a.stride;
   const float* W = base + a.w_off;
@@ -933,6 +935,7 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     a.loss = h->loss, a.loss_sum = h->loss_sum, a.count = h->count;
     a.q = h->q;
     a.part = nullptr, a.ptiles = a.psplits = 0, a.pb_off = 0;
+    a.cta0 = 0;
     if (use_dense && L - 2 == IDQN_IMG_LAYERS) {
       const dense::Args& df = ((ImgHost*)h->img_host)->dfwd;
       if (df.splits > 1) a.part = df.part, a.ptiles = df.tiles, a.psplits = df.splits, a.pb_off = h->layers[L - 2].b_off;
@@ -1222,6 +1225,7 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaMemsetAsync(h->tickets, 0, sizeof(int) * h->n_tickets, h->stream));
   CK(cudaMallocHost(&h->h_loss, sizeof(float) * std::max(K, B * h->A)));
   CK(cudaMallocHost(&h->h_i32, sizeof(int32_t) * std::max(K, 4)));
+  CK(cudaMalloc(&h->best_idx, sizeof(int32_t) * 4));
   CK(cudaStreamSynchronize(h->stream));
   *out = h;
   return IDQN_OK;
@@ -1245,6 +1249,7 @@ extern "C" int idqn_destroy(idqn_handle* h) {
     if (p) cudaFree(p);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->h_i32) cudaFreeHost(h->h_i32);
+  if (h->best_idx) cudaFree(h->best_idx);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int i = 0; i < 2; ++i)
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -1573,6 +1578,43 @@ static int enqueue_apply(idqn_handle* h, int which, int head, int u8, int n) {
   return IDQN_OK;
 }
 
+// best_action fast path (idqn.py:126-131 at Atari shapes): the single uint8 state runs through the SAME image-resident conv
+// kernels, weight-streaming Dense_0 kernel and head kernel as the learning step, as (online head, image 0) of the training
+// layout -- the step's activation buffers are scratch between steps.  q[(head * B + 0) * A ..] receives the Q-values.
+static bool apply_fast_ok(const idqn_handle* h, int which, int u8) {
+  if (!h->img_on || !h->img_host || which != IDQN_ONLINE || !u8 || h->n_layers != IDQN_IMG_LAYERS + 2) return false;
+  const ImgHost* H = (const ImgHost*)h->img_host;
+  return H->dense_on && H->dfwd.splits > 1 && !(h->cfg.flags & IDQN_F_SLOW_APPLY);
+}
+static int enqueue_apply_fast(idqn_handle* h, int head) {
+  ImgHost* H = (ImgHost*)h->img_host;
+  const int keep = h->n_launch, prof = h->prof_on;  // launch accounting / profiling belong to the learning step
+  h->prof_on = 0;
+  int rc = refresh_planes(h);
+  if (!rc) rc = img_launch_s2d(h, 1, true);
+  if (!rc) rc = img_launch_taps(h, 0, false, 1, 0, H->fwd[0].n_hg);  // every online head group of image 0
+  for (int li = 1; li < IDQN_IMG_LAYERS && !rc; ++li) rc = img_launch_taps(h, li, false, 2, head * h->B, 1);
+  if (!rc) rc = dense_launch(h, false, false, head * H->dfwd.tiles * H->dfwd.splits, H->dfwd.tiles * H->dfwd.splits);
+  if (!rc) {
+    const int L = h->n_layers;
+    const Layer& l = h->layers[L - 1];
+    HeadArgs a;
+    memset(&a, 0, sizeof(a));
+    const float* hid = h->act + h->layers[L - 2].act_off;
+    a.hid = NetPtr{hid, hid, h->act_stride, h->act_stride, 2 * h->K};
+    a.H = l.g.Kd, a.A = h->A, a.B = h->B, a.K = h->K;
+    a.online = h->online, a.target = h->target;
+    a.stride = h->stride, a.w_off = l.w_off, a.b_off = l.b_off;
+    a.q = h->q;
+    a.part = H->dfwd.part, a.ptiles = H->dfwd.tiles, a.psplits = H->dfwd.splits, a.pb_off = h->layers[L - 2].b_off;
+    a.hbias_off = -1;
+    a.cta0 = head * h->B;
+    CK(launch_pdl(h->pdl, head_q_kernel, dim3(1), dim3(128), 0, h->stream, a));
+  }
+  h->n_launch = keep, h->prof_on = prof;
+  return rc;
+}
+
 extern "C" int idqn_apply_host(idqn_handle* h, int which, int head, const void* x, int u8, int n, float* q) {
   REQUIRE(h && x && q && n >= 0, "bad argument");
   REQUIRE(which == IDQN_ONLINE || which == IDQN_TARGET, "apply needs the online or target arena");
@@ -1597,11 +1639,13 @@ extern "C" int idqn_best_action(idqn_handle* h, int which, int head, const void*
   REQUIRE(head >= 0 && head < h->K, "bad head");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(h->s, state, (size_t)h->in_elems * (u8 ? 1 : 4), cudaMemcpyHostToDevice, h->stream));
-  int rc = enqueue_apply(h, which, head, u8, 1);
+  const bool fast = apply_fast_ok(h, which, u8);
+  int rc = fast ? enqueue_apply_fast(h, head) : enqueue_apply(h, which, head, u8, 1);
   if (rc) return rc;
-  int32_t* d_out = (int32_t*)h->loss;  // scratch would alias the loss; use the tail of q instead
-  d_out = (int32_t*)(h->q + h->A);     // q[0..A) holds the values, the next word receives the index
-  argmax_kernel<<<1, 32, 0, h->stream>>>(h->q, h->A, d_out);
+  // Q-values: q[0..A) (generic path) or the (head, sample 0) row of the step's layout; the index goes to the pinned word
+  const float* qv = fast ? h->q + (int64_t)head * h->B * h->A : h->q;
+  int32_t* d_out = (int32_t*)h->best_idx;
+  argmax_kernel<<<1, 32, 0, h->stream>>>(qv, h->A, d_out);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(h->h_i32, d_out, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));

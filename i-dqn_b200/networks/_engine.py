@@ -293,6 +293,12 @@ class Engine:
     def best_action(self, which: int, head: int, state) -> int:
         x = np.asarray(state)
         u8 = x.dtype == np.uint8
+        if not u8 and self.architecture_type == "cnn":
+            # the Atari wrapper hands over float32 frames holding 0..255 (environments/atari.py:43-45): as uint8 they
+            # take the learning step's own kernels (exact: the network divides by 255 either way)
+            xu = x.astype(np.uint8)
+            if np.array_equal(xu, x):
+                x, u8 = xu, True
         x = np.ascontiguousarray(x, dtype=np.uint8 if u8 else np.float32)
         if x.size != self.in_elems:
             raise ValueError(f"state has {x.size} elements, expected {self.in_elems}")

@@ -66,6 +66,7 @@ typedef struct idqn_config {
 #define IDQN_F_NO_IMG 8     /* disable the image-resident TMA conv kernels (generic tcgen05 implicit GEMM instead) */
 #define IDQN_F_KEEP_GRADS 4 /* materialise every gradient in the IDQN_GRAD arena (disables fused wgrad+Adam) */
 #define IDQN_F_PARTITION 32 /* backward pass on two SM partitions (green contexts): conv chain | Dense_0 wgrad+Adam.  Measured slower than the single-stream order on B200 (both sides are per-SM latency bound): off by default */
+#define IDQN_F_SLOW_APPLY 512 /* best_action through the generic batch-1 kernels instead of the step's own kernels */
 #define IDQN_F_NO_DEFER 256 /* Dense_0 wgrad+Adam right after its data gradient instead of at the end of the backward pass */
 #define IDQN_F_NO_FORK 128  /* keep the conv weight-gradient kernels on the main stream (no second graph branch) */
 #define IDQN_F_OLD_WGRAD 64 /* Dense_0 wgrad+Adam on the generic tcgen05 kernel (Adam in its epilogue) instead of the TMA pipeline */

@@ -146,3 +146,24 @@ def test_engine_flag_constants_match_the_header():
     assert len(set(bits)) == len(bits) and all(b & (b - 1) == 0 for b in bits), "flags must be distinct single bits"
     for name, value in header.items():
         assert getattr(_lib, "F_" + name) == value, f"F_{name} != IDQN_F_{name}"
+
+
+def test_scalar_threefry_equals_the_pinned_array_version():
+    """The acting path draws its head with a Python-int threefry (27 us instead of 240 us per draw); it must agree bit
+    for bit with the array implementation that the Random123 vectors pin."""
+    from idqn_b200 import _prng
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        k = rng.integers(0, 2 ** 32, 2).astype(np.uint32)
+        c = rng.integers(0, 2 ** 32, 2).astype(np.uint32)
+        y0, y1 = _prng.threefry2x32(k, np.asarray([c[0]], np.uint32), np.asarray([c[1]], np.uint32))
+        assert _prng._threefry_scalar(int(k[0]), int(k[1]), int(c[0]), int(c[1])) == (int(y0[0]), int(y1[0]))
+        # randint through split() + the array block function == the scalar fast path
+        k1, k2 = _prng.split(k)
+        hi = int(_prng.threefry2x32(k1, np.zeros(1, np.uint32), np.zeros(1, np.uint32))[0][0])
+        lo = int(_prng.threefry2x32(k2, np.zeros(1, np.uint32), np.zeros(1, np.uint32))[0][0])
+        span = int(rng.integers(1, 19))
+        mult = (2 ** 16) % span
+        mult = (mult * mult) % span
+        off = ((((hi % span) * mult) & 0xFFFFFFFF) + (lo % span) & 0xFFFFFFFF) % span
+        assert _prng.randint(k, 0, span) == off

@@ -354,3 +354,33 @@ def test_freshly_constructed_agent_bootstraps_from_its_own_init():
         _, _, o_l = O.learn_on_batch(p0, t0, s_o, batch, "cnn", 0.99, 1, 3e-4, 1.5e-4, torch.float32)
         np.testing.assert_allclose(g_l, o_l, rtol=RTOL, err_msg=f"losses step {step}")
         agent.update_target_params(step)  # D-sync at step 2
+
+
+def test_best_action_fast_path_equals_generic_path():
+    """best_action on a uint8 (or integral float32) Atari state runs through the learning step's own kernels; the
+    generic batch-1 kernels (IDQN_F_SLOW_APPLY) and the oracle's argmax give the same action for every head, also
+    right after a learning step (the fast path shares the step's activation buffers)."""
+    from idqn_b200 import _lib
+    from idqn_b200.networks.idqn import iDQN
+    obs, feats, A, K, B = (84, 84, 4), [32, 64, 64, 512], 6, 5, 32
+    rng = np.random.default_rng(31)
+    params = O.init_params(rng, obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    agents = []
+    for flags in (0, _lib.F_SLOW_APPLY):
+        ag = iDQN(0, obs, A, K, feats, "cnn", 3e-4, 0.99, 1, 1, 8, 4, 1.5e-4, flags=flags)
+        ag.params, ag.target_params = params, params
+        agents.append(ag)
+    batch = make_batch(rng, B, obs, A, True)
+    for rnd in range(2):
+        for trial in range(6):
+            state = rng.integers(0, 256, obs).astype(np.uint8)
+            for head in range(K):
+                fast = agents[0].best_action(agents[0].params, state, idx_params=head)
+                slow = agents[1].best_action(agents[1].params, state, idx_params=head)
+                as_float = agents[0].best_action(agents[0].params, state.astype(np.float32), idx_params=head)
+                q = O.apply(O.tree_index(agents[0].params.to_host(), head), state[None], "cnn")
+                top2 = np.sort(np.asarray(q).ravel())[-2:]
+                if top2[1] - top2[0] > 1e-5 * max(1.0, abs(top2[1])):  # a clear maximum: all paths must agree
+                    assert fast == slow == as_float == int(np.argmax(q)), (rnd, trial, head, fast, slow, q)
+        for ag in agents:  # one learning step, then again: the step's buffers were reused in between
+            ag._engine.learn_host(batch, want_losses=False)
