@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, bench (ours + reference arm), ncu launch list, ncu --set full of one step.
+# One GPU-box pass: parity tests, smoke, bench, ncu launch list of an un-graphed bench run, ncu --set full of one step.
 # usage: tools/gpu_round.sh <tag>   (outputs under gpurun_out/<tag>_*)
 tag=${1:-run}
 mkdir -p gpurun_out
