@@ -254,6 +254,28 @@ def run_ours(args):
     ms_sync, _, _, nxt = timed(e2e_sync_step, e2e_steps, 3, nxt)
     e2e_sync_rate = e2e_steps / (ms_sync / 1e3)
 
+    # (2c) configs[4]: the same resident step fed by the prioritised sampler -- 1 M-leaf float64 SumTree on the device
+    # (inverse-CDF descent per sample), keys mapped to replay slots on the host
+    prio = None
+    if world == 1 and not args.no_prioritized:
+        from idqn_b200.sample_collection.samplers import PrioritizedSamplingDistribution
+        rb_p = ReplayBuffer(PrioritizedSamplingDistribution(seed=0, max_capacity=1 << 20, priority_exponent=1.0, device=local),
+                            batch_size=B, max_capacity=4096, stack_size=4, clipping=lambda r: np.clip(r, -1, 1), device=local)
+        rng_p = np.random.default_rng(1)
+        for t in range(4200):
+            rb_p.add(TransitionElement(frames[t], int(rng_p.integers(0, A)), float(rng_p.integers(-1, 2)),
+                                       bool(rng_p.random() < 0.01), False), priority=float(rng_p.random() + 0.1))
+
+        def prio_step(step):
+            agent.update_online_params(step, rb_p)
+            agent.update_target_params(step)
+
+        p_steps = max(args.steps // 2, 5)
+        ms_p, _, _, nxt = timed(prio_step, p_steps, 3, nxt)
+        prio = {"value": p_steps / (ms_p / 1e3), "unit": "steps/s", "sum_tree_capacity": 1 << 20,
+                "how": "resident step with PrioritizedSamplingDistribution: host PCG64 uniforms -> device SumTree descent "
+                       "(float64, depth 21) -> keys -> replay slots; one D2H of the 32 leaves per step"}
+
     # (3) live per-kernel timing (CUDA events after every launch, un-graphed) for the roofline of the top kernel
     names_buf = (np.zeros(64 * 32, np.uint8))
     ms_buf = np.zeros(64, np.float32)
@@ -314,6 +336,8 @@ def run_ours(args):
             "gpu_launches": kernels_per_step * args.steps,
             "roofline": rl, "kernel_ms": {k: round(v, 5) for k, v in acc.items()},
         }
+        if prio is not None:
+            out["prioritized_replay"] = prio
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out))
@@ -363,6 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prioritized", action="store_true", help="skip the prioritised-replay (configs[4]) leg")
     ap.add_argument("--flags", type=int, default=0, help="IDQN_F_* engine flags (A/B experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
