@@ -11,7 +11,9 @@ OK, EINVAL, ECUDA, ERANGE, EASSERT, ENOMEM = 0, -1, -2, -3, -4, -5
 ARCH_FC, ARCH_CNN = 0, 1
 ONLINE, TARGET, MU, NU, GRAD = 0, 1, 2, 3, 4
 F_NO_GRAPH, F_SIMT_ONLY, F_KEEP_GRADS, F_NO_IMG, F_NO_PDL, F_PARTITION, F_OLD_WGRAD, F_NO_FORK, F_NO_DEFER, F_SLOW_APPLY = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+F_TIMELINE = 1024
 MAX_FEATURES = 8
+MAX_ACTIONS = 32  # HEAD_MAXA of csrc/net.cu
 
 
 class LibraryError(RuntimeError):
@@ -50,13 +52,21 @@ SYMBOLS = {
     "idqn_learn_on_batch_dev": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
     "idqn_submit_batch_host": (_I, [_P, _P, _P, _I, _P, _P, _P, C.POINTER(_I64)]),
     "idqn_wait_losses": (_I, [_P, _I64, _P]),
+    "idqn_set_loss_accumulation": (_I, [_P, _I]),
     "idqn_read_cumulated_losses": (_I, [_P, _P, _I]),
     "idqn_kernels_per_step": (_I, [_P]),
     "idqn_profile_step": (_I, [_P, _I, _I, _P, _P, C.POINTER(_I)]),
     "idqn_debug_timeline": (_I, [_P, _I]),
+    "idqn_kernel_timeline": (_I, [_P, _P, _P, _I, C.POINTER(_I)]),
     "idqn_shift_params": (_I, [_P]),
     "idqn_sync_target": (_I, [_P]),
     "idqn_copy_online_to_target": (_I, [_P]),
+    "idqn_peer_export_size": (_I, []),
+    "idqn_peer_create": (_I, [_P, C.POINTER(_P), _P]),
+    "idqn_peer_connect": (_I, [_P, _P, _P]),
+    "idqn_peer_destroy": (_I, [_P]),
+    "idqn_peer_sync_target": (_I, [_P]),
+    "idqn_peer_shift_params": (_I, [_P]),
     "idqn_apply_host": (_I, [_P, _I, _I, _P, _I, _I, _P]),
     "idqn_best_action": (_I, [_P, _I, _I, _P, _I, C.POINTER(C.c_int32)]),
     "idqn_sumtree_create": (_I, [_I64, _I, C.POINTER(_P)]),

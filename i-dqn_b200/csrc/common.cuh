@@ -40,6 +40,29 @@ void idqn_set_error(const char* fmt, ...);
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---------------------------------------------------------------------------------------------
+// In-graph kernel timeline (IDQN_F_TIMELINE): every kernel of the step stamps the global timer when its first CTA
+// starts and when its last CTA ends, so the true schedule of the captured graph (branches, programmatic dependent
+// launch overlap, gaps between kernels) can be read back -- ncu serialises kernels and events cannot be recorded inside a
+// graph replay.  tl_id < 0: off (one predictable branch per CTA).
+#define IDQN_KTL_MAX 64
+static __device__ unsigned long long g_ktl[2 * IDQN_KTL_MAX];
+__device__ __forceinline__ unsigned long long ktl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void ktl_begin(int id) {
+  if (id >= 0 && threadIdx.x == 0) atomicMin(&g_ktl[2 * id], ktl_now());
+}
+// call where every thread of the CTA arrives (the timeline build syncs the CTA first)
+__device__ __forceinline__ void ktl_end(int id) {
+  if (id >= 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(&g_ktl[2 * id + 1], ktl_now());
+  }
+}
+
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args&&... args) {
@@ -135,6 +158,8 @@ struct idqn_handle {
   int32_t* count;       // [K]
   float* loss;          // [K] last step
   double* loss_sum;     // [K] cumulated (idqn.py:72)
+  int32_t* loss_acc_on; // device word: 1 = steps add their losses to loss_sum (update_online_params), 0 = they do not
+  int loss_acc_host;    // host mirror of that word
   // batch staging (device)
   void *s, *s2;         // [B][in_elems] u8 or f32 (allocated for f32)
   int32_t* action;
@@ -197,6 +222,7 @@ struct idqn_handle {
   int sm_count;
   // launch accounting / live per-kernel timing (idqn_profile_step)
   int n_launch;          // kernels enqueued by the last enqueue_learn_step
+  char tl_name[IDQN_KTL_MAX][32];  // IDQN_F_TIMELINE: kernel names by timeline id (= launch index inside the step)
   int prof_on, prof_n;
   cudaEvent_t prof_ev[IDQN_PROF_MAX + 1];
   char prof_name[IDQN_PROF_MAX][32];
@@ -211,8 +237,15 @@ struct idqn_replay {
   double* reward;
   uint8_t *terminal, *episode_end;
   cudaStream_t stream;
-  int64_t* d_slots;  // device copy of gather indices
+  int64_t* d_slots;  // device copy of the LEARNER's gather indices (read by the step graph on the learner's stream)
   int64_t cap_slots; // capacity of d_slots
+  int64_t* d_gslots; // index buffer of idqn_replay_gather_host (own buffer: the learner's graph may still read d_slots)
+  int64_t cap_gslots;
+  // the most recent learner step reads its sampled slots IN PLACE, asynchronously, on the learner's stream: a put into
+  // one of those slots first waits for that step's event (every other slot is written without waiting)
+  cudaEvent_t ev_learner;
+  int learner_pending;
+  std::vector<int64_t>* learner_slots;
   // pinned staging for gather_host
   void* h_stage;
   size_t h_stage_bytes;

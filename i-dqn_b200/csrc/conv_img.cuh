@@ -98,6 +98,7 @@ struct TapsArgs {
   int64_t out_net_stride;
   PlaneDst dst;
   int debug;
+  int tl_id;  // kernel timeline slot (IDQN_F_TIMELINE) or -1
 };
 
 __host__ __device__ inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
@@ -168,6 +169,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   tcgen05_after_sync();
   const uint32_t tmem = tmem_base_s;
   if (tid == 0) tl_stamp(p.debug, 1);
+  ktl_begin(p.tl_id);
 
   if (warp == 0) {
     // ===== image producer: one load per unit this CTA touches =====
@@ -419,6 +421,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   }
   tcgen05_before_sync();
   __syncthreads();
+  ktl_end(p.tl_id);
   if (warp == 2) tmem_dealloc(tmem, tmem_cols);
 }
 
@@ -446,6 +449,7 @@ struct WgradArgs {
   float* part;                      // [heads][groups][span] partial gradients in arena coordinates
   int64_t span, w_off, b_off;       // floats per partial; arena offsets of this layer's kernel / bias
   int debug;
+  int tl_id;
 };
 struct WgradSmem {
   uint32_t x_plane_bytes, x_bytes, z_plane_bytes, z_bytes, ones_off, bar_off, total;
@@ -481,6 +485,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
   __shared__ uint32_t tmem_base_s;
 
   pdl_trigger();
+  ktl_begin(p.tl_id);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ts = blockIdx.x % p.tsplit, zg = blockIdx.x / p.tsplit;
   const int z = zg / p.groups, gidx = zg - z * p.groups;
@@ -625,6 +630,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
   if (warp == 2 && lane == 0) tl_stamp(p.debug, 1201);
   tcgen05_before_sync();
   __syncthreads();
+  ktl_end(p.tl_id);
   if (warp == 1) tmem_dealloc(tmem, tmem_cols);
 }
 
@@ -646,11 +652,13 @@ struct S2dArgs {
   int n_src;           // 2: state and next_state (learning step); 1: state only (best_action)
   int64_t img_rows;    // allocated rows per image
   bf16 *hi, *lo;       // [2][imgs][img_rows][C2]
+  int tl_id;
 };
 __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
   // one thread per (g, img, by, bx, ry): s*IC contiguous output channels = s input pixels of one input row
   pdl_trigger();
   pdl_wait();
+  ktl_begin(a.tl_id);
   const int run = a.s * a.IC;
   const int64_t total = (int64_t)a.n_src * a.imgs * a.BH * a.BW * a.s;
   const int64_t img_elems = (int64_t)a.IH * a.IW * a.IC;
@@ -713,6 +721,7 @@ __global__ void __launch_bounds__(256) s2d_input_kernel(const S2dArgs a) {
       if (!a.u8) *reinterpret_cast<uint4*>(a.lo + o + e) = l;
     }
   }
+  ktl_end(a.tl_id);
 }
 
 // fp32 NHWC activation from the planes of its consumer layout (debug / parity: idqn_download_activation)

@@ -48,6 +48,7 @@ struct Args {
   int zP, zW, zC, zOff;
   int64_t zRows, zstride;
   int debug;
+  int tl_id;
 };
 
 struct Smem {
@@ -80,6 +81,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
   __shared__ uint32_t tmem_base_s;
 
   pdl_trigger();
+  ktl_begin(p.tl_id);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < p.stages; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
@@ -243,6 +245,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
   }
   tcgen05_before_sync();
   __syncthreads();
+  ktl_end(p.tl_id);
   if (warp == 1) tmem_dealloc(tmem, 128);
 }
 

@@ -53,6 +53,7 @@ struct Args {
   int keep_heads;             // planes of heads < keep_heads are written L2 evict_last: the next step's Dense_0 forward
                               // and data gradient find them in L2; the other planes are evict_first
   int64_t stride, w_off;
+  int tl_id;
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
@@ -86,6 +87,7 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  ktl_begin(p.tl_id);
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 16);
@@ -239,6 +241,7 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
   }
   tcgen05_before_sync();
   __syncthreads();
+  ktl_end(p.tl_id);
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 

@@ -52,6 +52,8 @@ static bool img_geom(const Layer& l, int layer_index, img::Geom& g) {
 }
 
 static const size_t IMG_SMEM_MAX = 227 * 1024;
+static const size_t IMG_SMEM_OPTIN = 226 * 1024;  // dynamic limit requested per kernel: the device maximum minus room for the kernels' few static __shared__ words
+static const int IMG_WGRAD_IPG = 2;  // images per partial-sum group of the conv weight gradients
 
 // decide whether the handle can run the image path and build everything it needs
 static int img_setup(idqn_handle* h) {
@@ -121,10 +123,12 @@ static int img_setup(idqn_handle* h) {
   // ---- partial weight gradients ----
   h->wspan = dense.w_off;  // the conv layers occupy the arena range [0, Dense_0.w_off)
   {
-    // x 2 tile splits per (head, image range); the conv backward chain owns one SM partition when there is one
-    const int conv_sms = h->partition ? ((smpart::Partition*)h->partition)->sms[0] : h->sm_count;
-    const int want = std::max(1, conv_sms / (2 * K));
-    const int ipg = (B + want - 1) / std::min(want, B);
+    // Partial sums over FIXED groups of IMG_WGRAD_IPG consecutive images (fp32 accumulation in TMEM inside a group,
+    // groups summed in index order by adam_kernel): the grouping -- hence every rounding of the conv weight gradients --
+    // depends on the batch size only, not on how many heads this handle owns, so a head computes bit-identical
+    // gradients whether it lives in a K-head handle or alone on its own GPU (parallel.py).  What adapts to K is the
+    // split of a layer's M tiles over CTAs (tsplit), which does not touch the summation order.
+    const int ipg = std::min(IMG_WGRAD_IPG, B);
     h->wgroups = (B + ipg - 1) / ipg;
     const size_t pb = sizeof(float) * h->wspan * h->wgroups * K;
     CK(cudaMalloc(&h->wpart, pb));
@@ -253,11 +257,20 @@ static int img_setup(idqn_handle* h) {
             ++ng;
           }
       a.n_tiles = (ng + 1) / 2;
-      a.tsplit = 2, a.tps = (a.n_tiles + 1) / 2;
-      if (a.n_tiles > img::MAX_TAPS || (a.tps + 1) * 2 * g.OC > 512) {
+      // tile split: the smallest one whose accumulators (+ the bias tile) fit the 512 TMEM columns, raised while the
+      // grid still fits the machine in one wave
+      const int conv_sms = h->partition ? ((smpart::Partition*)h->partition)->sms[0] : h->sm_count;
+      a.tsplit = 0;
+      for (int ts = 1; ts <= a.n_tiles; ++ts) {
+        const int tps = (a.n_tiles + ts - 1) / ts;
+        if ((ts - 1) * tps >= a.n_tiles || (tps + 1) * 2 * g.OC > 512) continue;  // empty last split / TMEM
+        if (!a.tsplit || K * h->wgroups * ts <= conv_sms) a.tsplit = ts;
+      }
+      if (a.n_tiles > img::MAX_TAPS || !a.tsplit) {
         idqn_set_error("internal: wgrad L%d needs too many accumulator tiles", li);
         return IDQN_EINVAL;
       }
+      a.tps = (a.n_tiles + a.tsplit - 1) / a.tsplit;
       for (int t = 0; t < a.n_tiles; ++t) {
         const int g0 = 2 * t, g1 = 2 * t + 1 < ng ? 2 * t + 1 : -1;
         a.sh0[t] = gsh[g0], a.hf0[t] = ghf[g0], a.row0[t] = grow[g0];
@@ -326,14 +339,12 @@ static int img_setup(idqn_handle* h) {
       {
         dense::Args& a = H->dfwd;
         a.nets = 2 * K, a.tiles = O / 128;
-        // split K so that the units fill the machine in whole rounds
+        // split K: the largest divisor of the K-block count (<= 16 splits, >= 4 blocks each; 7744 / 64 = 121 -> 11 x 11).
+        // A function of the layer shape only -- not of the number of nets -- so that the summation grouping of the
+        // forward pass, like every other reduction of the step, does not depend on how many heads the handle owns.
         int best = 1;
-        double best_eff = 0;
-        for (int sp = 1; sp <= 16; ++sp) {
-          const int units = a.nets * a.tiles * sp, rounds = (units + h->sm_count - 1) / h->sm_count;
-          const double eff = (double)units / ((double)rounds * h->sm_count);
-          if (eff > best_eff + 0.02 && (kblocks + sp - 1) / sp >= 4) best_eff = eff, best = sp;
-        }
+        for (int sp = 1; sp <= 16; ++sp)
+          if (kblocks % sp == 0 && kblocks / sp >= 4) best = sp;
         a.splits = best, a.kb_per_unit = (kblocks + best - 1) / best;
         a.n_units = a.nets * a.tiles * a.splits;
         a.stages = 5;
@@ -406,9 +417,14 @@ static int l2_keep_heads(const idqn_handle* h) {
   return std::min(env, h->K);
 }
 
+// The dynamic shared-memory limit of a kernel is raised ONCE to the device maximum and never lowered: the same
+// instantiation is launched with different sizes (conv layers 1 and 2), and a profiler that re-launches the kernel nodes
+// of the captured graph one by one (ncu) launches them under the function's CURRENT attribute -- lowering it for the
+// second layer made the first layer's node fail with LaunchFailed under ncu (round-1 GPUTEST: ncu_rc=9).
 template <class Kern>
 static cudaError_t img_set_smem(Kern kern, size_t bytes) {
-  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (bytes > IMG_SMEM_OPTIN) return cudaErrorInvalidValue;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IMG_SMEM_OPTIN);
 }
 
 // single_state: only the first image of `state` (best_action); otherwise the whole batch of state and next_state
@@ -416,6 +432,7 @@ static int img_launch_s2d(idqn_handle* h, int x_u8, bool single_state = false) {
   ImgHost* H = (ImgHost*)h->img_host;
   img::S2dArgs a = H->s2d;
   a.u8 = x_u8;
+  a.tl_id = single_state ? -1 : tl_next(h);
   if (single_state) a.imgs = 1, a.n_src = 1;
   a.src[0] = h->s, a.src[1] = h->s2;  // the staging set of this step (idqn_submit_batch_host points it at its slot)
   a.slots = nullptr;
@@ -439,6 +456,7 @@ static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes, int
   ImgHost* H = (ImgHost*)h->img_host;
   img::TapsArgs a = dgrad ? H->dg[li] : H->fwd[li];
   if (unit0 >= 0) a.unit0 = unit0, a.n_units = n_units;
+  a.tl_id = unit0 >= 0 ? -1 : tl_next(h);
   a.debug = img_debug_on(dgrad ? "dgrad" : "fwd", li);
   const ImgLayerState& S = h->il[li];
   const img::TapsSmem L = img::taps_smem(a, a_planes);
@@ -463,6 +481,7 @@ static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
   ImgHost* H = (ImgHost*)h->img_host;
   img::WgradArgs a = H->wg[li];
   a.debug = img_debug_on("wgrad", li);
+  a.tl_id = tl_next(h);
   const ImgLayerState& S = h->il[li];
   const img::WgradSmem L = img::wgrad_smem(a, a_planes);
   const int grid = a.heads * a.groups * a.tsplit;
@@ -486,6 +505,7 @@ static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst, int unit0 = -1, 
   ImgHost* H = (ImgHost*)h->img_host;
   dense::Args a = dgrad ? H->ddg : H->dfwd;
   if (unit0 >= 0) a.unit0 = unit0, a.n_units = n_units;
+  a.tl_id = unit0 >= 0 ? -1 : tl_next(h);
   const int li = IDQN_IMG_LAYERS;
   a.debug = img_debug_on(dgrad ? "ddgrad" : "dfwd", li);
   if (dgrad && z_dst) {
@@ -526,6 +546,7 @@ static int dense_wgrad_launch(idqn_handle* h, int tile0, int ntiles, bool keep_g
   static const int sp = getenv("IDQN_L2_STREAM") ? atoi(getenv("IDQN_L2_STREAM")) : 0;
   a.stream_policy = sp == 0 ? tma::L2_EVICT_NORMAL : (sp == 2 ? tma::L2_EVICT_LAST : tma::L2_EVICT_FIRST);
   a.stride = h->stride, a.w_off = l.w_off;
+  a.tl_id = tl_next(h);
   const int grid = std::min(a.heads * a.ntiles, h->sm_avail);
   CK(img_set_smem(dwt::dense_wgrad_adam_kernel, dwt::SMEM_TOTAL));
   CK(launch_pdl(0, dwt::dense_wgrad_adam_kernel, dim3(grid), dim3(dwt::NTHREADS), dwt::SMEM_TOTAL, h->stream, H->wmapX[0],

@@ -153,6 +153,7 @@ struct HeadArgs {
   int relu_mask;
   float* loss;
   double* loss_sum;
+  const int32_t* loss_acc_on;  // device flag: 0 = this step's losses are NOT added to loss_sum (direct learn_on_batch calls)
   int32_t* count;
   float* q;      // [2K][B][A]
   // deferred split-K reduce of the preceding Dense layer (dense_stream.cuh): partial tiles [net*ptiles + tile][split][32][128]
@@ -161,6 +162,7 @@ struct HeadArgs {
   int64_t pb_off;  // arena offset of that layer's bias
   int64_t hbias_off;  // >= 0: also write the bias gradient of the hidden layer (sum_b dhid) at this arena offset
   int cta0;           // head_q: first (net, sample) pair of this launch (best_action runs a single one)
+  int tl_id;          // kernel timeline slot (IDQN_F_TIMELINE) or -1
 };
 #define HEAD_MAXA 32
 
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(128) head_q_kernel(const HeadArgs a) {
   __shared__ float red[4][HEAD_MAXA];
   pdl_trigger();
   pdl_wait();
+  ktl_begin(a.tl_id);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = blockIdx.x + a.cta0;
   const int net = pair / a.B, b = pair - net * a.B;
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(128) head_q_kernel(const HeadArgs a) {
   }
   __syncthreads();
   if (tid < a.A) a.q[((int64_t)net * a.B + b) * a.A + tid] = ((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid])) + __ldg(base + a.b_off + tid);
+  ktl_end(a.tl_id);
 }
 
 // y = r + (1-done) gamma^n max_a' Q_target; delta = Q(s,a) - y; loss_k = mean delta^2 and the backward of the
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
   extern __shared__ float sm[];
   pdl_trigger();
   pdl_wait();
+  ktl_begin(a.tl_id);
   const int k = blockIdx.y, B = a.B, A = a.A, H = a.H, tid = threadIdx.x;
   float* coef = sm;        // [B]
   float* lterm = sm + B;   // [B]
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
       for (int b = 0; b < B; ++b) s += lterm[b];
       s /= (float)B;
       a.loss[k] = s;
-      a.loss_sum[k] += (double)s;
+      if (*a.loss_acc_on) a.loss_sum[k] += (double)s;  // idqn.py:72 accumulates inside update_online_params only
       a.count[k] += 1;  // ScaleByAdamState.count, read by the Adam kernels that follow
     }
     float* gb = a.grad + (int64_t)k * a.stride + a.b_off;
@@ -351,6 +356,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
       }
     }
   }
+  ktl_end(a.tl_id);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -365,9 +371,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
                                                    const int32_t* __restrict__ count, int64_t stride4, int64_t off4_a,
                                                    int64_t n4_a, int nblk_a, int64_t off4_b, int64_t n4_b, float lr,
                                                    float b1, float b2, float eps, const float4* __restrict__ part_a,
-                                                   int groups, int64_t span4, float4* __restrict__ gout) {
+                                                   int groups, int64_t span4, float4* __restrict__ gout, int tl_id) {
   pdl_trigger();
   pdl_wait();
+  ktl_begin(tl_id);
   const int k = blockIdx.y;
   const tc::AdamCoef ac = tc::adam_coef(b1, b2, lr, eps, count[k]);  // count already incremented for this step
   const bool in_a = (int)blockIdx.x < nblk_a;
@@ -413,6 +420,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
     ph[base + i] = h2;
     pl[base + i] = l2;
   }
+  ktl_end(tl_id);
 }
 
 __global__ void argmax_kernel(const float* __restrict__ q, int A, int32_t* out) {
@@ -427,7 +435,12 @@ __global__ void argmax_kernel(const float* __restrict__ q, int A, int32_t* out) 
 
 // ------------------------------------------------------------------------------------------
 // every kernel launch of the step goes through mark(): counts launches and, when profiling, drops an event
+// timeline slot of the launch about to be enqueued (its index inside the step), -1 when the timeline is off
+static int tl_next(const idqn_handle* h) {
+  return ((h->cfg.flags & IDQN_F_TIMELINE) && h->n_launch < IDQN_KTL_MAX) ? h->n_launch : -1;
+}
 static void mark(idqn_handle* h, const char* fmt, int li) {
+  if ((h->cfg.flags & IDQN_F_TIMELINE) && h->n_launch < IDQN_KTL_MAX) snprintf(h->tl_name[h->n_launch], 32, fmt, li);
   h->n_launch++;
   if (h->prof_on && h->prof_n < IDQN_PROF_MAX) {
     snprintf(h->prof_name[h->prof_n], 32, fmt, li);
@@ -850,7 +863,7 @@ static int launch_adam_ranges(idqn_handle* h, int64_t off_a, int64_t len_a, bool
                                            (uint2*)h->won_hi, (uint2*)h->won_lo, h->count, h->stride / 4, off_a / 4, n4a, ba,
                                            off_b / 4, n4b, h->cfg.learning_rate, 0.9f, 0.999f, h->cfg.adam_eps,
                                            a_from_partials ? (const float4*)h->wpart : nullptr, h->wgroups, h->wspan / 4,
-                                           (a_from_partials && keep) ? (float4*)h->grad : nullptr));
+                                           (a_from_partials && keep) ? (float4*)h->grad : nullptr, tl_next(h)));
   mark(h, "adam_%d", 0);
   return IDQN_OK;
 }
@@ -933,9 +946,11 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     a.grad = h->grad;
     a.dstride = h->act_stride;
     a.loss = h->loss, a.loss_sum = h->loss_sum, a.count = h->count;
+    a.loss_acc_on = h->loss_acc_on;
     a.q = h->q;
     a.part = nullptr, a.ptiles = a.psplits = 0, a.pb_off = 0;
     a.cta0 = 0;
+    a.tl_id = tl_next(h);
     if (use_dense && L - 2 == IDQN_IMG_LAYERS) {
       const dense::Args& df = ((ImgHost*)h->img_host)->dfwd;
       if (df.splits > 1) a.part = df.part, a.ptiles = df.tiles, a.psplits = df.splits, a.pb_off = h->layers[L - 2].b_off;
@@ -943,9 +958,11 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     CK(launch_pdl(h->pdl, head_q_kernel, dim3(2 * K * B), dim3(128), 0, h->stream, a));
     mark(h, "head_q_L%d", L - 1);
     a.hbias_off = -1;
+    a.tl_id = tl_next(h);
     if (L >= 2 && dense_wgrad_tma_ok(h, L - 2)) a.hbias_off = h->layers[L - 2].b_off;
     const size_t smem = (size_t)(3 * B + 32 * B + 32 * a.A + 32 * B) * sizeof(float);
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    REQUIRE(smem <= IMG_SMEM_OPTIN, "head_bwd_kernel needs %zu bytes of shared memory (batch %d, %d actions)", smem, B, a.A);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IMG_SMEM_OPTIN));
     CK(launch_pdl(h->pdl, head_bwd_kernel, dim3((a.H + 31) / 32, K), dim3(256), smem, h->stream, a));
     mark(h, "head_bwd_L%d", L - 1);
   }
@@ -1067,7 +1084,10 @@ int idqn_learn_step_resident(idqn_handle* h, int x_u8, float* losses_host) {
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       int rc = enqueue_learn_step(h, x_u8);
       cudaError_t e = cudaStreamEndCapture(h->stream, &g);
-      if (rc) return rc;
+      if (rc) {
+        if (e == cudaSuccess && g) cudaGraphDestroy(g);  // a failed enqueue must not leak the partial capture
+        return rc;
+      }
       CK(e);
       CK(cudaGraphInstantiate(&gexec, g, 0));
       CK(cudaGraphDestroy(g));
@@ -1116,6 +1136,7 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   REQUIRE(cfg && out, "null argument");
   REQUIRE(cfg->n_heads >= 1 && cfg->batch_size >= 1 && cfg->n_actions >= 1, "bad sizes");
   REQUIRE(cfg->n_features >= 0 && cfg->n_features <= IDQN_MAX_FEATURES, "bad n_features");
+  REQUIRE(cfg->n_actions <= HEAD_MAXA, "n_actions = %d: the fused final-layer kernels hold at most %d actions", cfg->n_actions, HEAD_MAXA);
   idqn_handle* h = new idqn_handle();
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
@@ -1164,6 +1185,10 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaMemsetAsync(h->loss, 0, sizeof(float) * K, h->stream));
   CK(cudaMalloc(&h->loss_sum, sizeof(double) * K));
   CK(cudaMemsetAsync(h->loss_sum, 0, sizeof(double) * K, h->stream));
+  CK(cudaMalloc(&h->loss_acc_on, sizeof(int32_t)));
+  CK(cudaMemsetAsync(h->loss_acc_on, 0, sizeof(int32_t), h->stream));
+  CK(cudaMemsetAsync(h->loss_acc_on, 1, 1, h->stream));  // little-endian int32 1
+  h->loss_acc_host = 1;
   CK(cudaMalloc(&h->s, sizeof(float) * h->in_elems * B));
   CK(cudaMalloc(&h->s2, sizeof(float) * h->in_elems * B));
   CK(cudaMalloc(&h->action, sizeof(int32_t) * B));
@@ -1226,6 +1251,11 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaMallocHost(&h->h_loss, sizeof(float) * std::max(K, B * h->A)));
   CK(cudaMallocHost(&h->h_i32, sizeof(int32_t) * std::max(K, 4)));
   CK(cudaMalloc(&h->best_idx, sizeof(int32_t) * 4));
+  if (cfg->flags & IDQN_F_TIMELINE) {
+    unsigned long long buf[2 * IDQN_KTL_MAX];
+    for (int i = 0; i < IDQN_KTL_MAX; ++i) buf[2 * i] = ~0ull, buf[2 * i + 1] = 0;
+    CK(cudaMemcpyToSymbol(g_ktl, buf, sizeof(buf)));
+  }
   CK(cudaStreamSynchronize(h->stream));
   *out = h;
   return IDQN_OK;
@@ -1239,6 +1269,7 @@ extern "C" int idqn_destroy(idqn_handle* h) {
     if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
   for (int i = 0; i <= IDQN_PROF_MAX; ++i)
     if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
+  if (h->loss_acc_on) cudaFree(h->loss_acc_on);
   void* ptrs[] = {h->online, h->target, h->mu,     h->nu,  h->grad, h->count, h->loss, h->loss_sum, h->s,
                   h->s2,     h->action, h->reward, h->terminal, h->act,  h->dact,  h->q,    h->part,     h->tickets};
   for (void* p : ptrs)
@@ -1468,6 +1499,20 @@ extern "C" int idqn_wait_losses(idqn_handle* h, int64_t ticket, float* losses) {
   return IDQN_OK;
 }
 
+// idqn.py:72: `self.cumulated_losses += losses` lives in update_online_params; a direct learn_on_batch call
+// (idqn.py:96-109) leaves the running sums alone.  The switch is a device word the loss kernel reads, so the captured
+// graph serves both callers.
+extern "C" int idqn_set_loss_accumulation(idqn_handle* h, int on) {
+  REQUIRE(h, "null handle");
+  on = on ? 1 : 0;
+  if (on == h->loss_acc_host) return IDQN_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  // stream-ordered fill: steps already enqueued keep the value they were enqueued under
+  CK(cudaMemsetAsync(h->loss_acc_on, on ? 1 : 0, 1, h->stream));
+  h->loss_acc_host = on;
+  return IDQN_OK;
+}
+
 extern "C" int idqn_read_cumulated_losses(idqn_handle* h, double* sums, int reset) {
   REQUIRE(h && sums, "null argument");
   CK(cudaSetDevice(h->cfg.device));
@@ -1608,6 +1653,7 @@ static int enqueue_apply_fast(idqn_handle* h, int head) {
     a.q = h->q;
     a.part = H->dfwd.part, a.ptiles = H->dfwd.tiles, a.psplits = H->dfwd.splits, a.pb_off = h->layers[L - 2].b_off;
     a.hbias_off = -1;
+    a.tl_id = -1;
     a.cta0 = head * h->B;
     CK(launch_pdl(h->pdl, head_q_kernel, dim3(1), dim3(128), 0, h->stream, a));
   }
@@ -1650,5 +1696,23 @@ extern "C" int idqn_best_action(idqn_handle* h, int which, int head, const void*
   CK(cudaMemcpyAsync(h->h_i32, d_out, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   *action = h->h_i32[0];
+  return IDQN_OK;
+}
+
+// IDQN_F_TIMELINE: first-CTA-start / last-CTA-end global-timer stamps (ns) of every kernel of the most recent step,
+// in launch order; resets the slots.  out: [2 * n] begin/end pairs, names: [32 * n]
+extern "C" int idqn_kernel_timeline(idqn_handle* h, unsigned long long* out, char* names, int max_entries, int* n_out) {
+  REQUIRE(h && out && names && n_out, "null argument");
+  REQUIRE(h->cfg.flags & IDQN_F_TIMELINE, "the handle was created without IDQN_F_TIMELINE");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  const int n = std::min(std::min(h->n_launch, IDQN_KTL_MAX), max_entries);
+  unsigned long long buf[2 * IDQN_KTL_MAX];
+  CK(cudaMemcpyFromSymbol(buf, g_ktl, sizeof(buf)));
+  memcpy(out, buf, sizeof(unsigned long long) * 2 * n);
+  for (int i = 0; i < n; ++i) memcpy(names + 32 * i, h->tl_name[i], 32);
+  for (int i = 0; i < IDQN_KTL_MAX; ++i) buf[2 * i] = ~0ull, buf[2 * i + 1] = 0;
+  CK(cudaMemcpyToSymbol(g_ktl, buf, sizeof(buf)));
+  *n_out = n;
   return IDQN_OK;
 }

@@ -62,9 +62,9 @@ static int ensure_slots(idqn_replay* r, int n) {
   return IDQN_OK;
 }
 
-static int launch_gather(idqn_replay* r, GatherArgs& a, cudaStream_t st) {
+static int launch_gather(idqn_replay* r, GatherArgs& a, cudaStream_t st, const int64_t* d_slots) {
   a.state = r->state, a.next_state = r->next_state, a.action = r->action, a.reward = r->reward;
-  a.terminal = r->terminal, a.episode_end = r->episode_end, a.slots = r->d_slots, a.state_bytes = r->state_bytes;
+  a.terminal = r->terminal, a.episode_end = r->episode_end, a.slots = d_slots, a.state_bytes = r->state_bytes;
   int64_t per = (r->state_bytes & 15) == 0 ? r->state_bytes / 16 : r->state_bytes;
   int chunks = (int)std::min<int64_t>(std::max<int64_t>((per + 255) / 256, 1), 64);
   replay_gather_kernel<<<dim3(chunks, 2 * a.n), 256, 0, st>>>(a);
@@ -95,6 +95,8 @@ extern "C" int idqn_replay_create(int64_t n_slots, int64_t state_bytes, int devi
   CK(cudaMalloc(&r->episode_end, n_slots));
   int rc = ensure_slots(r, 256);
   if (rc) return rc;
+  CK(cudaEventCreateWithFlags(&r->ev_learner, cudaEventDisableTiming));
+  r->learner_slots = new std::vector<int64_t>();
   *out = r;
   return IDQN_OK;
 }
@@ -103,7 +105,12 @@ extern "C" int idqn_replay_destroy(idqn_replay* r) {
   if (!r) return IDQN_OK;
   cudaSetDevice(r->device);
   cudaStreamSynchronize(r->stream);
-  void* ptrs[] = {r->state, r->next_state, r->action, r->reward, r->terminal, r->episode_end, r->d_slots};
+  if (r->ev_learner) {
+    cudaEventSynchronize(r->ev_learner);
+    cudaEventDestroy(r->ev_learner);
+  }
+  delete r->learner_slots;
+  void* ptrs[] = {r->state, r->next_state, r->action, r->reward, r->terminal, r->episode_end, r->d_slots, r->d_gslots};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (r->h_stage) cudaFreeHost(r->h_stage);
@@ -116,6 +123,12 @@ extern "C" int idqn_replay_put(idqn_replay* r, int64_t slot, const void* state, 
                                double reward, uint8_t is_terminal, uint8_t episode_end) {
   REQUIRE(r && state && next_state && slot >= 0 && slot < r->n_slots, "bad argument");
   CK(cudaSetDevice(r->device));
+  if (r->learner_pending) {
+    // a learner step enqueued by idqn_learn_from_replay may still be reading its sampled slots in place
+    if (cudaEventQuery(r->ev_learner) == cudaSuccess) r->learner_pending = 0;
+    else if (std::find(r->learner_slots->begin(), r->learner_slots->end(), slot) != r->learner_slots->end())
+      CK(cudaStreamWaitEvent(r->stream, r->ev_learner, 0));
+  }
   CK(cudaMemcpyAsync(r->state + slot * r->state_bytes, state, r->state_bytes, cudaMemcpyHostToDevice, r->stream));
   CK(cudaMemcpyAsync(r->next_state + slot * r->state_bytes, next_state, r->state_bytes, cudaMemcpyHostToDevice,
                      r->stream));
@@ -132,8 +145,12 @@ extern "C" int idqn_replay_gather_host(idqn_replay* r, const int64_t* slots, int
   REQUIRE(r && slots && n > 0 && state && next_state && action && reward && terminal && episode_end, "bad argument");
   for (int i = 0; i < n; ++i) REQUIRE(slots[i] >= 0 && slots[i] < r->n_slots, "slot %lld out of range", (long long)slots[i]);
   CK(cudaSetDevice(r->device));
-  int rc = ensure_slots(r, n);
-  if (rc) return rc;
+  if (n > r->cap_gslots) {
+    if (r->d_gslots) CK(cudaFree(r->d_gslots));
+    r->cap_gslots = std::max(n, 256);
+    CK(cudaMalloc(&r->d_gslots, sizeof(int64_t) * r->cap_gslots));
+  }
+  int rc = IDQN_OK;
   // device-side staging for the packed batch
   const size_t sb = (size_t)n * r->state_bytes;
   const size_t off_next = (sb + 255) / 256 * 256;
@@ -144,13 +161,13 @@ extern "C" int idqn_replay_gather_host(idqn_replay* r, const int64_t* slots, int
   const size_t total = off_end + ((size_t)n + 255) / 256 * 256;
   uint8_t* d_stage = nullptr;
   CK(cudaMallocAsync((void**)&d_stage, total, r->stream));
-  CK(cudaMemcpyAsync(r->d_slots, slots, sizeof(int64_t) * n, cudaMemcpyHostToDevice, r->stream));
+  CK(cudaMemcpyAsync(r->d_gslots, slots, sizeof(int64_t) * n, cudaMemcpyHostToDevice, r->stream));
   GatherArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n;
   a.o_state = d_stage, a.o_next = d_stage + off_next, a.o_action = (int32_t*)(d_stage + off_act);
   a.o_reward_f64 = (double*)(d_stage + off_rew), a.o_terminal = d_stage + off_term, a.o_episode_end = d_stage + off_end;
-  rc = launch_gather(r, a, r->stream);
+  rc = launch_gather(r, a, r->stream, r->d_gslots);
   if (rc) return rc;
   CK(cudaMemcpyAsync(state, a.o_state, sb, cudaMemcpyDeviceToHost, r->stream));
   CK(cudaMemcpyAsync(next_state, a.o_next, sb, cudaMemcpyDeviceToHost, r->stream));
@@ -160,6 +177,15 @@ extern "C" int idqn_replay_gather_host(idqn_replay* r, const int64_t* slots, int
   CK(cudaMemcpyAsync(episode_end, a.o_episode_end, n, cudaMemcpyDeviceToHost, r->stream));
   CK(cudaFreeAsync(d_stage, r->stream));
   CK(cudaStreamSynchronize(r->stream));
+  return IDQN_OK;
+}
+
+// the step just enqueued on the learner's stream reads `slots` of the store asynchronously: remember them (and an event
+// behind the step) so that idqn_replay_put orders a write into one of them after the read
+static int note_learner_read(idqn_handle* h, idqn_replay* r, const int64_t* slots, int n) {
+  CK(cudaEventRecord(r->ev_learner, h->stream));
+  r->learner_slots->assign(slots, slots + n);
+  r->learner_pending = 1;
   return IDQN_OK;
 }
 
@@ -190,14 +216,17 @@ extern "C" int idqn_learn_from_replay(idqn_handle* h, idqn_replay* r, const int6
     h->rsrc_on = 1, h->graph_set = 3;
     rc = idqn_learn_step_resident(h, u8, losses);
     h->rsrc_on = 0, h->graph_set = 0;
-    return rc;
+    if (rc) return rc;
+    return note_learner_read(h, r, slots, n);
   }
   GatherArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n;
   a.o_state = (uint8_t*)h->s, a.o_next = (uint8_t*)h->s2, a.o_action = h->action, a.o_reward_f32 = h->reward;
   a.o_terminal = h->terminal;
-  rc = launch_gather(r, a, h->stream);
+  rc = launch_gather(r, a, h->stream, r->d_slots);
   if (rc) return rc;
-  return idqn_learn_step_resident(h, u8, losses);
+  rc = idqn_learn_step_resident(h, u8, losses);
+  if (rc) return rc;
+  return note_learner_read(h, r, slots, n);
 }

@@ -3,6 +3,7 @@ device-resident views handed out as ``agent.params`` / ``agent.target_params`` /
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from collections import namedtuple
 from typing import Any, Dict, List, Optional, Sequence
@@ -101,6 +102,8 @@ class Engine:
                 f"architecture_type={architecture_type!r}: only 'cnn' and 'fc' have sm_100a kernels "
                 "('impala' is out of the hot-path scope, SURVEY §2 row 3)")
         features = [int(f) for f in features]
+        if int(n_actions) > L.MAX_ACTIONS:
+            raise ValueError(f"n_actions={n_actions}: the fused final-layer kernels hold at most {L.MAX_ACTIONS} actions")
         if len(features) > L.MAX_FEATURES:
             raise ValueError("too many feature layers")
         obs = tuple(int(d) for d in np.atleast_1d(observation_dim))
@@ -118,7 +121,8 @@ class Engine:
         cfg.batch_size = int(batch_size)
         cfg.learning_rate, cfg.adam_eps = float(learning_rate), float(adam_eps)
         cfg.gamma_n = float(np.float32(float(gamma) ** int(update_horizon)))  # idqn.py:122 python float -> f32
-        cfg.device, cfg.flags = int(device), int(flags)
+        # IDQN_FLAGS in the environment ORs extra IDQN_F_* bits into every handle (A/B runs under ncu / compute-sanitizer)
+        cfg.device, cfg.flags = int(device), int(flags) | int(os.environ.get("IDQN_FLAGS", "0"))
         self.cfg = cfg
         self.K, self.B, self.A = int(n_heads), int(batch_size), int(n_actions)
         self.architecture_type = architecture_type
@@ -236,6 +240,13 @@ class Engine:
         return s, s2, int(u8), a, r, d
 
     def learn_host(self, batch, want_losses: bool = True) -> Optional[np.ndarray]:
+        if not want_losses:
+            # nobody reads this step's losses (update_online_params, idqn.py:65-72, only accumulates them on the device):
+            # take the two-slot pipelined staging -- the H2D copies of this batch run on the copy stream while the
+            # previous step still computes and the call returns as soon as everything is enqueued, which is how the
+            # reference's own call behaves (jax dispatches learn_on_batch asynchronously)
+            self.submit_host(batch)
+            return None
         s, s2, u8, a, r, d = self.pack_batch(batch)
         losses = np.zeros(self.K, np.float32) if want_losses else None
         L.check(self.lib.idqn_learn_on_batch_host(self.h, L.ptr(s), L.ptr(s2), u8, L.ptr(a), L.ptr(r), L.ptr(d),
@@ -264,6 +275,10 @@ class Engine:
                                                  C.c_void_p(a_ptr), C.c_void_p(r_ptr), C.c_void_p(d_ptr),
                                                  L.ptr(losses) if want_losses else None))
         return losses
+
+    def set_loss_accumulation(self, on: bool) -> None:
+        """idqn.py:72 — whether the following steps add their losses to the device-side running sums."""
+        L.check(self.lib.idqn_set_loss_accumulation(self.h, int(bool(on))))
 
     def cumulated_losses(self, reset: bool = False) -> np.ndarray:
         out = np.zeros(self.K, np.float64)

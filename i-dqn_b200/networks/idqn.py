@@ -182,7 +182,11 @@ class iDQN:
         own = (isinstance(params, Tree) and params.is_view_of(self._engine, L.ONLINE)
                and isinstance(params_target, Tree) and params_target.is_view_of(self._engine, L.TARGET))
         if own:
-            losses = self._engine.learn_host(batch_samples)
+            self._engine.set_loss_accumulation(False)  # idqn.py:72: only update_online_params feeds cumulated_losses
+            try:
+                losses = self._engine.learn_host(batch_samples)
+            finally:
+                self._engine.set_loss_accumulation(True)
             return self.params, self.optimizer_state, self._out_loss(losses)
         eng = self._scratch_engine()
         eng.upload_tree(L.ONLINE, _host(params), squeezed=self._squeeze)

@@ -14,6 +14,7 @@ how the protocol is tested on CPU with the gloo backend (tests/test_parallel_glo
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -152,9 +153,27 @@ def make_sharded_idqn(key, observation_dim, n_actions, n_networks_total: int, fe
     if k_local == 0:
         raise ValueError(f"rank {rank} owns no head: use world_size <= n_networks ({n_networks_total})")
 
+    import ctypes as C
+    import os
+
+    use_peer = os.environ.get("IDQN_EXCHANGE", "peer") == "peer" and world_size > 1
+
     class ShardediDQN(iDQN):
         def update_target_params(self, step: int):
             eng = self._engine
+            if self._peer is not None:
+                # NVLink peer-memory exchange (csrc/peer.cu): everything is enqueued on the learner's stream
+                if step % self.target_update_frequency == 0:
+                    L.check(eng.lib.idqn_peer_shift_params(self._peer))
+                    cumulated = eng.cumulated_losses(reset=True)
+                    denom = self.target_update_frequency / self.update_to_data
+                    logs = {"loss": np.mean(cumulated) / denom}
+                    for i in range(self.n_networks):
+                        logs[f"networks/{start + i}_loss"] = cumulated[i] / denom
+                    return True, logs
+                if step % self.target_sync_frequency == 0:
+                    L.check(eng.lib.idqn_peer_sync_target(self._peer))
+                return False, {}
             if step % self.target_update_frequency == 0:
                 eng.copy_online_to_target()
                 with torch.cuda.stream(self._stream):
@@ -189,7 +208,24 @@ def make_sharded_idqn(key, observation_dim, n_actions, n_networks_total: int, fe
     agent._target = arena_tensor(agent._engine, L.TARGET)
     agent._stream = engine_stream(agent._engine)
     agent.head_offset, agent.n_networks_total = start, n_networks_total
-    with torch.cuda.stream(agent._stream):
-        warm_up_links(agent._online[0], rank, parts, dist, group)
+    agent._peer = None
+    if use_peer:
+        # CUDA-IPC handles of every rank's arenas travel once through the process group; from then on the target events
+        # are kernels storing into the neighbour's memory over NVLink
+        lib = agent._engine.lib
+        blob = C.create_string_buffer(int(lib.idqn_peer_export_size()))
+        peer = C.c_void_p()
+        L.check(lib.idqn_peer_create(agent._engine.h, C.byref(peer), blob))
+        blobs = [None] * world_size
+        dist.all_gather_object(blobs, bytes(blob.raw), group=group)
+        prev, nxt = _neighbours(rank, parts)
+        keep = [C.create_string_buffer(blobs[r], len(blobs[r])) if r is not None else None for r in (prev, nxt)]
+        L.check(lib.idqn_peer_connect(peer, keep[0], keep[1]))
+        agent._peer = peer
+        agent._peer_finalizer = weakref.finalize(agent, lib.idqn_peer_destroy, peer)
+        dist.barrier(group=group)  # every rank has mapped its neighbours before the first event
+    else:
+        with torch.cuda.stream(agent._stream):
+            warm_up_links(agent._online[0], rank, parts, dist, group)
     torch.cuda.synchronize()
     return agent

@@ -72,9 +72,21 @@ class PrioritizedSamplingDistribution(UniformSamplingDistribution):
         super().remove(key)
 
     def sample(self, size: int):
+        # samplers.py:105-108: an all-zero tree falls back to the uniform sampler (the reference spells the intent as
+        # ``super().sample(size).keys``, which cannot work on an ndarray; the fallback itself is what is kept).  The
+        # root is NOT read back every step: the device reports an empty tree as an out-of-range target, and only
+        # then the host looks at the root, rewinds the generator (the reference draws no uniforms in this branch) and
+        # samples uniformly -- the PCG64 stream stays the reference's in both branches.
+        rng_state = self._rng_key.bit_generator.state
         # rng.uniform(0.0, root) == 0.0 + root * rng.random(): the product is formed on the device (__dmul_rn),
         # so the root never has to come back to the host on the step path.
         units = self._rng_key.random(size)
-        leaves = self._sum_tree.sample_unit(units)
+        try:
+            leaves = self._sum_tree.sample_unit(units)
+        except ValueError:
+            if self._sum_tree.root != 0.0:
+                raise
+            self._rng_key.bit_generator.state = rng_state
+            return super().sample(size)
         table = self._index_to_key
         return np.fromiter((table[i] for i in leaves), dtype=np.int32, count=size)

@@ -69,6 +69,7 @@ typedef struct idqn_config {
 #define IDQN_F_SLOW_APPLY 512 /* best_action through the generic batch-1 kernels instead of the step's own kernels */
 #define IDQN_F_NO_DEFER 256 /* Dense_0 wgrad+Adam right after its data gradient instead of at the end of the backward pass */
 #define IDQN_F_NO_FORK 128  /* keep the conv weight-gradient kernels on the main stream (no second graph branch) */
+#define IDQN_F_TIMELINE 1024 /* kernels stamp the global timer at first-CTA start / last-CTA end: idqn_kernel_timeline reads the true in-graph schedule */
 #define IDQN_F_OLD_WGRAD 64 /* Dense_0 wgrad+Adam on the generic tcgen05 kernel (Adam in its epilogue) instead of the TMA pipeline */
 
 typedef struct idqn_handle idqn_handle;
@@ -125,6 +126,9 @@ int idqn_submit_batch_host(idqn_handle* h, const void* state_host, const void* n
                            const int32_t* action_host, const float* reward_host, const uint8_t* is_terminal_host,
                            int64_t* ticket);
 int idqn_wait_losses(idqn_handle* h, int64_t ticket, float* losses_host);
+/* idqn.py:72: only update_online_params adds a step's losses to the running sums; a direct learn_on_batch call does not.
+ * on = 0 makes the following steps leave the sums alone (stream-ordered; default on = 1) */
+int idqn_set_loss_accumulation(idqn_handle* h, int on);
 /* idqn.py:72,82-87: device-side sum of the per-head losses since the last reset */
 int idqn_read_cumulated_losses(idqn_handle* h, double* sums_host, int reset);
 
@@ -132,6 +136,9 @@ int idqn_read_cumulated_losses(idqn_handle* h, double* sums_host, int reset);
  * event after every launch -> ms[i] / names[32*i..] per kernel, in launch order (uses the staged batch) */
 int idqn_kernels_per_step(idqn_handle* h);
 int idqn_profile_step(idqn_handle* h, int state_is_u8, int max_entries, float* ms, char* names, int* n_out);
+/* IDQN_F_TIMELINE handles: global-timer stamps (ns) of the kernels of the most recent step in launch order, out[2*i] =
+ * start of the first CTA, out[2*i+1] = end of the last CTA, names[32*i..] the kernel tag; resets the slots */
+int idqn_kernel_timeline(idqn_handle* h, unsigned long long* out, char* names, int max_entries, int* n_out);
 /* pipeline timeline of CTA 0 of the kernel named by the IDQN_TL environment variable (fwd0..2, dgrad1..2, wgrad0..2,
  * dfwd3, ddgrad3) during the most recent step: entries (clock64 << 16 | tag), 0 = unused; returns the entry count */
 int idqn_debug_timeline(unsigned long long* out, int max_entries);
@@ -140,6 +147,22 @@ int idqn_debug_timeline(unsigned long long* out, int max_entries);
 int idqn_shift_params(idqn_handle* h);
 int idqn_sync_target(idqn_handle* h);
 int idqn_copy_online_to_target(idqn_handle* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Head-sharded chain over the GPUs of one box (one process per GPU): shift_params / sync_target_params
+ * (idqn.py:13-24) act on the GLOBAL head index, so at the target events of idqn.py:74-94 one boundary head crosses
+ * to the neighbouring rank.  Each rank exports CUDA-IPC handles of its arenas (idqn_peer_create fills a blob of
+ * idqn_peer_export_size() bytes; the host exchanges the blobs by any means), maps its neighbours'
+ * (idqn_peer_connect; NULL at the ends of the chain) and from then on the events are enqueued on the handle's stream:
+ * the boundary head is PUSHED into the neighbour's slot by a kernel storing to peer memory over NVLink, ordered by
+ * flags in peer memory -- no host synchronisation, no collective library on the event path. */
+typedef struct idqn_peer idqn_peer;
+int idqn_peer_export_size(void);
+int idqn_peer_create(idqn_handle* h, idqn_peer** out, void* export_blob);
+int idqn_peer_connect(idqn_peer* p, const void* prev_blob, const void* next_blob);
+int idqn_peer_destroy(idqn_peer* p);
+int idqn_peer_sync_target(idqn_peer* p);   /* idqn.py:91-92 sync_target_params across the shards */
+int idqn_peer_shift_params(idqn_peer* p);  /* idqn.py:75-80 target <- online, then shift_params across the shards */
 
 /* network.apply (architectures/dqn.py:37-70) of head `head` of arena `which` on n inputs -> q_host[n, A] */
 int idqn_apply_host(idqn_handle* h, int which, int head, const void* x_host, int x_is_u8, int n, float* q_host);

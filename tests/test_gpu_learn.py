@@ -259,17 +259,36 @@ def test_functional_learn_on_batch_is_pure_and_dqn_api():
     assert agent.update_target_params(3) == (False, {})
 
 
+class _ListBuffer:
+    """Stand-in replay buffer for update_online_params (idqn.py:65-72): hands out prepared batches in order."""
+
+    def __init__(self, batches):
+        self._batches, self._i = batches, 0
+
+    def sample(self):
+        b = self._batches[self._i]
+        self._i += 1
+        return b
+
+
 def test_loss_logging_and_cumulated_losses():
+    """idqn.py:72,82-87: update_online_params feeds cumulated_losses, update_target_params logs and resets them; a
+    direct learn_on_batch call (idqn.py:96-109) returns the losses and leaves the running sums alone."""
     from idqn_b200.networks.idqn import iDQN
     rng = np.random.default_rng(9)
     agent = iDQN(1, 8, 4, 3, [16], "fc", 1e-3, 0.99, 1, 1, 4, 2, 1e-8)
+    twin = iDQN(1, 8, 4, 3, [16], "fc", 1e-3, 0.99, 1, 1, 4, 2, 1e-8)  # same key: same parameters
+    batches = [make_batch(rng, 32, (8, 1), 4, False) for _ in range(4)]
+    rb = _ListBuffer(batches)
     tot = np.zeros(3)
     for step in range(1, 5):
-        batch = make_batch(rng, 32, (8, 1), 4, False)
-        _, _, l = agent.learn_on_batch(agent.params, agent.target_params, agent.optimizer_state, batch)
+        agent.update_online_params(step, rb)
+        _, _, l = twin.learn_on_batch(twin.params, twin.target_params, twin.optimizer_state, batches[step - 1])
         tot += l
         if step < 4:
             assert agent.update_target_params(step)[0] is False
+            twin.update_target_params(step)
+    assert (twin.cumulated_losses == 0).all(), "learn_on_batch must not feed cumulated_losses"
     np.testing.assert_allclose(agent.cumulated_losses, tot, rtol=1e-6)
     upd, logs = agent.update_target_params(4)
     assert upd
@@ -384,3 +403,50 @@ def test_best_action_fast_path_equals_generic_path():
                     assert fast == slow == as_float == int(np.argmax(q)), (rnd, trial, head, fast, slow, q)
         for ag in agents:  # one learning step, then again: the step's buffers were reused in between
             ag._engine.learn_host(batch, want_losses=False)
+
+
+def test_head_results_do_not_depend_on_how_many_heads_share_the_gpu():
+    """Every reduction of the step (conv weight-gradient partial sums, Dense_0 split-K, batch sums) is grouped by the
+    batch / layer shape only: head k of a K=3 agent and the same head alone in a K=1 agent (its target events fed by
+    hand from its neighbours, as parallel.py does across GPUs) stay BIT-IDENTICAL over 6 steps with one D-sync and one
+    T-shift.  This is the single-GPU proof that the head-sharded chain equals the unsharded one."""
+    from idqn_b200 import _lib as L
+    from idqn_b200.networks.idqn import iDQN
+    obs, feats, A, K, B, T, D = (84, 84, 4), [32, 64, 64, 512], 6, 3, 32, 4, 2
+    rng = np.random.default_rng(41)
+    params = O.init_params(rng, obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    target = O.init_params(np.random.default_rng(1041), obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    full = iDQN(0, obs, A, K, feats, "cnn", 3e-4, 0.99, 1, 1, T, D, 1.5e-4)
+    full.params, full.target_params = params, target
+    solo = []
+    for k in range(K):
+        ag = iDQN(0, obs, A, 1, feats, "cnn", 3e-4, 0.99, 1, 1, T, D, 1.5e-4)
+        ag.params = O.tree_map(lambda a: a[k:k + 1], params)
+        ag.target_params = O.tree_map(lambda a: a[k:k + 1], target)
+        solo.append(ag)
+    for step in range(1, 7):
+        batch = make_batch(rng, B, obs, A, True)
+        lf = full._engine.learn_host(batch, want_losses=True)
+        ls = np.concatenate([ag._engine.learn_host(batch, want_losses=True) for ag in solo])
+        np.testing.assert_array_equal(lf, ls, err_msg=f"losses step {step}")
+        full.update_target_params(step)
+        # the same events on the one-head agents, boundary heads moved by hand (idqn.py:13-24,74-94)
+        on = [ag.params.to_host() for ag in solo]
+        if step % T == 0:
+            for k, ag in enumerate(solo):
+                ag.target_params = on[k]
+                ag.params = on[min(k + 1, K - 1)]
+        elif step % D == 0:
+            for k, ag in enumerate(solo):
+                if k > 0:
+                    ag.target_params = on[k - 1]
+    for which, name in ((L.ONLINE, "online"), (L.TARGET, "target"), (L.MU, "mu"), (L.NU, "nu")):
+        f = full._engine.download_arena(which)
+        for k, ag in enumerate(solo):
+            np.testing.assert_array_equal(f[k], ag._engine.download_arena(which)[0], err_msg=f"{name} head {k}")
+
+
+def test_more_actions_than_the_head_kernels_hold_is_refused():
+    from idqn_b200.networks.idqn import iDQN
+    with pytest.raises(ValueError):
+        iDQN(0, 8, 33, 2, [16], "fc", 1e-3, 0.99, 1, 1, 4, 2, 1e-8)

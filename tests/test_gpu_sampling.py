@@ -316,3 +316,18 @@ def test_device_replay_feeds_learner_like_host_path():
     for m in pa["params"]:
         np.testing.assert_array_equal(pa["params"][m]["kernel"], pb["params"][m]["kernel"])
     np.testing.assert_array_equal(a.cumulated_losses, b.cumulated_losses)
+
+
+def test_prioritized_sampler_with_an_all_zero_tree_falls_back_to_uniform():
+    """samplers.py:105-108: with every priority zero (add(priority=None)) the prioritised sampler draws like the uniform
+    one -- same PCG64 stream, same keys -- instead of raising; once a positive priority exists the tree decides."""
+    from idqn_b200.sample_collection.samplers import PrioritizedSamplingDistribution, UniformSamplingDistribution
+    p = PrioritizedSamplingDistribution(seed=3, max_capacity=64)
+    u = UniformSamplingDistribution(seed=3)
+    for key in range(20):
+        p.add(key, priority=None)
+        u.add(key)
+    for _ in range(3):
+        np.testing.assert_array_equal(p.sample(8), u.sample(8))
+    p.update(np.asarray([7], np.int32), np.asarray([2.5]))
+    assert (p.sample(16) == 7).all()

@@ -96,3 +96,103 @@ def test_schedule_trace_appendix_b():
     assert got[12] == ["grad", "D"] and got[16] == ["grad", "T"]
     sch = O.ScheduleOracle(2.0, 8, 4)  # update_to_data is a float flag in the reference
     assert sch.events(3) == [] and sch.events(4) == ["grad", "D"]
+
+
+# ---- the second, independent oracle (NumPy float64, hand-derived backward) and the committed fixtures -----------------
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import golden_network as GN  # noqa: E402
+from golden_network import G  # noqa: E402
+from oracle import networks_np as N  # noqa: E402
+
+
+@pytest.mark.parametrize("arch,obs,feats,A,K,u8", [("fc", (8,), [100, 100], 4, 3, False),
+                                                   ("cnn", (84, 84, 4), [32, 64, 64, 512], 6, 1, True),
+                                                   ("cnn", (37, 50, 3), [5, 7, 9, 33], 18, 2, True)])
+def test_two_independent_oracles_agree_in_float64(arch, obs, feats, A, K, u8):
+    """torch autograd + F.conv2d (oracle/networks.py) vs explicit patch gathers + hand-derived chain rule
+    (oracle/networks_np.py): losses, every gradient, updated parameter and Adam moment agree to float64 rounding."""
+    rng = np.random.default_rng(7)
+    params = O.init_params(rng, obs, feats, arch, A, n_networks=K, bias_scale=0.01)
+    target = O.init_params(rng, obs, feats, arch, A, n_networks=K, bias_scale=0.01)
+    batch = small_batch(rng, 32, obs if arch == "cnn" else obs + (1,), A, u8=u8)
+    st = O.init_optimizer_state(params)
+    n_p, n_s, n_l, n_g = N.learn_on_batch(params, target, st, batch, arch, 0.99, 1, 3e-4, 1.5e-4)
+    o_p, o_s, o_l, o_g = O.learn_on_batch(params, target, st, batch, arch, 0.99, 1, 3e-4, 1.5e-4, torch.float64, return_grads=True)
+    np.testing.assert_allclose(n_l, o_l, rtol=1e-12)
+    for mod in n_g["params"]:
+        for leaf in n_g["params"][mod]:
+            for a, b in ((n_g, o_g), (n_p, o_p), (n_s["mu"], o_s["mu"]), (n_s["nu"], o_s["nu"])):
+                x, y = np.asarray(a["params"][mod][leaf], np.float64), np.asarray(b["params"][mod][leaf], np.float64)
+                assert np.linalg.norm(x - y) <= 1e-12 * max(np.linalg.norm(y), 1e-30), (mod, leaf)
+    assert (n_s["count"] == o_s["count"]).all()
+    assert N.schedule_events(8, 1, 8, 4) == ["learn", "T"] and N.schedule_events(4, 1, 8, 4) == ["learn", "D"]
+
+
+class NumpyChain:
+    """The fixture's own generator, re-run: the committed numbers must reproduce."""
+
+    def __init__(self, name):
+        self.c = G.CONFIGS[name]
+
+    def start(self, params, target):
+        f64 = lambda t: O.tree_map(lambda a: np.asarray(a, np.float64), t)
+        self.p, self.t = f64(params), f64(target)
+        K = self.c["K"]
+        self.st = {"count": np.zeros(K, np.int32), "mu": O.tree_map(np.zeros_like, self.p), "nu": O.tree_map(np.zeros_like, self.p)}
+
+    def step(self, batch):
+        c = self.c
+        self.p, self.st, losses, _ = N.learn_on_batch(self.p, self.t, self.st, batch, c["arch"], G.GAMMA, G.NSTEP, c["lr"], c["eps"])
+        return losses
+
+    def state(self):
+        return self.p, self.st["mu"], self.st["nu"], self.st["count"]
+
+    def events(self, step):
+        ev = N.schedule_events(step, 1, G.T, G.D)
+        if "T" in ev:
+            self.t = O.tree_map(np.copy, self.p)
+            self.p = N.shift_params(self.p)
+        elif "D" in ev:
+            self.t = N.sync_target_params(self.p, self.t)
+
+    def final(self):
+        return self.t, self.p
+
+
+class TorchChain(NumpyChain):
+    """oracle/networks.py free-running in float32: the drift a TRUE fp32 implementation shows against the float64
+    fixture -- the calibration of the envelope the CUDA path is held to (tests/golden_network.py)."""
+
+    def start(self, params, target):
+        self.p, self.t, self.st = params, target, O.init_optimizer_state(params)
+
+    def step(self, batch):
+        c = self.c
+        self.p, self.st, losses = O.learn_on_batch(self.p, self.t, self.st, batch, c["arch"], G.GAMMA, G.NSTEP, c["lr"], c["eps"], torch.float32)[:3]
+        return losses
+
+    def events(self, step):
+        ev = O.ScheduleOracle(1, G.T, G.D).events(step)
+        if "T" in ev:
+            self.t = O.tree_map(np.copy, self.p)
+            self.p = O.shift_params(self.p)
+        elif "D" in ev:
+            self.t = O.sync_target_params(self.p, self.t)
+
+
+@pytest.mark.parametrize("name,steps", [("mlp_k3", None), ("cnn_k1", 2)])
+def test_numpy_oracle_reproduces_the_committed_fixture(name, steps):
+    for row in GN.run_chain(name, NumpyChain(name), steps=steps):
+        for what in ("loss", "param", "mu", "nu", "final_target", "final_param"):
+            assert row.get(what, 0.0) <= 1e-12, (row["step"], what, row[what])
+
+
+@pytest.mark.parametrize("name", ["mlp_k3", "cnn_k1"])
+def test_torch_fp32_oracle_free_running_stays_inside_the_stated_envelope(name):
+    GN.check(GN.run_chain(name, TorchChain(name)))
