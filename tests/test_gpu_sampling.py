@@ -308,10 +308,13 @@ def test_device_replay_feeds_learner_like_host_path():
     rb_a, rb_b = fill(5), fill(5)
     mk = lambda: iDQN(3, (84, 84, 4), 6, 2, [32, 64, 64, 512], "cnn", 3e-4, 0.99, 1, 1, 8, 4, 1.5e-4)
     a, b = mk(), mk()
+    class HostOnly:  # hides learn_step_on: update_online_params falls back to rb.sample() + the host-buffer call
+        def sample(self):
+            return rb_b.sample()
+
     for step in range(1, 4):
         a.update_online_params(step, rb_a)  # device gather path
-        batch = rb_b.sample()  # host path with the same sampler stream
-        b.learn_on_batch(b.params, b.target_params, b.optimizer_state, batch)
+        b.update_online_params(step, HostOnly())  # host path with the same sampler stream
     pa, pb = a.params.to_host(), b.params.to_host()
     for m in pa["params"]:
         np.testing.assert_array_equal(pa["params"][m]["kernel"], pb["params"][m]["kernel"])
