@@ -54,6 +54,7 @@ SYMBOLS = {
     "idqn_wait_losses": (_I, [_P, _I64, _P]),
     "idqn_set_loss_accumulation": (_I, [_P, _I]),
     "idqn_read_cumulated_losses": (_I, [_P, _P, _I]),
+    "idqn_read_td_abs": (_I, [_P, _P]),
     "idqn_kernels_per_step": (_I, [_P]),
     "idqn_profile_step": (_I, [_P, _I, _I, _P, _P, C.POINTER(_I)]),
     "idqn_debug_timeline": (_I, [_P, _I]),
@@ -69,6 +70,8 @@ SYMBOLS = {
     "idqn_peer_shift_params": (_I, [_P]),
     "idqn_apply_host": (_I, [_P, _I, _I, _P, _I, _I, _P]),
     "idqn_best_action": (_I, [_P, _I, _I, _P, _I, C.POINTER(C.c_int32)]),
+    "idqn_select_action": (_I, [_P, _P, _I, C.c_uint32, C.c_uint32, _I, C.c_float, C.POINTER(C.c_int32), _P]),
+    "idqn_prng": (_I, [_I, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _P]),
     "idqn_sumtree_create": (_I, [_I64, _I, C.POINTER(_P)]),
     "idqn_sumtree_destroy": (_I, [_P]),
     "idqn_sumtree_depth": (_I, [_P]),
@@ -79,6 +82,9 @@ SYMBOLS = {
     "idqn_sumtree_query": (_I, [_P, _P, _P, _I64]),
     "idqn_sumtree_sample": (_I, [_P, _P, _P, _I64]),
     "idqn_sumtree_read_nodes": (_I, [_P, _P]),
+    "idqn_sumtree_max_recorded": (_I, [_P, C.POINTER(C.c_double)]),
+    "idqn_sumtree_set_at_max": (_I, [_P, C.c_int32]),
+    "idqn_sumtree_update_from_learner": (_I, [_P, _P, _P, _I]),
     "idqn_sumtree_nodes_ptr": (_P, [_P]),
     "idqn_replay_create": (_I, [_I64, _I64, _I, C.POINTER(_P)]),
     "idqn_replay_destroy": (_I, [_P]),

@@ -158,6 +158,8 @@ struct idqn_handle {
   int32_t* count;       // [K]
   float* loss;          // [K] last step
   double* loss_sum;     // [K] cumulated (idqn.py:72)
+  float* td_abs;        // [K][B] per-sample |TD error| of the last step (priorities of prioritised replay)
+  cudaEvent_t ev_step;  // recorded behind a step when another stream has to order itself after it (sum-tree update)
   int32_t* loss_acc_on; // device word: 1 = steps add their losses to loss_sum (update_online_params), 0 = they do not
   int loss_acc_host;    // host mirror of that word
   // batch staging (device)
@@ -202,6 +204,8 @@ struct idqn_handle {
   cudaEvent_t ev_h2d[2], ev_consumed[2], ev_done[2];
   int64_t next_ticket;
   int32_t* best_idx;     // device word receiving the argmax of best_action
+  cudaGraphExec_t* act_graph;  // [K] best_action fast path of head k as ONE graph launch (H2D state, 7 kernels, D2H action)
+  uint8_t* h_state;      // pinned staging of the acting state (source of the graphs' H2D node)
   // pinned host scratch
   float* h_loss;
   int32_t* h_i32;
@@ -252,3 +256,6 @@ struct idqn_replay {
 };
 
 int idqn_learn_step_resident(idqn_handle* h, int state_is_u8, float* losses_host);
+
+// SumTree (sumtree.cu); declared here so that the learner-side update can reach it
+struct idqn_sumtree;

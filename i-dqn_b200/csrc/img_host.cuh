@@ -53,7 +53,9 @@ static bool img_geom(const Layer& l, int layer_index, img::Geom& g) {
 
 static const size_t IMG_SMEM_MAX = 227 * 1024;
 static const size_t IMG_SMEM_OPTIN = 226 * 1024;  // dynamic limit requested per kernel: the device maximum minus room for the kernels' few static __shared__ words
-static const int IMG_WGRAD_IPG = 2;  // images per partial-sum group of the conv weight gradients
+// images per partial-sum group of the conv weight gradients.  3 -> 11 groups at batch 32: with the two tile splits the
+// accumulators need, K = 5 heads give 110 CTAs = one wave (2 -> 160 CTAs = two waves measured +14 us per K = 5 step)
+static const int IMG_WGRAD_IPG = 3;
 
 // decide whether the handle can run the image path and build everything it needs
 static int img_setup(idqn_handle* h) {

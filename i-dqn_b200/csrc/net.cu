@@ -153,6 +153,7 @@ struct HeadArgs {
   int relu_mask;
   float* loss;
   double* loss_sum;
+  float* td_abs;               // [K][B] |Q(s_b, a_b) - y_b| of this step: the priorities of prioritised replay (rb.update)
   const int32_t* loss_acc_on;  // device flag: 0 = this step's losses are NOT added to loss_sum (direct learn_on_batch calls)
   int32_t* count;
   float* q;      // [2K][B][A]
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a) {
     const float y = a.reward[b] + (notdone * a.gamma_n) * mx;
     const int ab = a.action[b];
     const float d = qo[b * A + ab] - y;
+    if (blockIdx.x == 0) a.td_abs[k * B + b] = fabsf(d);
     lterm[b] = d * d;
     coef[b] = 2.f * d / (float)B;  // d mean_b(delta^2) / d Q(s_b, a_b)
     act_s[b] = ab;
@@ -947,6 +949,7 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     a.dstride = h->act_stride;
     a.loss = h->loss, a.loss_sum = h->loss_sum, a.count = h->count;
     a.loss_acc_on = h->loss_acc_on;
+    a.td_abs = h->td_abs;
     a.q = h->q;
     a.part = nullptr, a.ptiles = a.psplits = 0, a.pb_off = 0;
     a.cta0 = 0;
@@ -1185,6 +1188,9 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaMemsetAsync(h->loss, 0, sizeof(float) * K, h->stream));
   CK(cudaMalloc(&h->loss_sum, sizeof(double) * K));
   CK(cudaMemsetAsync(h->loss_sum, 0, sizeof(double) * K, h->stream));
+  CK(cudaMalloc(&h->td_abs, sizeof(float) * K * B));
+  CK(cudaMemsetAsync(h->td_abs, 0, sizeof(float) * K * B, h->stream));
+  CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
   CK(cudaMalloc(&h->loss_acc_on, sizeof(int32_t)));
   CK(cudaMemsetAsync(h->loss_acc_on, 0, sizeof(int32_t), h->stream));
   CK(cudaMemsetAsync(h->loss_acc_on, 1, 1, h->stream));  // little-endian int32 1
@@ -1251,6 +1257,8 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaMallocHost(&h->h_loss, sizeof(float) * std::max(K, B * h->A)));
   CK(cudaMallocHost(&h->h_i32, sizeof(int32_t) * std::max(K, 4)));
   CK(cudaMalloc(&h->best_idx, sizeof(int32_t) * 4));
+  h->act_graph = new cudaGraphExec_t[K]();
+  CK(cudaMallocHost(&h->h_state, (size_t)h->in_elems * 4));
   if (cfg->flags & IDQN_F_TIMELINE) {
     unsigned long long buf[2 * IDQN_KTL_MAX];
     for (int i = 0; i < IDQN_KTL_MAX; ++i) buf[2 * i] = ~0ull, buf[2 * i + 1] = 0;
@@ -1270,6 +1278,8 @@ extern "C" int idqn_destroy(idqn_handle* h) {
   for (int i = 0; i <= IDQN_PROF_MAX; ++i)
     if (h->prof_ev[i]) cudaEventDestroy(h->prof_ev[i]);
   if (h->loss_acc_on) cudaFree(h->loss_acc_on);
+  if (h->td_abs) cudaFree(h->td_abs);
+  if (h->ev_step) cudaEventDestroy(h->ev_step);
   void* ptrs[] = {h->online, h->target, h->mu,     h->nu,  h->grad, h->count, h->loss, h->loss_sum, h->s,
                   h->s2,     h->action, h->reward, h->terminal, h->act,  h->dact,  h->q,    h->part,     h->tickets};
   for (void* p : ptrs)
@@ -1281,6 +1291,12 @@ extern "C" int idqn_destroy(idqn_handle* h) {
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->h_i32) cudaFreeHost(h->h_i32);
   if (h->best_idx) cudaFree(h->best_idx);
+  if (h->act_graph) {
+    for (int k = 0; k < h->K; ++k)
+      if (h->act_graph[k]) cudaGraphExecDestroy(h->act_graph[k]);
+    delete[] h->act_graph;
+  }
+  if (h->h_state) cudaFreeHost(h->h_state);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int i = 0; i < 2; ++i)
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -1513,6 +1529,15 @@ extern "C" int idqn_set_loss_accumulation(idqn_handle* h, int on) {
   return IDQN_OK;
 }
 
+// per-sample absolute TD errors of the most recent step, [K][B] (what rb.update(keys, priorities) is fed with)
+extern "C" int idqn_read_td_abs(idqn_handle* h, float* out) {
+  REQUIRE(h && out, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(out, h->td_abs, sizeof(float) * h->K * h->B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return IDQN_OK;
+}
+
 extern "C" int idqn_read_cumulated_losses(idqn_handle* h, double* sums, int reset) {
   REQUIRE(h && sums, "null argument");
   CK(cudaSetDevice(h->cfg.device));
@@ -1684,8 +1709,40 @@ extern "C" int idqn_best_action(idqn_handle* h, int which, int head, const void*
   REQUIRE(which == IDQN_ONLINE || which == IDQN_TARGET, "best_action needs the online or target arena");
   REQUIRE(head >= 0 && head < h->K, "bad head");
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaMemcpyAsync(h->s, state, (size_t)h->in_elems * (u8 ? 1 : 4), cudaMemcpyHostToDevice, h->stream));
   const bool fast = apply_fast_ok(h, which, u8);
+  if (fast && !(h->cfg.flags & IDQN_F_NO_GRAPH)) {
+    // one graph launch per call: H2D of the state from pinned staging, the 7 kernels of the fast path, argmax, D2H of the
+    // action (captured once per head; 9 API calls -> 1)
+    int rc = refresh_planes(h);  // outside the capture: stale planes are a property of the moment, not of the graph
+    if (rc) return rc;
+    memcpy(h->h_state, state, (size_t)h->in_elems);
+    cudaGraphExec_t& gx = h->act_graph[head];
+    if (!gx) {
+      cudaGraph_t g;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      cudaError_t e0 = cudaMemcpyAsync(h->s, h->h_state, (size_t)h->in_elems, cudaMemcpyHostToDevice, h->stream);
+      rc = e0 == cudaSuccess ? enqueue_apply_fast(h, head) : IDQN_ECUDA;
+      if (!rc) {
+        argmax_kernel<<<1, 32, 0, h->stream>>>(h->q + (int64_t)head * h->B * h->A, h->A, (int32_t*)h->best_idx);
+        if (cudaGetLastError() != cudaSuccess ||
+            cudaMemcpyAsync(h->h_i32, h->best_idx, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+          rc = IDQN_ECUDA;
+      }
+      cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+      if (rc || e != cudaSuccess) {
+        if (e == cudaSuccess && g) cudaGraphDestroy(g);
+        if (!rc) idqn_set_error("best_action: graph capture failed: %s", cudaGetErrorString(e));
+        return rc ? rc : IDQN_ECUDA;
+      }
+      CK(cudaGraphInstantiate(&gx, g, 0));
+      CK(cudaGraphDestroy(g));
+    }
+    CK(cudaGraphLaunch(gx, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *action = h->h_i32[0];
+    return IDQN_OK;
+  }
+  CK(cudaMemcpyAsync(h->s, state, (size_t)h->in_elems * (u8 ? 1 : 4), cudaMemcpyHostToDevice, h->stream));
   int rc = fast ? enqueue_apply_fast(h, head) : enqueue_apply(h, which, head, u8, 1);
   if (rc) return rc;
   // Q-values: q[0..A) (generic path) or the (head, sample 0) row of the step's layout; the index goes to the pinned word
@@ -1715,4 +1772,79 @@ extern "C" int idqn_kernel_timeline(idqn_handle* h, unsigned long long* out, cha
   CK(cudaMemcpyToSymbol(g_ktl, buf, sizeof(buf)));
   *n_out = n;
   return IDQN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Acting draw (slimdqn/sample_collection/utils.py:8-15 + idqn.py:126-131): jax's threefry2x32 PRNG restated on the host
+// in C (the Python-int version cost 27 us per environment step).  Pinned against the values the JAX documentation prints
+// for random.split / random.uniform (tests/test_cabi_and_host.py) and against the Random123 known answers.
+static inline uint32_t tf_rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* y0, uint32_t* y1) {
+  static const int rot[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0], x1 += ks[1];
+  for (int i = 0; i < 5; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      x0 += x1;
+      x1 = tf_rotl(x1, rot[i % 2][j]) ^ x0;
+    }
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
+  }
+  *y0 = x0, *y1 = x1;
+}
+// jax.random.split(key, num): counters arange(2 num) as (x0 = first half, x1 = second half); keys = concat(y0, y1).reshape(num, 2)
+static void tf_split(uint32_t k0, uint32_t k1, int num, uint32_t* out /* [num][2] */) {
+  std::vector<uint32_t> flat(2 * num);
+  for (int i = 0; i < num; ++i) threefry2x32(k0, k1, (uint32_t)i, (uint32_t)(num + i), &flat[i], &flat[num + i]);
+  for (int i = 0; i < 2 * num; ++i) out[i] = flat[i];
+}
+static uint32_t tf_bits32(uint32_t k0, uint32_t k1) {
+  uint32_t a, b;
+  threefry2x32(k0, k1, 0, 0, &a, &b);
+  return a;
+}
+static float tf_uniform(uint32_t k0, uint32_t k1) {  // jax.random.uniform(key): mantissa bits | 1.0f, minus 1
+  const uint32_t bits = (tf_bits32(k0, k1) >> 9) | 0x3F800000u;
+  float f;
+  memcpy(&f, &bits, 4);
+  return f - 1.0f;
+}
+static int32_t tf_randint(uint32_t k0, uint32_t k1, int32_t minval, int32_t maxval) {  // jax.random.randint(key, (), lo, hi), int32
+  uint32_t ks[4];
+  tf_split(k0, k1, 2, ks);
+  const uint32_t hi = tf_bits32(ks[0], ks[1]), lo = tf_bits32(ks[2], ks[3]);
+  const uint32_t span = maxval > minval ? (uint32_t)(maxval - minval) : 1u;
+  uint32_t mult = 65536u % span;
+  mult = (uint32_t)(((uint64_t)mult * mult) % span);
+  uint32_t off = (uint32_t)((uint64_t)(hi % span) * mult) + (lo % span);
+  return minval + (int32_t)(off % span);
+}
+
+extern "C" int idqn_prng(int what, uint32_t key0, uint32_t key1, int32_t a, int32_t b, uint32_t* out) {
+  REQUIRE(out, "null argument");
+  switch (what) {
+    case 0: tf_split(key0, key1, a, out); return IDQN_OK;                                 // split(key, a) -> out[2a]
+    case 1: { float u = tf_uniform(key0, key1); memcpy(out, &u, 4); return IDQN_OK; }     // uniform(key) -> float bits
+    case 2: out[0] = (uint32_t)tf_randint(key0, key1, a, b); return IDQN_OK;              // randint(key, (), a, b)
+  }
+  REQUIRE(false, "unknown draw %d", what);
+}
+
+// select_action (utils.py:8-15): uniform_key, action_key, kwargs_key = split(key, 3); explore if uniform(uniform_key) <= epsilon,
+// else best_action(params, state, key=kwargs_key) whose head is randint(kwargs_key, (), 0, K) (idqn.py:128).
+// info[0] = 1 if the random action was taken, info[1] = the head that was (or would have been) asked.
+extern "C" int idqn_select_action(idqn_handle* h, const void* state, int u8, uint32_t key0, uint32_t key1, int n_actions,
+                                  float epsilon, int32_t* action, int32_t* info) {
+  REQUIRE(h && state && action, "null argument");
+  uint32_t ks[6];
+  tf_split(key0, key1, 3, ks);
+  const bool explore = tf_uniform(ks[0], ks[1]) <= epsilon;
+  const int32_t head = tf_randint(ks[4], ks[5], 0, h->K);
+  if (info) info[0] = explore ? 1 : 0, info[1] = head;
+  if (explore) {
+    *action = tf_randint(ks[2], ks[3], 0, n_actions);
+    return IDQN_OK;  // no device work at all on an exploring step
+  }
+  return idqn_best_action(h, IDQN_ONLINE, head, state, u8, action);
 }

@@ -36,6 +36,8 @@ struct idqn_peer {
   PeerFlags* prev_flags;
   int prev_heads;                      // heads held by rank r-1 (its last slot = prev_heads - 1)
   unsigned int epoch_d, epoch_t;       // events executed so far (every rank runs the same schedule)
+  cudaStream_t push_stream;            // the push runs NEXT to the in-shard copies of the event
+  cudaEvent_t ev_fork, ev_pushed;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -116,6 +118,9 @@ extern "C" int idqn_peer_create(idqn_handle* h, idqn_peer** out, void* export_bl
   CK(cudaMalloc(&p->flags, sizeof(PeerFlags)));
   CK(cudaMemset(p->flags, 0, sizeof(PeerFlags)));
   CK(cudaMalloc(&p->stage, sizeof(float) * h->stride));
+  CK(cudaStreamCreateWithFlags(&p->push_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&p->ev_pushed, cudaEventDisableTiming));
   PeerExport* e = (PeerExport*)export_blob;
   memset(e, 0, sizeof(*e));
   CK(cudaIpcGetMemHandle(&e->online, h->online));
@@ -154,6 +159,12 @@ extern "C" int idqn_peer_destroy(idqn_peer* p) {
     if (m) cudaIpcCloseMemHandle(m);
   if (p->flags) cudaFree(p->flags);
   if (p->stage) cudaFree(p->stage);
+  if (p->push_stream) {
+    cudaStreamSynchronize(p->push_stream);
+    cudaStreamDestroy(p->push_stream);
+  }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_pushed) cudaEventDestroy(p->ev_pushed);
   delete p;
   return IDQN_OK;
 }
@@ -175,15 +186,21 @@ extern "C" int idqn_peer_sync_target(idqn_peer* p) {
     peer_signal_kernel<<<1, 32, 0, st>>>(&p->prev_flags->next_ready_d, e);
     CK(cudaGetLastError());
   }
-  // my online[last] is final (the step that produced it precedes us on the stream): push it into the right neighbour's target[0]
+  // my online[last] is final (the step that produced it precedes us on the stream): push it into the right neighbour's
+  // target[0] -- on a second stream, next to the in-shard copies below (both only READ the online arena)
   if (p->has_next) {
     const float* src = h->online + (int64_t)(h->K - 1) * h->stride;
-    peer_push_kernel<<<push_grid(h), 512, 0, st>>>((const uint4*)src, (uint4*)p->next_target, n16, &p->flags->next_ready_d,
-                                                   &p->next_flags->prev_arrived_d, &p->flags->done_ctas[0], e);
+    CK(cudaEventRecord(p->ev_fork, st));
+    CK(cudaStreamWaitEvent(p->push_stream, p->ev_fork, 0));
+    peer_push_kernel<<<push_grid(h), 512, 0, p->push_stream>>>((const uint4*)src, (uint4*)p->next_target, n16,
+                                                                &p->flags->next_ready_d, &p->next_flags->prev_arrived_d,
+                                                                &p->flags->done_ctas[0], e);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev_pushed, p->push_stream));
   }
   int rc = idqn_sync_target(h);  // in-shard part, target[1:] <- online[:-1], fp32 + planes
   if (rc) return rc;
+  if (p->has_next) CK(cudaStreamWaitEvent(st, p->ev_pushed, 0));  // the next step rewrites online[last]
   if (p->has_prev) {
     peer_wait_kernel<<<1, 32, 0, st>>>(&p->flags->prev_arrived_d, e);
     CK(cudaGetLastError());

@@ -24,6 +24,7 @@ struct idqn_sumtree {
   double* d_val;   // values in, deltas after
   int32_t* d_out;
   int* d_err;
+  double* d_maxrec;  // max_recorded_priority (sum_tree.py:18,32), tracked on the device
   // pinned host scratch
   int* h_err;
   double* h_root;
@@ -33,9 +34,11 @@ struct idqn_sumtree {
 
 // ------------------------------------------------------------------------------------------
 // n <= 1024: one CTA sorts (leaf, position) pairs, keeps the first occurrence of each leaf, then propagates.
+// val == nullptr: every listed leaf is set to *maxrec (insertion of a new element at max_recorded_priority)
 __global__ void __launch_bounds__(1024) sumtree_set_small_kernel(double* __restrict__ nodes, int64_t first_leaf,
                                                                  int depth, const int32_t* __restrict__ idx,
-                                                                 const double* __restrict__ val, int n) {
+                                                                 const double* __restrict__ val, int n,
+                                                                 double* __restrict__ maxrec) {
   __shared__ unsigned long long keys[ST_SMALL];
   __shared__ int leaf_s[ST_SMALL];
   __shared__ double delta_s[ST_SMALL];
@@ -66,9 +69,14 @@ __global__ void __launch_bounds__(1024) sumtree_set_small_kernel(double* __restr
       if (i == 0 || leaf != (int)(keys[i - 1] >> 32)) {
         int pos = (int)(keys[i] & 0xffffffffu);
         leaf_s[m] = leaf;
-        delta_s[m] = val[pos] - nodes[first_leaf + leaf];  // sum_tree.py:34
+        delta_s[m] = (val ? val[pos] : *maxrec) - nodes[first_leaf + leaf];  // sum_tree.py:34
         ++m;
       }
+    }
+    if (val) {  // sum_tree.py:32: max over ALL given values (duplicates included)
+      double mx = *maxrec;
+      for (int i = 0; i < n; ++i) mx = fmax(mx, val[i]);
+      *maxrec = mx;
     }
     m_s = m;
   }
@@ -102,6 +110,17 @@ __global__ void sumtree_propagate_kernel(double* __restrict__ nodes, int64_t fir
   double x = nodes[node];
   for (int64_t j = i; j < m && (((first_leaf + leaf[j] + 1) >> lev) - 1) == node; ++j) x = x + delta[j];
   nodes[node] = x;
+}
+
+__global__ void sumtree_max_kernel(double* maxrec, double v) { *maxrec = fmax(*maxrec, v); }
+
+// priorities of prioritised replay from the learner's per-head |TD| of its last step: val[i] = mean_k td[k][i] in float64
+__global__ void sumtree_td_priority_kernel(const float* __restrict__ td, int K, int B, double* __restrict__ val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  double s = 0.0;
+  for (int k = 0; k < K; ++k) s += (double)td[k * B + i];  // fixed order
+  val[i] = s / (double)K;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -206,6 +225,11 @@ extern "C" int idqn_sumtree_create(int64_t capacity, int device, idqn_sumtree** 
   CK(cudaMemsetAsync(t->d_err, 0, sizeof(int), t->stream));
   CK(cudaMallocHost(&t->h_err, sizeof(int)));
   CK(cudaMallocHost(&t->h_root, sizeof(double)));
+  CK(cudaMalloc(&t->d_maxrec, sizeof(double)));
+  {
+    const double one = 1.0;  // sum_tree.py:18
+    CK(cudaMemcpyAsync(t->d_maxrec, &one, sizeof(double), cudaMemcpyHostToDevice, t->stream));
+  }
   int rc = ensure_scratch(t, 1024);
   if (rc) return rc;
   CK(cudaStreamSynchronize(t->stream));
@@ -217,7 +241,7 @@ extern "C" int idqn_sumtree_destroy(idqn_sumtree* t) {
   if (!t) return IDQN_OK;
   cudaSetDevice(t->device);
   cudaStreamSynchronize(t->stream);
-  void* ptrs[] = {t->nodes, t->d_idx, t->d_val, t->d_out, t->d_err};
+  void* ptrs[] = {t->nodes, t->d_idx, t->d_val, t->d_out, t->d_err, t->d_maxrec};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (t->h_err) cudaFreeHost(t->h_err);
@@ -249,7 +273,7 @@ extern "C" int idqn_sumtree_set(idqn_sumtree* t, const int32_t* idx, const doubl
     CK(cudaMemcpyAsync(t->d_val, val, sizeof(double) * n, cudaMemcpyHostToDevice, t->stream));
     int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(64, (n * t->depth + 31) / 32 * 32));
     sumtree_set_small_kernel<<<1, threads, 0, t->stream>>>(t->nodes, t->first_leaf, t->depth, t->d_idx, t->d_val,
-                                                          (int)n);
+                                                          (int)n, t->d_maxrec);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(t->stream));  // the caller's host buffers may go away
     return IDQN_OK;
@@ -268,6 +292,8 @@ extern "C" int idqn_sumtree_set(idqn_sumtree* t, const int32_t* idx, const doubl
     }
   }
   const int64_t m = (int64_t)u.size();
+  sumtree_max_kernel<<<1, 1, 0, t->stream>>>(t->d_maxrec, *std::max_element(val, val + n));
+  CK(cudaGetLastError());
   CK(cudaMemcpyAsync(t->d_idx, u.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, t->stream));
   CK(cudaMemcpyAsync(t->d_val, v.data(), sizeof(double) * m, cudaMemcpyHostToDevice, t->stream));
   const int threads = 256;
@@ -347,4 +373,42 @@ extern "C" int idqn_sumtree_query(idqn_sumtree* t, const double* targets, int32_
 }
 extern "C" int idqn_sumtree_sample(idqn_sumtree* t, const double* unit_uniforms, int32_t* out, int64_t n) {
   return query_impl<true>(t, unit_uniforms, out, n);
+}
+
+extern "C" int idqn_sumtree_max_recorded(idqn_sumtree* t, double* value) {
+  REQUIRE(t && value, "bad argument");
+  CK(cudaSetDevice(t->device));
+  CK(cudaMemcpyAsync(t->h_root, t->d_maxrec, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+  CK(cudaStreamSynchronize(t->stream));
+  *value = *t->h_root;
+  return IDQN_OK;
+}
+
+extern "C" int idqn_sumtree_set_at_max(idqn_sumtree* t, int32_t leaf) {
+  REQUIRE(t && leaf >= 0 && leaf < ((int64_t)1 << (t->depth - 1)), "leaf index %d outside the tree", leaf);
+  CK(cudaSetDevice(t->device));
+  CK(cudaMemcpyAsync(t->d_idx, &leaf, sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
+  sumtree_set_small_kernel<<<1, 64, 0, t->stream>>>(t->nodes, t->first_leaf, t->depth, t->d_idx, nullptr, 1, t->d_maxrec);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(t->stream));
+  return IDQN_OK;
+}
+
+extern "C" int idqn_sumtree_update_from_learner(idqn_sumtree* t, idqn_handle* h, const int32_t* leaves, int n) {
+  REQUIRE(t && h && leaves, "null argument");
+  REQUIRE(n == h->B && n <= ST_SMALL, "%d leaves for a learner batch of %d", n, h->B);
+  REQUIRE(t->device == h->cfg.device, "sum tree and learner live on different devices");
+  for (int i = 0; i < n; ++i)
+    REQUIRE(leaves[i] >= 0 && leaves[i] < ((int64_t)1 << (t->depth - 1)), "leaf index %d outside the tree", leaves[i]);
+  CK(cudaSetDevice(t->device));
+  // ordered behind the learner's step, on the tree's own stream (later queries follow on the same stream)
+  CK(cudaEventRecord(h->ev_step, h->stream));
+  CK(cudaStreamWaitEvent(t->stream, h->ev_step, 0));
+  CK(cudaMemcpyAsync(t->d_idx, leaves, sizeof(int32_t) * n, cudaMemcpyHostToDevice, t->stream));
+  sumtree_td_priority_kernel<<<(n + 127) / 128, 128, 0, t->stream>>>(h->td_abs, h->K, h->B, t->d_val);
+  CK(cudaGetLastError());
+  const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(64, ((int64_t)n * t->depth + 31) / 32 * 32));
+  sumtree_set_small_kernel<<<1, threads, 0, t->stream>>>(t->nodes, t->first_leaf, t->depth, t->d_idx, t->d_val, n, t->d_maxrec);
+  CK(cudaGetLastError());
+  return IDQN_OK;  // no host synchronisation: the leaves were staged by the pageable copy before it returned
 }

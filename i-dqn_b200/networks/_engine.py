@@ -280,6 +280,12 @@ class Engine:
         """idqn.py:72 — whether the following steps add their losses to the device-side running sums."""
         L.check(self.lib.idqn_set_loss_accumulation(self.h, int(bool(on))))
 
+    def td_abs(self) -> np.ndarray:
+        """|Q(s_b, a_b) - y_b| per head and sample of the most recent step, float32 [K, B]."""
+        out = np.zeros((self.K, self.B), np.float32)
+        L.check(self.lib.idqn_read_td_abs(self.h, L.ptr(out)))
+        return out
+
     def cumulated_losses(self, reset: bool = False) -> np.ndarray:
         out = np.zeros(self.K, np.float64)
         L.check(self.lib.idqn_read_cumulated_losses(self.h, L.ptr(out), int(reset)))
@@ -320,6 +326,25 @@ class Engine:
         out = C.c_int32()
         L.check(self.lib.idqn_best_action(self.h, which, head, L.ptr(x), int(u8), C.byref(out)))
         return int(out.value)
+
+    def select_action(self, state, key, n_actions: int, epsilon: float):
+        """utils.py:8-15 in one C call: the three threefry draws, and on a greedy step best_action of the drawn head as
+        one CUDA-graph launch.  Returns (action, explored, head)."""
+        from .. import _prng
+        x = np.asarray(state)
+        u8 = x.dtype == np.uint8
+        if not u8 and self.architecture_type == "cnn":
+            xu = x.astype(np.uint8)  # atari.py:43-45 hands over float32 frames holding 0..255
+            if np.array_equal(xu, x):
+                x, u8 = xu, True
+        x = np.ascontiguousarray(x, dtype=np.uint8 if u8 else np.float32)
+        if x.size != self.in_elems:
+            raise ValueError(f"state has {x.size} elements, expected {self.in_elems}")
+        k = _prng.as_key(key)
+        out, info = C.c_int32(), np.zeros(2, np.int32)
+        L.check(self.lib.idqn_select_action(self.h, L.ptr(x), int(u8), int(k[0]), int(k[1]), int(n_actions),
+                                            float(epsilon), C.byref(out), L.ptr(info)))
+        return int(out.value), bool(info[0]), int(info[1])
 
     def mark_head_planes_dirty(self, which: int, head: int) -> None:
         """One head of an arena was rewritten behind the library's back (neighbour exchange): rebuild its planes."""

@@ -106,9 +106,17 @@ class iDQN:
                       device=c["device"], flags=c["flags"])
 
     # ---- state (live device views) -------------------------------------------------------------------
+    def _view(self, which: int) -> Tree:
+        # live views are stateless handles on an arena: built once (the acting path reads agent.params every environment step)
+        cache = self.__dict__.setdefault("_views", {})
+        v = cache.get((which, self._squeeze))
+        if v is None or v._engine_ref() is not self._engine:
+            v = cache[(which, self._squeeze)] = Tree(self._engine, which, self._squeeze)
+        return v
+
     @property
     def params(self) -> Tree:
-        return Tree(self._engine, L.ONLINE, self._squeeze)
+        return self._view(L.ONLINE)
 
     @params.setter
     def params(self, value):
@@ -117,7 +125,7 @@ class iDQN:
 
     @property
     def target_params(self) -> Tree:
-        return Tree(self._engine, L.TARGET, self._squeeze)
+        return self._view(L.TARGET)
 
     @target_params.setter
     def target_params(self, value):
@@ -129,8 +137,7 @@ class iDQN:
     @property
     def optimizer_state(self):
         e = self._engine
-        return (ScaleByAdamState(CountView(e, self._squeeze), Tree(e, L.MU, self._squeeze), Tree(e, L.NU, self._squeeze)),
-                EmptyState())
+        return (ScaleByAdamState(CountView(e, self._squeeze), self._view(L.MU), self._view(L.NU)), EmptyState())
 
     @optimizer_state.setter
     def optimizer_state(self, value):

@@ -212,6 +212,7 @@ class ReplayBuffer:
         if size is None:
             size = self._batch_size
         keys = self._sampling_distribution.sample(size)
+        self.last_keys = keys
         s, s2, a, r, d, e = self._store.gather(np.asarray(keys, np.int64) % self._max_capacity)
         return ReplayElement(state=s, action=a, reward=r, next_state=s2, is_terminal=d, episode_end=e)
 
@@ -236,3 +237,11 @@ class ReplayBuffer:
 
     def update(self, keys, **kwargs: Any) -> None:
         self._sampling_distribution.update(keys, **kwargs)
+
+    def update_from_learner(self, engine) -> None:
+        """``update(last sampled keys, priorities = |TD error| of the step that just consumed them)`` with the priorities
+        taken from the learner on the device (replay_buffer.py:232-237 wired to the learning step)."""
+        upd = getattr(self._sampling_distribution, "update_from_learner", None)
+        if upd is None:
+            raise TypeError("update_from_learner needs a PrioritizedSamplingDistribution")
+        upd(self.last_keys, engine)

@@ -47,8 +47,16 @@ class PrioritizedSamplingDistribution(UniformSamplingDistribution):
         self._sum_tree = SumTree(self._max_capacity, device=device)
         super().__init__(seed=seed)
 
-    def add(self, key: ReplayItemID, priority: float) -> None:
+    AT_MAX = object()  # default priority of add(): the tree's max_recorded_priority (sum_tree.py:18,32)
+
+    def add(self, key: ReplayItemID, priority=AT_MAX) -> None:
+        """samplers.py:66-73.  Without a priority the element enters at ``max_recorded_priority`` so that it is sampled
+        at least once -- the wiring the reference ships the pieces for but never connects (its ``collect_single_sample``
+        passes no priority, utils.py:27-35, and its ``add`` would raise a TypeError there)."""
         super().add(key)
+        if priority is PrioritizedSamplingDistribution.AT_MAX:
+            self._sum_tree.set_at_max(self._key_to_index[key])
+            return
         if priority is None:
             priority = 0.0
         # scalar power, exactly as samplers.py:72 (numpy's vectorised pow can differ from the scalar one by 1 ulp)
@@ -60,6 +68,19 @@ class PrioritizedSamplingDistribution(UniformSamplingDistribution):
         priorities = np.where(priorities == 0.0, 0.0, priorities ** self._priority_exponent)  # array power, :81
         leaves = np.fromiter((self._key_to_index[int(k)] for k in keys), dtype=np.int32, count=len(keys))
         self._sum_tree.set(leaves, np.atleast_1d(priorities))
+
+    def update_from_learner(self, keys, engine) -> None:
+        """``update(keys, priorities)`` with priorities = mean over the heads of the |TD error| of ``engine``'s last step
+        (replay_buffer.py:232-237 fed from the learner).  With priority_exponent == 1 nothing leaves the device."""
+        leaves = np.fromiter((self._key_to_index[int(k)] for k in keys), dtype=np.int32, count=len(keys))
+        if self._priority_exponent == 1.0:
+            self._sum_tree.update_from_learner(engine, leaves)
+        else:  # the array power stays numpy's (bit-exact with the reference): priorities visit the host
+            td = engine.td_abs().astype(np.float64)
+            pr = td[0].copy()
+            for k in range(1, td.shape[0]):
+                pr += td[k]
+            self.update(np.asarray(keys), pr / td.shape[0])
 
     def remove(self, key: ReplayItemID) -> None:
         hole = self._key_to_index[key]

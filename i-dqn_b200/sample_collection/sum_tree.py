@@ -24,7 +24,14 @@ class SumTree:
         self._depth = int(lib.idqn_sumtree_depth(h))
         self._first_leaf_offset = (2 ** (self._depth - 1)) - 1
         self._n_nodes = int(lib.idqn_sumtree_num_nodes(h))
-        self.max_recorded_priority = 1.0  # sum_tree.py:18
+        self.device = int(device)
+
+    @property
+    def max_recorded_priority(self) -> float:
+        """sum_tree.py:18,32 — tracked on the device (the learner-side priority updates never visit the host)."""
+        v = C.c_double()
+        L.check(self._lib.idqn_sumtree_max_recorded(self._h, C.byref(v)))
+        return float(v.value)
 
     @property
     def _nodes(self) -> np.ndarray:
@@ -43,10 +50,20 @@ class SumTree:
         assert (values >= 0.0).all(), "Values must be positive."
         if indices.size == 0:
             return
-        self.max_recorded_priority = max(self.max_recorded_priority, max(values.ravel()))
         idx = np.ascontiguousarray(indices.ravel(), dtype=np.int32)
         val = np.ascontiguousarray(values.ravel(), dtype=np.float64)
         L.check(self._lib.idqn_sumtree_set(self._h, L.ptr(idx), L.ptr(val), idx.size))
+
+    def set_at_max(self, index: int) -> None:
+        """``set(index, max_recorded_priority)`` without reading the maximum back: how a NEW element enters a prioritised
+        buffer (it will be sampled at least once)."""
+        L.check(self._lib.idqn_sumtree_set_at_max(self._h, int(index)))
+
+    def update_from_learner(self, engine, leaves) -> None:
+        """``set(leaves, mean_k |TD_k|)`` with the per-sample TD errors of ``engine``'s last step taken on the device,
+        ordered behind that step; no host synchronisation."""
+        lv = np.ascontiguousarray(np.asarray(leaves).ravel(), dtype=np.int32)
+        L.check(self._lib.idqn_sumtree_update_from_learner(self._h, engine.h, L.ptr(lv), lv.size))
 
     def get(self, index):  # sum_tree.py:49-51
         scalar = np.ndim(index) == 0

@@ -8,6 +8,12 @@ from .replay_buffer import ReplayBuffer, TransitionElement
 
 
 def select_action(best_action_fn, params, state, key, n_actions, epsilon_fn, n_training_steps):
+    agent = getattr(best_action_fn, "__self__", None)
+    engine = getattr(agent, "_engine", None)
+    if engine is not None and getattr(params, "_engine_ref", lambda: None)() is engine and getattr(params, "_which", None) == 0 \
+            and getattr(agent, "n_networks", 0) == engine.K and not getattr(agent, "_squeeze", False):
+        # the agent's own live parameters: draws + (on a greedy step) the forward pass in one call into the library
+        return engine.select_action(state, key, n_actions, epsilon_fn(n_training_steps))[0]
     uniform_key, action_key, kwargs_key = _prng.split(key, 3)
     if _prng.uniform(uniform_key) <= epsilon_fn(n_training_steps):  # utils.py:12
         return _prng.randint(action_key, 0, n_actions)

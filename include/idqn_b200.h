@@ -129,6 +129,9 @@ int idqn_wait_losses(idqn_handle* h, int64_t ticket, float* losses_host);
 /* idqn.py:72: only update_online_params adds a step's losses to the running sums; a direct learn_on_batch call does not.
  * on = 0 makes the following steps leave the sums alone (stream-ordered; default on = 1) */
 int idqn_set_loss_accumulation(idqn_handle* h, int on);
+/* |Q(s_b,a_b) - y_b| per head and sample of the most recent step, float32 [K][B]: the priorities a prioritised replay buffer
+ * is updated with (replay_buffer.py:232-237) */
+int idqn_read_td_abs(idqn_handle* h, float* out_host);
 /* idqn.py:72,82-87: device-side sum of the per-head losses since the last reset */
 int idqn_read_cumulated_losses(idqn_handle* h, double* sums_host, int reset);
 
@@ -170,6 +173,15 @@ int idqn_apply_host(idqn_handle* h, int which, int head, const void* x_host, int
  * argmax_a Q(params[head], state) for ONE state (float32 holding 0..255 for Atari, atari.py:43-45, or uint8) */
 int idqn_best_action(idqn_handle* h, int which, int head, const void* state_host, int state_is_u8, int32_t* action);
 
+/* select_action (slimdqn/sample_collection/utils.py:8-15) in ONE call: the three jax.random draws of the step (threefry2x32,
+ * restated on the host in C), and -- only on a greedy step -- best_action of the drawn head as one CUDA-graph launch.
+ * key0/key1: the uint32[2] jax key; info (optional, int32[2]): {explored, head}. */
+int idqn_select_action(idqn_handle* h, const void* state_host, int state_is_u8, uint32_t key0, uint32_t key1,
+                       int n_actions, float epsilon, int32_t* action, int32_t* info);
+/* the draws themselves (tests / host mirrors): what = 0 split(key, a) -> out[2a]; 1 uniform(key) -> float32 bits in out[0];
+ * 2 randint(key, (), a, b) -> out[0] */
+int idqn_prng(int what, uint32_t key0, uint32_t key1, int32_t a, int32_t b, uint32_t* out);
+
 /* ------------------------------------------------------------------------------------------------
  * SumTree (slimdqn/sample_collection/sum_tree.py:8-102): float64 nodes resident on the device.
  * set/query reproduce the reference's arithmetic bit for bit (ordered per-ancestor adds, strict <). */
@@ -187,6 +199,15 @@ int idqn_sumtree_query(idqn_sumtree* t, const double* targets_host, int32_t* ind
 /* samplers.py:110-111: targets = root * unit_uniforms (Generator.uniform(0, root)), then query */
 int idqn_sumtree_sample(idqn_sumtree* t, const double* unit_uniforms_host, int32_t* indices_host, int64_t n);
 int idqn_sumtree_read_nodes(idqn_sumtree* t, double* nodes_host);  /* whole _nodes array (tests) */
+/* sum_tree.py:18,32 max_recorded_priority, tracked on the device (device-side updates never visit the host) */
+int idqn_sumtree_max_recorded(idqn_sumtree* t, double* value_host);
+/* set(leaf, max_recorded_priority): how a prioritised buffer inserts a NEW element (it is sampled at least once) */
+int idqn_sumtree_set_at_max(idqn_sumtree* t, int32_t leaf);
+/* PrioritizedSamplingDistribution.update(keys, priorities) (samplers.py:75-87) with the priorities taken straight from
+ * the learner's last step on the device: priority_i = mean over the K heads of |TD_k,i| (float64), leaves_host[i] = the
+ * sampler's leaf of sample i.  Ordered after that step, before any later query; nothing visits the host.
+ * Only priority_exponent == 1 is served here (the reference's array power has to stay numpy's, bit for bit). */
+int idqn_sumtree_update_from_learner(idqn_sumtree* t, idqn_handle* h, const int32_t* leaves_host, int n);
 void* idqn_sumtree_nodes_ptr(idqn_sumtree* t);
 
 /* ------------------------------------------------------------------------------------------------

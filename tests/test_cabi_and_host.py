@@ -167,3 +167,36 @@ def test_scalar_threefry_equals_the_pinned_array_version():
         mult = (mult * mult) % span
         off = ((((hi % span) * mult) & 0xFFFFFFFF) + (lo % span) & 0xFFFFFFFF) % span
         assert _prng.randint(k, 0, span) == off
+
+
+def test_prng_matches_the_values_the_jax_documentation_prints():
+    """Pins of the derived draws against published JAX output (default threefry implementation; "Pseudorandom numbers"
+    tutorial of the JAX documentation): PRNGKey(42) -> [0 42]; split(PRNGKey(42)) -> [2465931498 3679230171], [255383827
+    267815257]; split(PRNGKey(0)) -> [4146024105 967050713], [2718843009 1272950319]; uniform(PRNGKey(0)) -> 0.41845703.
+    jax is not installable here, so these literature values are the pin for the counter layout of split and the
+    bits -> float mapping of uniform; randint is built from the same two primitives (jax._src.random._randint)."""
+    from idqn_b200 import _prng
+    np.testing.assert_array_equal(_prng.as_key(42), [0, 42])
+    np.testing.assert_array_equal(_prng.split(42), [[2465931498, 3679230171], [255383827, 267815257]])
+    np.testing.assert_array_equal(_prng.split(0), [[4146024105, 967050713], [2718843009, 1272950319]])
+    assert _prng.uniform(0) == np.float32(0.41845703)
+
+
+def test_c_draws_equal_the_python_restatement():
+    """idqn_prng / idqn_select_action draw in C what _prng draws in Python (no GPU involved)."""
+    import ctypes as C
+    from idqn_b200 import _lib as L
+    from idqn_b200 import _prng
+    lib = L.lib()
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        k = rng.integers(0, 2 ** 32, 2, dtype=np.uint64).astype(np.uint32)
+        num = int(rng.integers(1, 5))
+        out = np.zeros(2 * num, np.uint32)
+        L.check(lib.idqn_prng(0, int(k[0]), int(k[1]), num, 0, L.ptr(out)))
+        np.testing.assert_array_equal(out.reshape(num, 2), _prng.split(k, num))
+        L.check(lib.idqn_prng(1, int(k[0]), int(k[1]), 0, 0, L.ptr(out)))
+        assert out[:1].view(np.float32)[0] == _prng.uniform(k)
+        lo, span = int(rng.integers(-5, 5)), int(rng.integers(1, 40))
+        L.check(lib.idqn_prng(2, int(k[0]), int(k[1]), lo, lo + span, L.ptr(out)))
+        assert int(out[:1].view(np.int32)[0]) == _prng.randint(k, lo, lo + span)

@@ -450,3 +450,30 @@ def test_more_actions_than_the_head_kernels_hold_is_refused():
     from idqn_b200.networks.idqn import iDQN
     with pytest.raises(ValueError):
         iDQN(0, 8, 33, 2, [16], "fc", 1e-3, 0.99, 1, 1, 4, 2, 1e-8)
+
+
+def test_select_action_in_one_call_equals_the_host_mirror():
+    """utils.py:8-15 through idqn_select_action (C draws + graph-launched best_action of the drawn head) against the
+    Python mirror (split / uniform / randint of _prng, then best_action with the explicit head): same action, same
+    explore decision, same head, for greedy and exploring steps."""
+    from idqn_b200 import _prng
+    from idqn_b200.networks.idqn import iDQN
+    from idqn_b200.sample_collection.utils import select_action
+    obs, feats, A, K = (84, 84, 4), [32, 64, 64, 512], 6, 5
+    rng = np.random.default_rng(51)
+    agent = iDQN(0, obs, A, K, feats, "cnn", 3e-4, 0.99, 1, 1, 8, 4, 1.5e-4)
+    agent.params = O.init_params(rng, obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    explored = 0
+    for trial in range(40):
+        key = _prng.split(1000 + trial, 1)[0]
+        state = rng.integers(0, 256, obs).astype(np.float32 if trial % 2 else np.uint8)
+        eps = 0.5
+        u_key, a_key, kw_key = _prng.split(key, 3)
+        want_explore = bool(_prng.uniform(u_key) <= eps)
+        want_head = _prng.randint(kw_key, 0, K)
+        want = _prng.randint(a_key, 0, A) if want_explore else agent.best_action(agent.params, state, idx_params=want_head)
+        got, got_explore, got_head = agent._engine.select_action(state, key, A, eps)
+        assert (got, got_explore, got_head) == (want, want_explore, want_head), trial
+        assert select_action(agent.best_action, agent.params, state, key, A, lambda n: eps, 0) == want
+        explored += want_explore
+    assert 5 < explored < 35

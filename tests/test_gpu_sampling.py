@@ -334,3 +334,50 @@ def test_prioritized_sampler_with_an_all_zero_tree_falls_back_to_uniform():
         np.testing.assert_array_equal(p.sample(8), u.sample(8))
     p.update(np.asarray([7], np.int32), np.asarray([2.5]))
     assert (p.sample(16) == 7).all()
+
+
+def test_prioritized_replay_wired_to_the_learner_end_to_end():
+    """§8f N3: a prioritised buffer feeding the learner with the priorities written back after every step
+    (replay_buffer.py:232-237 + samplers.py:75-87 + sum_tree.py:18,32, which the reference ships but never connects):
+    new elements enter at max_recorded_priority, the step's per-sample |TD| (mean over the heads) goes into the tree on
+    the device, the next batch is sampled from the updated tree.  The reference-side oracle classes driven with the
+    SAME priorities (read back from the device) must produce the same keys every step and, at the end, bit-identical
+    tree nodes and max_recorded_priority."""
+    from idqn_b200.networks.idqn import iDQN
+    from idqn_b200.sample_collection import replay_buffer, samplers
+    from idqn_b200.sample_collection.replay_buffer import TransitionElement
+    from oracle.samplers import PrioritizedSamplerOracle
+    cap, K = 200, 2
+    rb = replay_buffer.ReplayBuffer(samplers.PrioritizedSamplingDistribution(seed=11, max_capacity=cap), batch_size=32,
+                                    max_capacity=cap, stack_size=4, update_horizon=1, gamma=0.99,
+                                    clipping=lambda x: np.clip(x, -1, 1))
+    oracle = PrioritizedSamplerOracle(seed=11, max_capacity=cap)
+    agent = iDQN(3, (84, 84, 4), 6, K, [32, 64, 64, 512], "cnn", 3e-4, 0.99, 1, 1, 8, 4, 1.5e-4)
+    r = np.random.default_rng(2)
+
+    def add(n):
+        for _ in range(n):
+            before = rb.add_count
+            term = r.random() < 0.02
+            rb.add(TransitionElement(r.integers(0, 256, (84, 84)).astype(np.uint8), int(r.integers(0, 6)),
+                                     float(r.integers(-1, 2)), bool(term), bool(term)))  # no priority: enters at the maximum
+            for key in range(before, rb.add_count):  # mirror ReplayBuffer.add (:207-213) on the oracle
+                oracle.add(key, priority=oracle.tree.max_recorded_priority)
+                if key + 1 > cap:
+                    oracle.remove(key - cap)
+
+    add(150)
+    for step in range(1, 13):
+        assert agent.update_online_params(step, rb) is None
+        keys = np.asarray(rb.last_keys)
+        np.testing.assert_array_equal(keys, oracle.sample(32), err_msg=f"sampled keys, step {step}")
+        rb.update_from_learner(agent._engine)
+        td = agent._engine.td_abs().astype(np.float64)
+        assert td.shape == (K, 32) and (td >= 0).all() and td.max() > 0
+        oracle.update(keys, (td[0] + td[1]) / K)
+        agent.update_target_params(step)
+        add(10)  # the buffer wraps (evictions + re-insertions at the running maximum) while the learner runs
+    s = rb._sampling_distribution
+    assert s._sum_tree._nodes.tobytes() == oracle.tree.nodes.tobytes()
+    assert s._sum_tree.max_recorded_priority == oracle.tree.max_recorded_priority
+    np.testing.assert_array_equal(np.asarray(s._index_to_key), np.asarray(oracle.index_to_key))

@@ -31,3 +31,12 @@ for name, st in (("float32 state", state), ("uint8 state", state.astype(np.uint8
     for i in range(n):
         agent._engine.best_action(0, i % K, st)
     print(f"  engine.best_action, {name}: {(time.perf_counter() - t0) / n * 1e6:.1f} us")
+
+# the whole acting decision (utils.py:8-15) in one call into the library: C threefry draws + graph-launched forward
+from idqn_b200.sample_collection.utils import select_action
+for eps in (0.0, 0.1, 1.0):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n):
+        select_action(agent.best_action, agent.params, st, _prng.as_key(i), A, lambda s: eps, 0)
+    print(f"  select_action (epsilon {eps}): {(time.perf_counter() - t0) / n * 1e6:.1f} us per environment step")
