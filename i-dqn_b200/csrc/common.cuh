@@ -179,6 +179,9 @@ struct idqn_handle {
   __nv_bfloat16 *in_hi, *in_lo;                      // [2][B*in_elems]  state, next_state
   __nv_bfloat16* ones;                               // {1,0 x7 | 0 x8}: bias-gradient row of the wgrad GEMMs
   unsigned long long planes_dirty[2];                // online / target planes stale: bit k = head k (bit 63: every head)
+  int fast_dense;                                    // the big Dense layer has NO maintained planes: arena range [d0_lo, d0_hi)
+  int64_t d0_lo, d0_hi;                              //   is skipped by every plane producer (refresh, target events, Adam)
+  unsigned long long dense0_valid[2];                // ... and rebuilt on demand for the generic kernels: bit k = head k valid
   __nv_bfloat16 *wpl_hi, *wpl_lo;                    // the allocation behind won_*/wtg_*: [2K][stride], online first
   // image-resident conv path (conv_img.cuh); img_on == 0 -> the generic kernels of gemm_tc.cuh run instead
   int img_on;

@@ -1,14 +1,18 @@
 // Weight-streaming tcgen05 kernels for the big Dense layer (Dense_0: 7744 x 512) at batch 32 (sm_100a).
 //
 // At batch 32 the layer is bound by reading its 15.9 MB kernel once per net: the weights are the M-side operand
-// (128 rows per tile), the batch sits on N.  A persistent CTA streams 64-deep K blocks of the weight planes
-// (hi, lo) and of the small batch operand through a TMA ring (SWIZZLE_128B, tma_core.cuh); per K = 16 step
+// (128 rows per tile), the batch sits on N.  The kernel reads the fp32 MASTER weights -- there are no bf16 copies of
+// this layer in HBM (they cost 79 MB of extra writes per K = 5 step in the wgrad+Adam kernel and doubled every target
+// event): a persistent CTA streams 64-deep K blocks of fp32 weights and of the small bf16 batch operand through a TMA
+// ring, four converter warps split every fp32 tile into bf16 hi/lo operand tiles IN SHARED MEMORY, written straight in
+// the SWIZZLE_128B layout tcgen05.mma expects, and per K = 16 step
 //     W_hi * [x_hi | x_lo]   (one MMA, N = 64: the batch planes sit next to each other in the stage)
 //   + W_lo * x_hi            (one MMA, N = 32)
-// accumulate in TMEM ("bf16x3" split, fp32-faithful); the epilogue adds the two column sets.
+// accumulate in TMEM ("bf16x3" split, fp32-faithful to 2^-17); the epilogue adds the two column sets.
 //   MODE 0  forward   y[b][o]  = relu(sum_i x[b][i] W[i][o] + bias[o])      A = W^T: MN-major, rows = i, M = o
 //           split-K over units; the partial tiles are summed in split order by the consumer (head_q_kernel)
 //   MODE 1  dgrad     dx[b][i] = relu'(x[b][i]) sum_o dy[b][o] W[i][o]       A = W:   K-major, rows = i = M, K = o
+// Warp roles: 0 = TMA producer, 1 = MMA issue, 2..5 = epilogue, 6..9 = fp32 -> bf16 hi/lo converters.
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -21,14 +25,22 @@ using img::tl_stamp;
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
-constexpr int NTHREADS = 192;  // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue
-constexpr int BKD = 64;        // K depth of a stage (128-byte rows)
+constexpr int NTHREADS = 320;  // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue, warps 6..9: converters
+constexpr int CONV_T0 = 192, CONV_THREADS = 128;
+constexpr int BKD = 64;        // K depth of a stage
 constexpr int NB = 32;         // batch columns
+constexpr uint32_t W_BYTES = 128 * BKD * 4;   // fp32 weight tile of a stage: 32 KB
+constexpr uint32_t B_BYTES = NB * BKD * 2;    // one plane of the batch tile: 4 KB
+constexpr uint32_t STAGE_BYTES = W_BYTES + 2 * B_BYTES;  // 40 KB
+constexpr uint32_t OP_PLANE = 128 * BKD * 2;  // one bf16 plane of the converted weight tile: 16 KB
+constexpr uint32_t OP_BYTES = 2 * OP_PLANE;   // hi + lo
+constexpr int N_OP = 2;                       // converted operand buffers
 
 struct Args {
   int n_units, tiles, splits, kb_per_unit;  // unit = (net, tile, split); kb_per_unit K blocks each
   int unit0;                                // first unit of this launch (best_action: the units of one net)
   int nets;
+  int heads;            // K: nets < heads read the online arena, the others the target arena (forward)
   int stages;
   // forward
   int I, O;
@@ -41,10 +53,10 @@ struct Args {
   const bf16* xmask_hi; // its bf16 hi plane (hi > 0 <=> x > 0)
   float* part;          // fwd: [nets*tiles][splits][32][128]
   int* tickets;         // fwd: [nets*tiles]
-  // dgrad planes destination: dyZ layout of the preceding conv layer (zP > 0) or plain
-  // L2 policy of the weight-plane loads: nets < keep_heads (online heads whose planes dense_wgrad_tma wrote evict_last)
-  // are kept, every other net's planes are streamed evict_first
+  // L2 policy of the weight loads: nets < keep_heads are kept (evict_last: the data gradient re-reads them ~20 us after the
+  // forward), every other net's weights are streamed evict_first
   int keep_heads;
+  // dgrad planes destination: dyZ layout of the preceding conv layer (zP > 0) or plain
   int zP, zW, zC, zOff;
   int64_t zRows, zstride;
   int debug;
@@ -52,21 +64,21 @@ struct Args {
 };
 
 struct Smem {
-  uint32_t a_bytes, b_bytes, stage_bytes, bar_off, total;
+  uint32_t op_off, bar_off, total;
 };
 __host__ __device__ inline Smem smem_layout(const Args& p) {
   Smem s;
-  s.a_bytes = 128 * BKD * 2;    // one plane of the weight tile: 16 KB
-  s.b_bytes = NB * BKD * 2;     // one plane of the batch tile: 4 KB
-  s.stage_bytes = 2 * s.a_bytes + 2 * s.b_bytes;
-  s.bar_off = p.stages * s.stage_bytes;
+  s.op_off = p.stages * STAGE_BYTES;
+  s.bar_off = s.op_off + N_OP * OP_BYTES;
   s.total = s.bar_off + 256 + 1024;
   return s;
 }
 
+__device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
-dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+dense_stream_kernel(const __grid_constant__ CUtensorMap mapW_on, const __grid_constant__ CUtensorMap mapW_tg,
                     const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                     const Args p) {
   extern __shared__ uint8_t smem_raw[];
@@ -74,18 +86,21 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const Smem L = smem_layout(p);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* full = bars;             // [stages]
-  uint64_t* empty = bars + 8;        // [stages]
+  uint64_t* full = bars;             // [stages]  TMA landed
+  uint64_t* empty = bars + 8;        // [stages]  count 2: converters have read the fp32 tile + MMAs have read the batch tile
   uint64_t* acc_full = bars + 16;    // [2]
   uint64_t* acc_empty = bars + 18;   // [2]
+  uint64_t* op_full = bars + 20;     // [N_OP]  converted operand written
+  uint64_t* op_empty = bars + 22;    // [N_OP]  MMAs reading it complete
   __shared__ uint32_t tmem_base_s;
 
   pdl_trigger();
   ktl_begin(p.tl_id);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < p.stages; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < p.stages; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 2);
     for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 4);
+    for (int i = 0; i < N_OP; ++i) mbar_init(&op_full[i], 1), mbar_init(&op_empty[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, 128);  // 2 accumulator buffers x 64 columns
@@ -103,26 +118,19 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ui) {
         const int uu = u + p.unit0;
         const int sp = uu % p.splits, nt = uu / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
+        const CUtensorMap* mapW = net < p.heads ? &mapW_on : &mapW_tg;
+        const int head = net < p.heads ? net : net - p.heads;
         for (int kb = 0; kb < p.kb_per_unit; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
           tl_stamp(p.debug, 2000 + ui * 16 + kb);
-          tma::expect_tx(&full[st], L.stage_bytes);
-          const uint32_t s0 = base + st * L.stage_bytes;
+          tma::expect_tx(&full[st], STAGE_BYTES);
+          const uint32_t s0 = base + st * STAGE_BYTES;
           const int k0 = (sp * p.kb_per_unit + kb) * BKD;
           const uint64_t pol = net < p.keep_heads ? tma::L2_EVICT_LAST : tma::L2_EVICT_FIRST;
-          if (MODE == 0) {
-            // A = W^T: two 64-wide o groups x 64 i rows per plane
-            for (int g = 0; g < 2; ++g) {
-              tma::load_3d_hint(s0 + g * 8192, &mapA_hi, &full[st], tile * 128 + g * 64, k0, net, pol);
-              tma::load_3d_hint(s0 + L.a_bytes + g * 8192, &mapA_lo, &full[st], tile * 128 + g * 64, k0, net, pol);
-            }
-          } else {
-            // A = W: 128 i rows x 64 o
-            tma::load_3d_hint(s0, &mapA_hi, &full[st], k0, tile * 128, net, pol);
-            tma::load_3d_hint(s0 + L.a_bytes, &mapA_lo, &full[st], k0, tile * 128, net, pol);
-          }
-          tma::load_3d(s0 + 2 * L.a_bytes, &mapB_hi, &full[st], k0, 0, net);
-          tma::load_3d(s0 + 2 * L.a_bytes + L.b_bytes, &mapB_lo, &full[st], k0, 0, net);
+          if (MODE == 0) tma::load_3d_hint(s0, mapW, &full[st], tile * 128, k0, head, pol);  // [64 i][128 o] fp32
+          else tma::load_3d_hint(s0, mapW, &full[st], k0, tile * 128, head, pol);            // [128 i][64 o] fp32
+          tma::load_3d(s0 + W_BYTES, &mapB_hi, &full[st], k0, 0, net);
+          tma::load_3d(s0 + W_BYTES + B_BYTES, &mapB_lo, &full[st], k0, 0, net);
           if (++st == p.stages) st = 0, ph ^= 1;
         }
       }
@@ -132,32 +140,75 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
       const uint32_t idesc2 = make_idesc_bf16(128, 2 * NB, MODE == 0, false);
       const uint32_t idesc1 = make_idesc_bf16(128, NB, MODE == 0, false);
       const uint32_t hi32 = tma::desc_hi32(1024, tma::LT_SW128);
-      const uint32_t astep = MODE == 0 ? 128u : 2u;  // K = 16: 16 rows of 128 B (MN-major) or 32 bytes (K-major)
-      int st = 0, ai = 0;
-      uint32_t ph = 0;
+      const uint32_t astep = MODE == 0 ? 128u : 2u;    // K = 16: 16 rows of 128 B (MN-major) or 32 bytes (K-major)
+      const uint32_t a_lbo = MODE == 0 ? 8192u : 16u;  // MN-major: second 64-wide o group; K-major: unused
+      int st = 0, ai = 0, ob = 0;
+      uint32_t oph = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ai) {
         const int ab = ai & 1;
         mbar_wait(&acc_empty[ab], ((ai >> 1) & 1) ^ 1);
         const uint32_t d = tmem + (uint32_t)ab * 2 * NB;
         for (int kb = 0; kb < p.kb_per_unit; ++kb) {
-          mbar_wait(&full[st], ph);
+          mbar_wait(&op_full[ob], oph);  // implies full[st]: the converters waited for the stage before writing
           tcgen05_after_sync();
           tl_stamp(p.debug, 3000 + ai * 32 + kb);
-          const uint32_t s0 = base + st * L.stage_bytes;
-          const uint32_t a_lbo = MODE == 0 ? 8192u : 16u;  // MN-major: second 64-wide o group; K-major: unused
-          const uint32_t ah = tma::desc_lo32(s0, a_lbo), al = tma::desc_lo32(s0 + L.a_bytes, a_lbo);
-          const uint32_t bh = tma::desc_lo32(s0 + 2 * L.a_bytes, 16);
+          const uint32_t a0 = base + L.op_off + ob * OP_BYTES;
+          const uint32_t ah = tma::desc_lo32(a0, a_lbo), al = tma::desc_lo32(a0 + OP_PLANE, a_lbo);
+          const uint32_t bh = tma::desc_lo32(base + st * STAGE_BYTES + W_BYTES, 16);
 #pragma unroll
           for (int j = 0; j < BKD / 16; ++j) {
             if (kb == 0 && j == 0) tma::mma_bf16_split<false>(d, ah, hi32, bh, hi32, idesc2);
             else tma::mma_bf16_split<true>(d, ah + j * astep, hi32, bh + 2 * j, hi32, idesc2);
             tma::mma_bf16_split<true>(d, al + j * astep, hi32, bh + 2 * j, hi32, idesc1);
           }
+          mma_commit(&op_empty[ob]);
           mma_commit(&empty[st]);
           tl_stamp(p.debug, 3000 + ai * 32 + 16 + kb);
-          if (++st == p.stages) st = 0, ph ^= 1;
+          if (++st == p.stages) st = 0;
+          if (++ob == N_OP) ob = 0, oph ^= 1;
         }
         mma_commit(&acc_full[ab]);
+      }
+    }
+  } else if (warp >= 6) {
+    // ===== converters: fp32 weight tile -> bf16 hi / lo operand tiles in the SWIZZLE_128B UMMA layout =====
+    // MODE 0: tile [64 rows i][128 o] (512-byte rows); operand = two 64-wide o groups (8 KB apart) of [64 rows i][64 o]
+    // MODE 1: tile [128 rows i][64 o] (256-byte rows); operand = [128 rows i][64 o]
+    // a thread converts 4 consecutive floats: one conflict-free LDS.128, one 8-byte store per plane (half a 16-byte chunk;
+    // chunk c of row r sits at c ^ (r & 7), the swizzle TMA would have applied)
+    const int ct = tid - CONV_T0;
+    constexpr int F4_PER_ROW = MODE == 0 ? 32 : 16;
+    int st = 0, ob = 0;
+    uint32_t ph = 0, oph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int kb = 0; kb < p.kb_per_unit; ++kb) {
+        mbar_wait(&full[st], ph);
+        mbar_wait(&op_empty[ob], oph ^ 1);
+        const float4* src = reinterpret_cast<const float4*>(smem + st * STAGE_BYTES);
+        uint8_t* dst = smem + L.op_off + ob * OP_BYTES;
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) v[it] = src[it * CONV_THREADS + ct];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int idx = it * CONV_THREADS + ct;
+          const int r = idx / F4_PER_ROW, c4 = idx % F4_PER_ROW;
+          uint32_t off;
+          if (MODE == 0) off = (uint32_t)(c4 >> 4) * 8192u + (uint32_t)r * 128u + ((uint32_t)(((c4 & 15) >> 1) ^ (r & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
+          else off = (uint32_t)r * 128u + ((uint32_t)((c4 >> 1) ^ (r & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
+          uint2 h2, l2;
+          split4(v[it], h2, l2);
+          *reinterpret_cast<uint2*>(dst + off) = h2;
+          *reinterpret_cast<uint2*>(dst + OP_PLANE + off) = l2;
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        conv_bar_sync();
+        if (ct == 0) {
+          tma::arrive(&op_full[ob]);
+          tma::arrive(&empty[st]);  // the fp32 tile has been read (the MMAs still own the batch tile of the stage)
+        }
+        if (++st == p.stages) st = 0, ph ^= 1;
+        if (++ob == N_OP) ob = 0, oph ^= 1;
       }
     }
   } else {

@@ -1,6 +1,7 @@
 // Weight gradient of the big Dense layer (Dense_0: 7744 x 512) fused with optax.adam (idqn.py:52,106-107 of the
 // reference), as a persistent TMA pipeline (sm_100a).  This is the HBM-bound kernel of the step: per parameter it
-// reads W, mu, nu (12 B) and writes W, mu, nu and the bf16 hi/lo planes of the new W (16 B); the gradient
+// reads W, mu, nu (12 B) and writes W, mu, nu (12 B) -- nothing else: the layer has no bf16 copies in HBM (its forward
+// and data-gradient kernels split the fp32 master in shared memory, dense_stream.cuh); the gradient
 //     dW[i][o] = sum_b x[b][i] dy[b][o]         (contraction over the batch only, K = 32)
 // is produced on the tensor core straight into TMEM and never goes to memory.
 //
@@ -11,8 +12,7 @@
 //   TMA loads (un-swizzled fp32 boxes {256 o, 8 i}, two per array) W, mu, nu + the [32 b][32 i] x planes   (warp 0)
 //   tcgen05.mma per column block: D^T[128 o][64] = dy_hi^T [x_hi | x_lo], D^T[:, 0:32] += dy_lo^T x_hi     (warp 1)
 //   epilogue, thread = (column o of one column block, 8 rows): g from TMEM, W/mu/nu from the stage (lanes =
-//   consecutive floats, conflict free), Adam in registers, results written back IN PLACE, planes stored from
-//   registers                                                                                        (warps 2..17)
+//   consecutive floats, conflict free), Adam in registers, results written back IN PLACE             (warps 2..17)
 //   TMA stores of the three updated tiles from the same stage; the stage returns to the producer when the bulk
 //   stores have read it (cp.async.bulk.wait_group.read).
 // Three stages of 52 KB; the dy^T operand of the whole head ([32 b][512 o] hi/lo, 64 KB) stays resident and is
@@ -47,11 +47,8 @@ struct Args {
   int I, O;
   const int32_t* count;
   float lr, b1, b2, eps;
-  bf16 *Wh, *Wl;              // weight planes, refreshed with the new W
   float* grad;                // optional: materialised gradient (IDQN_F_KEEP_GRADS)
   unsigned long long stream_policy;  // L2 policy of the W / mu / nu loads and stores
-  int keep_heads;             // planes of heads < keep_heads are written L2 evict_last: the next step's Dense_0 forward
-                              // and data gradient find them in L2; the other planes are evict_first
   int64_t stride, w_off;
   int tl_id;
 };
@@ -182,7 +179,6 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
         last_z = z;
         ac = adam_coef(p.b1, p.b2, p.lr, p.eps, p.count[z]);  // count already incremented for this step
       }
-      const uint64_t plane_policy = z < p.keep_heads ? tma::L2_EVICT_LAST : tma::L2_EVICT_FIRST;
       const int ab = ti & 1;
       mbar_wait(&acc_full[ab], (ti >> 1) & 1);
       mbar_wait(&full[st], ph);  // the stage's W / mu / nu tiles (async-proxy writes) are visible after this wait
@@ -229,11 +225,9 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
         }
         prev_st = st;
       }
+      if (p.grad) {  // the optional gradient after the barrier: off the stores' critical path
 #pragma unroll
-      for (int e = 0; e < TM; ++e) {  // planes (and the optional gradient) after the barrier: off the stores' critical path
-        const int64_t go = gb + (int64_t)e * p.O;
-        tma::st1_planes_hint(p.Wh + go, p.Wl + go, P[e], plane_policy);
-        if (p.grad) p.grad[go] = g[e];
+        for (int e = 0; e < TM; ++e) p.grad[gb + (int64_t)e * p.O] = g[e];
       }
       if (++st == STAGES) st = 0, ph ^= 1;
     }

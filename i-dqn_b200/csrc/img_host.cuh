@@ -12,7 +12,7 @@ struct ImgHost {
   img::S2dArgs s2d;
   // weight-streaming kernels of the big Dense layer (dense_stream.cuh)
   int dense_on;
-  alignas(64) CUtensorMap dmapWf[2], dmapWd[2], dmapX[2], dmapDy[2];
+  alignas(64) CUtensorMap fmapWf[2], fmapWd, dmapX[2], dmapDy[2];  // fp32 Dense_0 kernel: fwd boxes {128 o, 64 i} of the online / target arena, dgrad boxes {64 o, 128 i} (online)
   alignas(64) CUtensorMap wmapX[2], wmapP[3];  // dense_wgrad_tma.cuh: x planes {32 i, 32 b}; fp32 W / mu / nu {256 o, 8 i}
   int wgrad_tma_on;
   dense::Args dfwd, ddg;
@@ -301,13 +301,16 @@ static int img_setup(idqn_handle* h) {
     const int I = dense.g.Kd, O = dense.g.OC;
     H->dense_on = B == dense::NB && O % 128 == 0 && I % 64 == 0 && O % 64 == 0;
     if (H->dense_on) {
+      {
+        // the fp32 master kernel of every head: {O, I, K}; the streaming kernels split it into bf16 hi/lo in shared memory
+        const uint64_t wdims[3] = {(uint64_t)O, (uint64_t)I, (uint64_t)K};
+        const uint64_t wstr[2] = {(uint64_t)O * 4, (uint64_t)h->stride * 4};
+        const uint32_t boxf[3] = {128, 64, 1}, boxd[3] = {64, 128, 1};
+        REQUIRE(tma::encode_f32(&H->fmapWf[0], h->online + dense.w_off, 3, wdims, wstr, boxf), "tensor map dense W (fwd, online)");
+        REQUIRE(tma::encode_f32(&H->fmapWf[1], h->target + dense.w_off, 3, wdims, wstr, boxf), "tensor map dense W (fwd, target)");
+        REQUIRE(tma::encode_f32(&H->fmapWd, h->online + dense.w_off, 3, wdims, wstr, boxd), "tensor map dense W (dgrad)");
+      }
       for (int pl = 0; pl < 2; ++pl) {
-        const __nv_bfloat16* wb = (pl ? h->wpl_lo : h->wpl_hi) + dense.w_off;
-        const uint64_t wdims[3] = {(uint64_t)O, (uint64_t)I, (uint64_t)2 * K};
-        const uint64_t wstr[2] = {(uint64_t)O * 2, (uint64_t)h->stride * 2};
-        const uint32_t boxf[3] = {64, 64, 1}, boxd[3] = {64, 128, 1};
-        REQUIRE(tma::encode_bf16(&H->dmapWf[pl], wb, 3, wdims, wstr, boxf, 128), "tensor map dense W (fwd)");
-        REQUIRE(tma::encode_bf16(&H->dmapWd[pl], wb, 3, wdims, wstr, boxd, 128), "tensor map dense W (dgrad)");
         const __nv_bfloat16* xb = (pl ? h->act_lo : h->act_hi) + prev.act_off;
         const uint64_t xdims[3] = {(uint64_t)I, (uint64_t)B, (uint64_t)2 * K};
         const uint64_t xstr[2] = {(uint64_t)I * 2, (uint64_t)h->act_stride * 2};
@@ -349,7 +352,7 @@ static int img_setup(idqn_handle* h) {
           if (kblocks % sp == 0 && kblocks / sp >= 4) best = sp;
         a.splits = best, a.kb_per_unit = (kblocks + best - 1) / best;
         a.n_units = a.nets * a.tiles * a.splits;
-        a.stages = 5;
+        a.stages = 4, a.heads = K;
         a.I = I, a.O = O;
         a.w = NetPtr{h->online, h->target, h->stride, h->stride, K};
         a.b_off = dense.b_off;
@@ -364,7 +367,7 @@ static int img_setup(idqn_handle* h) {
         dense::Args& a = H->ddg;
         a.nets = K, a.tiles = (I + 127) / 128, a.splits = 1, a.kb_per_unit = O / 64;
         a.n_units = a.nets * a.tiles;
-        a.stages = 5;
+        a.stages = 4, a.heads = K;
         a.I = I, a.O = O;
         a.y = h->dact + prev.act_off, a.xact = nullptr, a.xmask_hi = h->act_hi + prev.act_off, a.ystride = h->act_stride;
         a.yh = h->dact_hi + prev.act_off, a.yl = h->dact_lo + prev.act_off;
@@ -373,6 +376,10 @@ static int img_setup(idqn_handle* h) {
     }
   }
   h->img_on = 1;
+  // Dense_0 lives in HBM as fp32 only (no bf16 planes are maintained for it) when both its streaming kernels and the
+  // TMA wgrad+Adam pipeline serve it; the generic kernels rebuild the planes they need on demand (ensure_dense0_planes)
+  h->fast_dense = H->dense_on && H->wgrad_tma_on && !(c.flags & (IDQN_F_OLD_WGRAD | IDQN_F_SIMT_ONLY));
+  h->d0_lo = dense.w_off, h->d0_hi = dense.b_off;
   return IDQN_OK;
 }
 
@@ -521,11 +528,11 @@ static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst, int unit0 = -1, 
   if (dgrad) {
     CK(img_set_smem(dense::dense_stream_kernel<1>, L.total));
     CK(launch_pdl(h->pdl, dense::dense_stream_kernel<1>, dim3(grid), dim3(dense::NTHREADS), L.total, h->stream,
-                  H->dmapWd[0], H->dmapWd[1], H->dmapDy[0], H->dmapDy[1], a));
+                  H->fmapWd, H->fmapWd, H->dmapDy[0], H->dmapDy[1], a));
   } else {
     CK(img_set_smem(dense::dense_stream_kernel<0>, L.total));
     CK(launch_pdl(h->pdl, dense::dense_stream_kernel<0>, dim3(grid), dim3(dense::NTHREADS), L.total, h->stream,
-                  H->dmapWf[0], H->dmapWf[1], H->dmapX[0], H->dmapX[1], a));
+                  H->fmapWf[0], H->fmapWf[1], H->dmapX[0], H->dmapX[1], a));
   }
   CK(cudaGetLastError());
   mark(h, dgrad ? "dense_dgrad_L%d" : "dense_fwd_L%d", li);
@@ -541,9 +548,7 @@ static int dense_wgrad_launch(idqn_handle* h, int tile0, int ntiles, bool keep_g
   a.I = l.g.Kd, a.O = l.g.OC;
   a.count = h->count;
   a.lr = h->cfg.learning_rate, a.b1 = 0.9f, a.b2 = 0.999f, a.eps = h->cfg.adam_eps;
-  a.Wh = h->won_hi, a.Wl = h->won_lo;
   a.grad = keep_grads ? h->grad : nullptr;
-  a.keep_heads = l2_keep_heads(h);
   // measured: 98.6 us with the default policy for the fp32 streams, 100.8 us with evict_first
   static const int sp = getenv("IDQN_L2_STREAM") ? atoi(getenv("IDQN_L2_STREAM")) : 0;
   a.stream_policy = sp == 0 ? tma::L2_EVICT_NORMAL : (sp == 2 ? tma::L2_EVICT_LAST : tma::L2_EVICT_FIRST);

@@ -515,11 +515,35 @@ static int launch_input_planes(idqn_handle* h, int x_u8, int nsamples, int two) 
   return IDQN_OK;
 }
 
-// weights uploaded from the host: rebuild their planes (outside the captured step)
+static int to_planes_range(idqn_handle* h, int w, int head, int64_t lo_f, int64_t hi_f) {
+  if (hi_f <= lo_f) return IDQN_OK;
+  const float* src = (w ? h->target : h->online) + (int64_t)head * h->stride;
+  __nv_bfloat16* ph = (w ? h->wtg_hi : h->won_hi) + (int64_t)head * h->stride;
+  __nv_bfloat16* pl = (w ? h->wtg_lo : h->won_lo) + (int64_t)head * h->stride;
+  const int64_t n8 = (hi_f - lo_f) / 8;
+  const int blocks = (int)std::min<int64_t>((n8 + 255) / 256, 8192);
+  tcg::to_planes_kernel<<<blocks, 256, 0, h->stream>>>(src + lo_f, ph + lo_f, pl + lo_f, n8);
+  CK(cudaGetLastError());
+  return IDQN_OK;
+}
+
+// weights uploaded from the host / received from a neighbour: rebuild their planes (outside the captured step).  With
+// fast_dense the big Dense layer keeps no planes: only the small ranges around it are converted.
 static int refresh_planes(idqn_handle* h) {
   for (int w = 0; w < 2; ++w) {
     unsigned long long dirty = h->planes_dirty[w];
     if (!dirty) continue;
+    if (h->fast_dense) {
+      for (int k = 0; k < h->K; ++k) {
+        if (!((dirty >> 63) || (k < 63 && ((dirty >> k) & 1ull)))) continue;
+        int rc = to_planes_range(h, w, k, 0, h->d0_lo);
+        if (!rc) rc = to_planes_range(h, w, k, h->d0_hi, h->stride);
+        if (rc) return rc;
+        if (k < 64) h->dense0_valid[w] &= ~(1ull << k);
+      }
+      h->planes_dirty[w] = 0;
+      continue;
+    }
     const float* src = w ? h->target : h->online;
     __nv_bfloat16 *hi = w ? h->wtg_hi : h->won_hi, *lo = w ? h->wtg_lo : h->won_lo;
     int first = 0, count = h->K;  // one launch over a contiguous run of heads
@@ -535,6 +559,38 @@ static int refresh_planes(idqn_handle* h) {
     tcg::to_planes_kernel<<<blocks, 256, 0, h->stream>>>(src + o, hi + o, lo + o, n8);
     CK(cudaGetLastError());
     h->planes_dirty[w] = 0;
+  }
+  return IDQN_OK;
+}
+
+// the generic tensor-core kernels (network.apply on arbitrary arenas / batch sizes) read planes of EVERY layer: rebuild the
+// big Dense layer's planes of one head from its fp32 master when they are not current
+static int ensure_dense0_planes(idqn_handle* h, int w, int head) {
+  if (!h->fast_dense) return IDQN_OK;
+  if (head < 64 && ((h->dense0_valid[w] >> head) & 1ull)) return IDQN_OK;
+  int rc = to_planes_range(h, w, head, h->d0_lo, h->d0_hi);
+  if (rc) return rc;
+  if (head < 64) h->dense0_valid[w] |= 1ull << head;
+  return IDQN_OK;
+}
+
+// copy the maintained planes of `nheads` heads (fp32 masters are copied by the caller): all of them, or with fast_dense
+// only the ranges around the big Dense layer
+static int copy_planes(idqn_handle* h, __nv_bfloat16* dhi, __nv_bfloat16* dlo, const __nv_bfloat16* shi,
+                       const __nv_bfloat16* slo, int nheads) {
+  if (nheads <= 0) return IDQN_OK;
+  if (!h->fast_dense) {
+    CK(cudaMemcpyAsync(dhi, shi, 2 * h->stride * nheads, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(dlo, slo, 2 * h->stride * nheads, cudaMemcpyDeviceToDevice, h->stream));
+    return IDQN_OK;
+  }
+  const size_t pitch = 2 * (size_t)h->stride;
+  const int64_t r0[2] = {0, h->d0_hi}, r1[2] = {h->d0_lo, h->stride};
+  for (int r = 0; r < 2; ++r) {
+    const size_t width = 2 * (size_t)(r1[r] - r0[r]);
+    if (!width) continue;
+    CK(cudaMemcpy2DAsync(dhi + r0[r], pitch, shi + r0[r], pitch, width, nheads, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(dlo + r0[r], pitch, slo + r0[r], pitch, width, nheads, cudaMemcpyDeviceToDevice, h->stream));
   }
   return IDQN_OK;
 }
@@ -1077,6 +1133,7 @@ int idqn_learn_step_resident(idqn_handle* h, int x_u8, float* losses_host) {
     int rc = refresh_planes(h);
     if (rc) return rc;
   }
+  h->dense0_valid[0] = 0;  // the step rewrites the big Dense layer's fp32 master only
   if (h->cfg.flags & IDQN_F_NO_GRAPH) {
     int rc = enqueue_learn_step(h, x_u8);
     if (rc) return rc;
@@ -1119,6 +1176,7 @@ extern "C" int idqn_profile_step(idqn_handle* h, int x_u8, int max_entries, floa
     if (rc) return rc;
   }
   h->prof_on = 1, h->prof_n = 0;
+  h->dense0_valid[0] = 0;
   CK(cudaEventRecord(h->prof_ev[0], h->stream));
   int rc = enqueue_learn_step(h, x_u8 ? 1 : 0);
   h->prof_on = 0;
@@ -1561,9 +1619,10 @@ extern "C" int idqn_shift_params(idqn_handle* h) {  // idqn.py:13-17
   for (int k = 0; k + 1 < h->K; ++k) {
     const int64_t d = (int64_t)k * h->stride, s = (int64_t)(k + 1) * h->stride;
     CK(cudaMemcpyAsync(h->online + d, h->online + s, sizeof(float) * h->stride, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->won_hi + d, h->won_hi + s, 2 * h->stride, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->won_lo + d, h->won_lo + s, 2 * h->stride, cudaMemcpyDeviceToDevice, h->stream));
+    int rc = copy_planes(h, h->won_hi + d, h->won_lo + d, h->won_hi + s, h->won_lo + s, 1);
+    if (rc) return rc;
   }
+  h->dense0_valid[0] = 0;
   return IDQN_OK;
 }
 extern "C" int idqn_sync_target(idqn_handle* h) {  // idqn.py:20-24
@@ -1576,8 +1635,9 @@ extern "C" int idqn_sync_target(idqn_handle* h) {  // idqn.py:20-24
   if (h->K > 1) {
     const int64_t n = h->stride * (h->K - 1);
     CK(cudaMemcpyAsync(h->target + h->stride, h->online, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->wtg_hi + h->stride, h->won_hi, 2 * n, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->wtg_lo + h->stride, h->won_lo, 2 * n, cudaMemcpyDeviceToDevice, h->stream));
+    int rc = copy_planes(h, h->wtg_hi + h->stride, h->wtg_lo + h->stride, h->won_hi, h->won_lo, h->K - 1);
+    if (rc) return rc;
+    h->dense0_valid[1] &= 1ull;  // only head 0 of the target arena keeps what it had
   }
   return IDQN_OK;
 }
@@ -1590,8 +1650,9 @@ extern "C" int idqn_copy_online_to_target(idqn_handle* h) {  // idqn.py:78, dqn.
   }
   const int64_t n = h->stride * h->K;
   CK(cudaMemcpyAsync(h->target, h->online, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->wtg_hi, h->won_hi, 2 * n, cudaMemcpyDeviceToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->wtg_lo, h->won_lo, 2 * n, cudaMemcpyDeviceToDevice, h->stream));
+  int rc = copy_planes(h, h->wtg_hi, h->wtg_lo, h->won_hi, h->won_lo, h->K);
+  if (rc) return rc;
+  h->dense0_valid[1] = 0;
   return IDQN_OK;
 }
 // planes of externally modified arenas (NCCL / peer copies into idqn_arena_ptr memory) must be rebuilt
@@ -1610,6 +1671,8 @@ extern "C" int idqn_mark_head_planes_dirty(idqn_handle* h, int which, int head) 
 // network.apply of one head on n <= B inputs (already staged in h->s), result in h->q[0..n*A)
 static int enqueue_apply(idqn_handle* h, int which, int head, int u8, int n) {
   int rc = refresh_planes(h);
+  if (rc) return rc;
+  rc = ensure_dense0_planes(h, which == IDQN_TARGET, head);
   if (rc) return rc;
   const bool tgt = which == IDQN_TARGET;
   const float* base = arena_of(h, which) + (int64_t)head * h->stride;
