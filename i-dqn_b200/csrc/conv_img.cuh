@@ -81,6 +81,7 @@ struct TapsArgs {
   int tiles, tpp, P, M_valid, W_valid;  // tiles per image, tiles per pass, pitch, valid rows, valid columns (ox < W_valid)
   // taps
   int n_taps, kt, tap_group;             // kt = K=16 steps per tap; taps per ring slot
+  int pair;                              // forward: the two M tiles of a unit share every weight group (one pass)
   int a_shift[MAX_TAPS];                 // rows
   int w_c1[MAX_TAPS], w_c2[MAX_TAPS];    // TMA coordinates (dims 1, 2) of the tap's weight box
   // B tile
@@ -121,6 +122,10 @@ __host__ __device__ inline TapsSmem taps_smem(const TapsArgs& p, int a_planes) {
 // Work is cut into jobs = (unit, M tile); every CTA takes a contiguous, balanced range of jobs, so consecutive jobs
 // reuse the image already resident in shared memory.  Weight tiles arrive in groups of `tap_group` taps per ring
 // slot (one barrier round trip per group).
+// PASSES.  With p.pair (forward layers whose image has two M tiles and whose accumulators fit twice: conv1, conv2) the two
+// tiles of a unit that fall into the CTA's job range are processed as ONE pass: every weight group is loaded once and
+// multiplied into both tiles' accumulators, which halves the weight traffic -- with two ring slots next to the two
+// resident images the MMA thread was waiting ~0.3 us for the next tap's weights after every ~0.5 us of MMAs.
 // Split products: the hi and lo weight tiles of a tap sit next to each other in the ring slot, so ONE MMA of width
 // 2N computes A_hi*[B_hi | B_lo] (the A tile, the larger operand, is read from shared memory once for both), a
 // second MMA of width N adds A_lo*B_hi into the first N columns; the epilogue sums the two column sets.
@@ -143,14 +148,18 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.N, N2 = 2 * p.N;   // accumulator columns per job: [0,N) hi*hi + lo*hi, [N,2N) hi*lo
+  const int N = p.N, N2 = 2 * p.N;   // accumulator columns per tile: [0,N) hi*hi + lo*hi, [N,2N) hi*lo
+  const bool pair = KIND == 0 && p.pair;
+  const int ACCW = (pair ? 2 : 1) * N2;  // columns of one accumulator buffer (one pass)
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * N2) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * ACCW) tmem_cols <<= 1;
   const int n_groups = (p.n_taps + p.tap_group - 1) / p.tap_group;
   const uint32_t tap_bytes = 2u * p.hpg * p.b_box_bytes;  // hi boxes then lo boxes of one tap
   // this CTA's jobs
   const int J = p.n_units * p.tiles;
   const int j0 = (int)((int64_t)blockIdx.x * J / gridDim.x), j1 = (int)((int64_t)(blockIdx.x + 1) * J / gridDim.x);
+  // tiles of the pass that starts at job j (pair mode: both tiles of a unit when both are ours)
+#define PASS_TILES(j) ((pair && ((j) & 1) == 0 && (j) + 1 < j1) ? 2 : 1)
 
   // rows of an M tile past the image read whatever follows in shared memory (the other buffer, the ring): they only
   // produce accumulator rows that the epilogue drops
@@ -196,18 +205,18 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===== weight producer: groups of taps per ring slot =====
+    // ===== weight producer: groups of taps per ring slot, once per pass =====
     if (elect_one()) {
-      int ws = 0;
+      int ws = 0, pi = 0;
       uint32_t wphase = 0;
-      for (int j = j0; j < j1; ++j) {
+      for (int j = j0; j < j1; j += PASS_TILES(j), ++pi) {
         const int u = p.unit0 + j / p.tiles;
         const int hg = u % p.n_hg, g = (u / p.n_hg) / p.imgs;
         const int net0 = g * p.nets_per_g + hg * p.hpg;
         const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
         for (int grp = 0; grp < n_groups; ++grp) {
           mbar_wait(&w_empty[ws], wphase ^ 1);
-          tl_stamp(p.debug, 2000 + (j - j0) * 16 + grp);
+          tl_stamp(p.debug, 2000 + pi * 16 + grp);
           const int tg0 = grp * p.tap_group, tg1 = min(p.n_taps, tg0 + p.tap_group);
           tma::expect_tx(&w_full[ws], 2u * nb * p.b_box_bytes * (tg1 - tg0));
           for (int t = tg0; t < tg1; ++t) {
@@ -235,28 +244,31 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       mbar_wait(&x_full[0], 0);  // waits of the very first group
       mbar_wait(&w_full[0], 0);
       tcgen05_after_sync();
-      for (int j = j0; j < j1; ++j, ++ai) {
+      for (int j = j0; j < j1; ++ai) {
+        const int npt = PASS_TILES(j);
         const int tile = j % p.tiles, xb = xi & 1, ab = ai & 1;
-        const bool last_job = j == j1 - 1, unit_ends = last_job || tile == p.tiles - 1;
+        const bool last_job = j + npt >= j1, unit_ends = last_job || tile + npt == p.tiles;
         const uint32_t a_hi = base + xb * L.a_buf_bytes, a_lo = a_hi + L.a_plane_bytes;
-        const uint32_t d = tmem + (uint32_t)ab * N2;
         for (int grp = 0; grp < n_groups; ++grp) {
           tl_stamp(p.debug, 3000 + ai * 32 + grp);
           const int tg0 = grp * p.tap_group, tg1 = min(p.n_taps, tg0 + p.tap_group);
-          for (int t = tg0; t < tg1; ++t) {
-            const uint32_t b_hi = base + L.ring_off + ws * L.slot_bytes + (uint32_t)(t - tg0) * tap_bytes;
-            // descriptor low words; offsets in 16-byte units.  B: N groups at LBO = box bytes (hi boxes then lo boxes)
-            uint32_t bh = tma::desc_lo32(b_hi, p.b_box_bytes);
-            uint32_t ah = tma::desc_lo32(a_hi, 16) + (uint32_t)p.a_shift[t] * 8 + (uint32_t)tile * 1024;
-            uint32_t al = tma::desc_lo32(a_lo, 16) + (uint32_t)p.a_shift[t] * 8 + (uint32_t)tile * 1024;
-            for (int j4 = 0; j4 < p.kt; j4 += 4) {
+          for (int ti = 0; ti < npt; ++ti) {
+            const uint32_t d = tmem + (uint32_t)ab * ACCW + (uint32_t)ti * N2;
+            for (int t = tg0; t < tg1; ++t) {
+              const uint32_t b_hi = base + L.ring_off + ws * L.slot_bytes + (uint32_t)(t - tg0) * tap_bytes;
+              // descriptor low words; offsets in 16-byte units.  B: N groups at LBO = box bytes (hi boxes then lo boxes)
+              uint32_t bh = tma::desc_lo32(b_hi, p.b_box_bytes);
+              uint32_t ah = tma::desc_lo32(a_hi, 16) + (uint32_t)p.a_shift[t] * 8 + (uint32_t)(tile + ti) * 1024;
+              uint32_t al = tma::desc_lo32(a_lo, 16) + (uint32_t)p.a_shift[t] * 8 + (uint32_t)(tile + ti) * 1024;
+              for (int j4 = 0; j4 < p.kt; j4 += 4) {
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                if (t == 0 && j4 == 0 && jj == 0) tma::mma_bf16_split<false>(d, ah, a_hi32, bh, b_hi32, idesc2);
-                else tma::mma_bf16_split<true>(d, ah + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc2);
-                if (A_PLANES == 2) tma::mma_bf16_split<true>(d, al + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc1);
+                for (int jj = 0; jj < 4; ++jj) {
+                  if (t == 0 && j4 == 0 && jj == 0) tma::mma_bf16_split<false>(d, ah, a_hi32, bh, b_hi32, idesc2);
+                  else tma::mma_bf16_split<true>(d, ah + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc2);
+                  if (A_PLANES == 2) tma::mma_bf16_split<true>(d, al + 2 * jj, a_hi32, bh + jj * bstep, b_hi32, idesc1);
+                }
+                ah += half16, al += half16, bh += 4 * bstep;
               }
-              ah += half16, al += half16, bh += 4 * bstep;
             }
           }
           mma_commit(&w_empty[ws]);
@@ -282,6 +294,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           }
         }
         if (unit_ends) ++xi;
+        j += npt;
       }
     }
     __syncwarp();
@@ -292,19 +305,21 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     const int r = q * 32 + lane;  // row inside the tile
     pdl_wait();
     int ai = 0;
-    for (int j = j0; j < j1; ++j, ++ai) {
-      const int tile = j % p.tiles, u = p.unit0 + j / p.tiles;
+    for (int j = j0; j < j1; ++ai) {
+      const int npt = PASS_TILES(j);
+      const int tile0 = j % p.tiles, u = p.unit0 + j / p.tiles;
       const int hg = u % p.n_hg, gi = u / p.n_hg, g = gi / p.imgs, im = gi - g * p.imgs;
       const int net0 = g * p.nets_per_g + hg * p.hpg;
       const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
       const int ab = ai & 1;
-      const int m = tile * 128 + r;
-      const int my = m / p.P, mx = m - my * p.P;
-      const bool rowok = m < p.M_valid && mx < p.W_valid;
-      // dgrad: the relu' masks of this thread's (at most two) 32-column chunks do not depend on the accumulator:
-      // they are requested BEFORE the wait for the MMAs, so their L2 latency hides behind the MMA phase of the job
+      j += npt;
+      // dgrad (never paired): the relu' masks of this thread's (at most two) 32-column chunks do not depend on the
+      // accumulator: they are requested BEFORE the wait for the MMAs, so their L2 latency hides behind the MMA phase
       uint4 xa[2][4];
       if (KIND == 1) {
+        const int m = tile0 * 128 + r;
+        const int my = m / p.P, mx = m - my * p.P;
+        const bool rowok = m < p.M_valid && mx < p.W_valid;
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           const int c0 = chalf * 32 + kk * 64;
@@ -316,11 +331,11 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           for (int k4 = 0; k4 < 4; ++k4) xa[kk][k4] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + mi) + k4);
         }
       }
-      // forward: likewise the bias of this thread's first chunk
+      // forward: likewise the bias of this thread's first chunk (the same for both tiles of a pass)
       float4 bb0[8];
       if (KIND == 0) {
         const int c0 = chalf * 32, hl = c0 / p.OC, oc = c0 - hl * p.OC;
-        const int net = net0 + ((rowok && hl < nb) ? hl : 0);
+        const int net = net0 + (hl < nb ? hl : 0);
         const float4* bias = reinterpret_cast<const float4*>(p.w.get<float>(net) + p.b_off + oc);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) bb0[k4] = __ldg(bias + k4);
@@ -328,7 +343,11 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       mbar_wait(&acc_full[ab], (ai >> 1) & 1);
       tcgen05_after_sync();
       if (warp == 3 && lane == 0) tl_stamp(p.debug, 1200 + 2 * ai);
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * N2;
+      for (int ti = 0; ti < npt; ++ti) {
+      const int m = (tile0 + ti) * 128 + r;
+      const int my = m / p.P, mx = m - my * p.P;
+      const bool rowok = m < p.M_valid && mx < p.W_valid;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * ACCW + (uint32_t)ti * N2;
       // per-row bases, computed once per tile
       int64_t orow = 0, prow = 0;
       if (KIND == 0) {
@@ -413,12 +432,14 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           }
         }
       }
+      }
       tcgen05_before_sync();
       __syncwarp();
       if (warp == 3 && lane == 0) tl_stamp(p.debug, 1201 + 2 * ai);
       if (lane == 0) tma::arrive(&acc_empty[ab]);
     }
   }
+#undef PASS_TILES
   tcgen05_before_sync();
   __syncthreads();
   ktl_end(p.tl_id);
@@ -464,6 +485,40 @@ __host__ __device__ inline WgradSmem wgrad_smem(const WgradArgs& p, int a_planes
   s.bar_off = s.ones_off + 2048;
   s.total = s.bar_off + 64 + 1024;
   return s;
+}
+
+// what the MMA-issuing thread of conv_wgrad_kernel needs per K = 16 step
+struct WgradIssue {
+  const uint32_t* xlo;   // per tile: descriptor low word of the X hi plane at k = 0
+  uint32_t x0, x1, x2;   // the first three of them by value (registers) for the specialised loops
+  uint32_t xpl16, x_hi32, zh0, z_hi32, tmem, N2, idesc2, idesc1, dbias, ones_lo, z_row_bytes;
+  bool has_bias;
+};
+// generic step (any tile count; ACC = false: the very first step of the CTA, which initialises the accumulators)
+template <int A_PLANES, bool ACC>
+__device__ __forceinline__ void wgrad_issue_step(const WgradIssue& w, int nt, int j) {
+  const uint32_t zh = w.zh0 + (uint32_t)j * w.z_row_bytes;  // 16 rows = row_bytes 16-byte units
+  const uint32_t xk = (uint32_t)j * 128;                    // 16 rows of 128 bytes
+  for (int t = 0; t < nt; ++t) {
+    const uint32_t d = w.tmem + (uint32_t)t * w.N2;
+    tma::mma_bf16_split<ACC>(d, w.xlo[t] + xk, w.x_hi32, zh, w.z_hi32, w.idesc2);
+    if (A_PLANES == 2) tma::mma_bf16_split<true>(d, w.xlo[t] + xk + w.xpl16, w.x_hi32, zh, w.z_hi32, w.idesc1);
+  }
+  if (w.has_bias) tma::mma_bf16_split<ACC>(w.dbias, w.ones_lo, w.x_hi32, zh, w.z_hi32, w.idesc2);  // ones^T [dy_hi | dy_lo]
+}
+// accumulating step with a compile-time tile count: straight-line code
+template <int A_PLANES, int NT>
+__device__ __forceinline__ void wgrad_issue_tiles(const WgradIssue& w, int j) {
+  const uint32_t zh = w.zh0 + (uint32_t)j * w.z_row_bytes;
+  const uint32_t xk = (uint32_t)j * 128;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const uint32_t d = w.tmem + (uint32_t)t * w.N2;
+    const uint32_t x = (t == 0 ? w.x0 : (t == 1 ? w.x1 : w.x2)) + xk;
+    tma::mma_bf16_split<true>(d, x, w.x_hi32, zh, w.z_hi32, w.idesc2);
+    if (A_PLANES == 2) tma::mma_bf16_split<true>(d, x + w.xpl16, w.x_hi32, zh, w.z_hi32, w.idesc1);
+  }
+  if (w.has_bias) tma::mma_bf16_split<true>(w.dbias, w.ones_lo, w.x_hi32, zh, w.z_hi32, w.idesc2);
 }
 
 // CTA = (head z, image range, tile split ts): tiles [ts*tps, (ts+1)*tps) of the layer, the last split also owns the
@@ -566,23 +621,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
         tcgen05_after_sync();
         if (elect_one()) {
         tl_stamp(p.debug, 3000 + 2 * i);
-        for (int j = 0; j < p.k16; ++j) {
-          const uint32_t zh = zh0 + (uint32_t)j * p.z_row_bytes;  // 16 rows = row_bytes 16-byte units
-          const uint32_t xk = (uint32_t)j * 128;                  // 16 rows of 128 bytes
-          const bool first = i == 0 && j == 0;
-#pragma unroll
-          for (int t = 0; t < MAX_TAPS; ++t) {
-            if (t < nt) {
-              const uint32_t d = tmem + (uint32_t)t * N2;
-              if (first) tma::mma_bf16_split<false>(d, xlo[t] + xk, x_hi32, zh, z_hi32, idesc2);
-              else tma::mma_bf16_split<true>(d, xlo[t] + xk, x_hi32, zh, z_hi32, idesc2);
-              if (A_PLANES == 2) tma::mma_bf16_split<true>(d, xlo[t] + xk + xpl16, x_hi32, zh, z_hi32, idesc1);
-            }
-          }
-          if (has_bias) {  // bias gradient: ones^T [dy_hi | dy_lo]
-            if (first) tma::mma_bf16_split<false>(dbias, ones_lo, x_hi32, zh, z_hi32, idesc2);
-            else tma::mma_bf16_split<true>(dbias, ones_lo, x_hi32, zh, z_hi32, idesc2);
-          }
+        // The issuing thread is ONE instruction stream: the loop is specialised on the number of accumulator tiles of this
+        // CTA (a 16-way predicated unroll cost ~300 cycles per K = 16 step for the one or two MMAs it contained -- 5x the
+        // tensor time, tools/mma_rate.cu) and the non-accumulating first step is peeled off.
+        const WgradIssue w{xlo, xlo[0], nt > 1 ? xlo[1] : 0u, nt > 2 ? xlo[2] : 0u, xpl16, x_hi32, zh0, z_hi32, tmem, (uint32_t)N2, idesc2, idesc1, dbias, ones_lo, p.z_row_bytes, has_bias};
+        int j = 0;
+        if (i == 0) {
+          wgrad_issue_step<A_PLANES, false>(w, nt, 0);
+          j = 1;
+        }
+        switch (nt) {
+          case 1: for (; j < p.k16; ++j) wgrad_issue_tiles<A_PLANES, 1>(w, j); break;
+          case 2: for (; j < p.k16; ++j) wgrad_issue_tiles<A_PLANES, 2>(w, j); break;
+          case 3: for (; j < p.k16; ++j) wgrad_issue_tiles<A_PLANES, 3>(w, j); break;
+          default: for (; j < p.k16; ++j) wgrad_issue_step<A_PLANES, true>(w, nt, j); break;
         }
         mma_commit(empty);
         tl_stamp(p.debug, 3001 + 2 * i);

@@ -159,6 +159,8 @@ static int img_setup(idqn_handle* h) {
       a.tiles = (a.M_valid + 127) / 128;
       a.N = a.hpg * g.OC;
       a.tpp = std::max(1, std::min(a.tiles, 128 / a.N));  // 2 buffers x tpp tiles x 2N columns <= 512
+      // two-tile passes (conv_taps_kernel): two accumulator buffers x two tiles x 2N columns must fit the 512 TMEM columns
+      a.pair = a.tiles == 2 && 8 * a.N <= 512 && !getenv("IDQN_NO_PAIR");
       a.n_taps = g.T * g.T, a.kt = g.C2 / 16;
       for (int ty = 0; ty < g.T; ++ty)
         for (int tx = 0; tx < g.T; ++tx) {
