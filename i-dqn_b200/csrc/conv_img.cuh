@@ -74,6 +74,7 @@ __device__ __forceinline__ int64_t plane_index(const PlaneDst& d, int net, int i
 
 struct TapsArgs {
   int n_units, imgs, nets_per_g, hpg, n_hg;
+  int n_units_total;  // units of the whole layer (n_units may be a window of them)
   int unit0;  // first unit of this launch (best_action runs a single (net, image) unit of the training layout)
   // A image
   int a_rows_alloc, a_chunks, a_chunk_rows, a_halves, a_buf_rows;
@@ -82,6 +83,8 @@ struct TapsArgs {
   // taps
   int n_taps, kt, tap_group;             // kt = K=16 steps per tap; taps per ring slot
   int pair;                              // forward: the two M tiles of a unit share every weight group (one pass)
+  int resident;                          // every tap group of a net has its own ring slot: weights are loaded when the net changes, not per pass
+  int hg_major;                          // unit order: head group slowest (consecutive units share their weights) instead of fastest
   int a_shift[MAX_TAPS];                 // rows
   int w_c1[MAX_TAPS], w_c2[MAX_TAPS];    // TMA coordinates (dims 1, 2) of the tap's weight box
   // B tile
@@ -103,6 +106,15 @@ struct TapsArgs {
 };
 
 __host__ __device__ inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+// unit -> (head group, (input, image) index)
+__device__ __forceinline__ void unit_decode(const TapsArgs& p, int u, int& hg, int& gi) {
+  if (p.hg_major) {
+    const int per = p.n_units_total / p.n_hg;
+    hg = u / per, gi = u - hg * per;
+  } else {
+    hg = u % p.n_hg, gi = u / p.n_hg;
+  }
+}
 
 struct TapsSmem {
   uint32_t a_plane_bytes, a_buf_bytes, ring_off, slot_bytes, bar_off, total;
@@ -190,7 +202,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         const int u = p.unit0 + j / p.tiles, xb = xi & 1;
         mbar_wait(&x_empty[xb], ((xi >> 1) & 1) ^ 1);
         tl_stamp(p.debug, 1000 + xi);
-        const int gi = u / p.n_hg;  // (g, img) linear
+        int hg_, gi;
+        unit_decode(p, u, hg_, gi);  // gi = (g, img) linear
         const uint32_t bytes = (uint32_t)A_PLANES * p.a_halves * p.a_chunks * p.a_chunk_rows * 128;
         tma::expect_tx(&x_full[xb], bytes);
         const int row0 = gi * p.a_rows_alloc;
@@ -207,14 +220,22 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   } else if (warp == 1) {
     // ===== weight producer: groups of taps per ring slot, once per pass =====
     if (elect_one()) {
-      int ws = 0, pi = 0;
+      int ws = 0, pi = 0, last_net0 = -1;
       uint32_t wphase = 0;
       for (int j = j0; j < j1; j += PASS_TILES(j), ++pi) {
         const int u = p.unit0 + j / p.tiles;
-        const int hg = u % p.n_hg, g = (u / p.n_hg) / p.imgs;
+        int hg, gi;
+        unit_decode(p, u, hg, gi);
+        const int g = gi / p.imgs;
         const int net0 = g * p.nets_per_g + hg * p.hpg;
         const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
+        if (p.resident) {
+          // slot = tap group; (re)loaded only when the net changes: the slots' barriers count reloads
+          if (net0 == last_net0) continue;
+          last_net0 = net0;
+        }
         for (int grp = 0; grp < n_groups; ++grp) {
+          if (p.resident) ws = grp;
           mbar_wait(&w_empty[ws], wphase ^ 1);
           tl_stamp(p.debug, 2000 + pi * 16 + grp);
           const int tg0 = grp * p.tap_group, tg1 = min(p.n_taps, tg0 + p.tap_group);
@@ -226,8 +247,9 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
               tma::load_4d(slot + (p.hpg + jn) * p.b_box_bytes, &mapW_lo, &w_full[ws], 0, p.w_c1[t], p.w_c2[t], net0 + jn);
             }
           }
-          if (++ws == p.ring) ws = 0, wphase ^= 1;
+          if (!p.resident && ++ws == p.ring) ws = 0, wphase ^= 1;
         }
+        if (p.resident) wphase ^= 1;
       }
     }
   } else if (warp == 2) {
@@ -239,17 +261,38 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       const uint32_t a_hi32 = tma::desc_hi32(1024, tma::LT_SW128), b_hi32 = tma::desc_hi32(8 * p.b_row_bytes, b_lt);
       const uint32_t half16 = (uint32_t)p.a_buf_rows * 8;                 // next 64-channel half of the image
       const uint32_t bstep = KIND == 0 ? p.b_row_bytes : 2u;              // K = 16 step of B: 16 rows (MN-major) or 32 bytes
-      int xi = 0, ws = 0, ai = 0;
+      int xi = 0, ws = 0, ai = 0, last_net0 = -1;
       uint32_t wphase = 0;
-      mbar_wait(&x_full[0], 0);  // waits of the very first group
-      mbar_wait(&w_full[0], 0);
-      tcgen05_after_sync();
+      bool new_unit = true;
       for (int j = j0; j < j1; ++ai) {
         const int npt = PASS_TILES(j);
         const int tile = j % p.tiles, xb = xi & 1, ab = ai & 1;
         const bool last_job = j + npt >= j1, unit_ends = last_job || tile + npt == p.tiles;
         const uint32_t a_hi = base + xb * L.a_buf_bytes, a_lo = a_hi + L.a_plane_bytes;
+        // resident weights: this pass waits for its slots only if its net differs from the previous pass's, and hands them
+        // back only if the next pass's does
+        bool reload = true, release = true;
+        if (p.resident) {
+          int hg, gi;
+          unit_decode(p, p.unit0 + j / p.tiles, hg, gi);
+          const int net0 = (gi / p.imgs) * p.nets_per_g + hg * p.hpg;
+          reload = net0 != last_net0;
+          last_net0 = net0;
+          if (!last_job) {
+            unit_decode(p, p.unit0 + (j + npt) / p.tiles, hg, gi);
+            release = (gi / p.imgs) * p.nets_per_g + hg * p.hpg != net0;
+          }
+          if (reload && ai > 0) wphase ^= 1;
+        }
         for (int grp = 0; grp < n_groups; ++grp) {
+          // waits of this group (the MMAs queued before keep draining meanwhile)
+          if (grp == 0) {
+            mbar_wait(&acc_empty[ab], ((ai >> 1) & 1) ^ 1);
+            if (new_unit) mbar_wait(&x_full[xb], (xi >> 1) & 1);
+          }
+          if (p.resident) ws = grp;
+          if (reload) mbar_wait(&w_full[ws], wphase);
+          tcgen05_after_sync();
           tl_stamp(p.debug, 3000 + ai * 32 + grp);
           const int tg0 = grp * p.tap_group, tg1 = min(p.n_taps, tg0 + p.tap_group);
           for (int ti = 0; ti < npt; ++ti) {
@@ -271,28 +314,16 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
               }
             }
           }
-          mma_commit(&w_empty[ws]);
+          if (release) mma_commit(&w_empty[ws]);
           const bool last_grp = grp == n_groups - 1;
           if (last_grp) {
             mma_commit(&acc_full[ab]);
             if (unit_ends) mma_commit(&x_empty[xb]);
           }
           tl_stamp(p.debug, 3000 + ai * 32 + 16 + grp);
-          if (++ws == p.ring) ws = 0, wphase ^= 1;
-          // waits of the NEXT group, issued while the MMAs just queued drain
-          if (!(last_grp && last_job)) {
-            if (last_grp) {
-              const int an = ai + 1;
-              mbar_wait(&acc_empty[an & 1], ((an >> 1) & 1) ^ 1);
-              if (unit_ends) {
-                const int xn = xi + 1;
-                mbar_wait(&x_full[xn & 1], (xn >> 1) & 1);
-              }
-            }
-            mbar_wait(&w_full[ws], wphase);
-            tcgen05_after_sync();
-          }
+          if (!p.resident && ++ws == p.ring) ws = 0, wphase ^= 1;
         }
+        new_unit = unit_ends;
         if (unit_ends) ++xi;
         j += npt;
       }
@@ -308,7 +339,9 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     for (int j = j0; j < j1; ++ai) {
       const int npt = PASS_TILES(j);
       const int tile0 = j % p.tiles, u = p.unit0 + j / p.tiles;
-      const int hg = u % p.n_hg, gi = u / p.n_hg, g = gi / p.imgs, im = gi - g * p.imgs;
+      int hg, gi;
+      unit_decode(p, u, hg, gi);
+      const int g = gi / p.imgs, im = gi - g * p.imgs;
       const int net0 = g * p.nets_per_g + hg * p.hpg;
       const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
       const int ab = ai & 1;

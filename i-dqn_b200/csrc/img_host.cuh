@@ -188,6 +188,16 @@ static int img_setup(idqn_handle* h) {
       if (2 * img::round_up(2 * a.hpg * a.b_box_bytes * a.tap_group, 1024) + abuf2 + 2048 > IMG_SMEM_MAX) a.tap_group = 1;
       const uint32_t slot = img::round_up(2 * a.hpg * a.b_box_bytes * a.tap_group, 1024);
       a.ring = (int)std::min<size_t>(a.tap_group > 1 ? 2 : 4, (IMG_SMEM_MAX - 2048 - abuf2) / slot);
+      a.n_units_total = a.n_units;
+      {  // resident weights: one slot per tap group if they all fit next to the two image buffers (conv0: 2 x 48 KB + 128 KB).
+         // Opt-in (IDQN_RESIDENT=1): measured 0.3014 vs 0.3016 ms per K = 5 step -- conv0 is bound by its epilogue (1.7 us per
+         // job against 0.9 us of MMAs), not by the weight loads
+        const int ng = (a.n_taps + a.tap_group - 1) / a.tap_group;
+        if (ng <= 8 && (size_t)ng * slot + abuf2 + 2048 <= IMG_SMEM_MAX && getenv("IDQN_RESIDENT")) {
+          a.resident = 1, a.ring = ng;
+          a.hg_major = 1;  // consecutive units of a CTA share their head group, hence their weights
+        }
+      }
       const int over = a.tiles * 128 + a.a_shift[a.n_taps - 1] - a.a_buf_rows;
       if (a.ring < 2 || over * 128 > (int)(a.ring * slot)) {
         idqn_set_error("internal: image path does not fit shared memory (fwd L%d)", li);
@@ -229,6 +239,11 @@ static int img_setup(idqn_handle* h) {
       if (2 * img::round_up(2 * a.b_box_bytes * a.tap_group, 1024) + abuf2 + 2048 > IMG_SMEM_MAX) a.tap_group = 1;
       const uint32_t slot = img::round_up(2 * a.b_box_bytes * a.tap_group, 1024);
       a.ring = (int)std::min<size_t>(a.tap_group > 1 ? 2 : 4, (IMG_SMEM_MAX - 2048 - abuf2) / slot);
+      a.n_units_total = a.n_units;
+      {  // resident weights (conv1 data gradient: 2 x 64 KB of weights + 88 KB of dyZ images)
+        const int ng = (a.n_taps + a.tap_group - 1) / a.tap_group;
+        if (ng <= 8 && (size_t)ng * slot + abuf2 + 2048 <= IMG_SMEM_MAX && getenv("IDQN_RESIDENT")) a.resident = 1, a.ring = ng;
+      }
       const int over = a.tiles * 128 + shmax - a.a_buf_rows;
       if (a.ring < 2 || over * 128 > (int)(a.ring * slot)) {
         idqn_set_error("internal: image path does not fit shared memory (dgrad L%d)", li);
@@ -466,7 +481,12 @@ static int img_launch_s2d(idqn_handle* h, int x_u8, bool single_state = false) {
 static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes, int unit0 = -1, int n_units = -1) {
   ImgHost* H = (ImgHost*)h->img_host;
   img::TapsArgs a = dgrad ? H->dg[li] : H->fwd[li];
-  if (unit0 >= 0) a.unit0 = unit0, a.n_units = n_units;
+  if (unit0 >= 0) {
+    // a window of the layer's units in the (input, image)-major order (best_action: one image): per-pass weight loads
+    a.unit0 = unit0, a.n_units = n_units;
+    a.hg_major = 0;
+    if (a.resident) a.resident = 0, a.ring = std::min(a.ring, 2);
+  }
   a.tl_id = unit0 >= 0 ? -1 : tl_next(h);
   a.debug = img_debug_on(dgrad ? "dgrad" : "fwd", li);
   const ImgLayerState& S = h->il[li];

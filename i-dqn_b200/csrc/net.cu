@@ -1212,12 +1212,20 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   REQUIRE(prop.major == 10, "libidqn_b200 is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
   h->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    // the learner's stream carries the critical chain of the step (forward, data gradients, the HBM-bound update); the side
+    // branch of the step graph (conv weight gradients) gets the LOWEST priority so that its CTAs only fill SMs the chain
+    // leaves idle (kernel nodes captured from a stream inherit its priority)
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const bool prio = !getenv("IDQN_NO_PRIORITY");
+    CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio ? hi : 0));
+    CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio ? lo : 0));
+  }
   h->sm_avail = h->sm_count;
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming));
-  CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_side_done, cudaEventDisableTiming));
   for (int i = 0; i < IDQN_IMG_LAYERS; ++i) CK(cudaEventCreateWithFlags(&h->ev_conv[i], cudaEventDisableTiming));
   if ((cfg->flags & IDQN_F_PARTITION) && !(cfg->flags & (IDQN_F_SIMT_ONLY | IDQN_F_NO_IMG)) && cfg->arch == IDQN_ARCH_CNN) {

@@ -477,3 +477,37 @@ def test_select_action_in_one_call_equals_the_host_mirror():
         assert select_action(agent.best_action, agent.params, state, key, A, lambda n: eps, 0) == want
         explored += want_explore
     assert 5 < explored < 35
+
+
+def test_training_loop_mirror_runs_the_reference_schedule():
+    """§8f N2: experiments/base/dqn.py:12-69 over the device agent -- acting (select_action in one call), replay add,
+    asynchronous learning steps with update_to_data = 2, D-syncs, T-updates with the device-side loss sums.  The learner
+    must have taken exactly the steps the reference's schedule prescribes and the loop's bookkeeping must add up."""
+    from idqn_b200.experiments.dqn import SyntheticAtari, linear_schedule, train
+    from idqn_b200.networks.idqn import iDQN
+    from idqn_b200.sample_collection.replay_buffer import ReplayBuffer
+    from idqn_b200.sample_collection.samplers import UniformSamplingDistribution
+    K, T, D, utd = 2, 16, 4, 2
+    agent = iDQN(5, (84, 84, 4), 6, K, [32, 64, 64, 512], "cnn", 3e-4, 0.99, 1, utd, T, D, 1.5e-4)
+    rb = ReplayBuffer(UniformSamplingDistribution(seed=1), batch_size=32, max_capacity=500, stack_size=4,
+                      clipping=lambda r: np.clip(r, -1, 1))
+    env = SyntheticAtari(episode_length=41)
+    logs = []
+
+    class Log:
+        def log(self, d):
+            logs.append(d)
+
+    p = dict(n_epochs=2, n_training_steps_per_epoch=100, n_initial_samples=60, epsilon_end=0.1, epsilon_duration=150,
+             horizon=1000, wandb=Log())
+    returns, lengths = train(7, p, agent, env, rb)
+    n_steps = sum(sum(l) for l in lengths)
+    assert n_steps == len(env.actions) >= 200 and all(0 <= a < 6 for a in env.actions)
+    want_learn = sum(1 for s in range(61, n_steps + 1) if s % utd == 0)
+    assert int(np.asarray(agent.optimizer_state[0].count)[0]) == want_learn
+    t_logs = [d for d in logs if "loss" in d]
+    assert len(t_logs) == sum(1 for s in range(61, n_steps + 1) if s % T == 0)
+    assert all(np.isfinite(d["loss"]) and d["loss"] > 0 for d in t_logs)
+    assert [d["epoch"] for d in logs if "epoch" in d] == [0, 1]
+    sched = linear_schedule(1.0, 0.1, 150)
+    assert sched(0) == 1.0 and abs(sched(75) - 0.55) < 1e-12 and sched(150) == sched(10 ** 6) == 0.1
