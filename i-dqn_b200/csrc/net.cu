@@ -1554,16 +1554,19 @@ extern "C" int idqn_submit_batch_host(idqn_handle* h, const void* s, const void*
     int32_t* a0 = h->action;
     float* r0 = h->reward;
     uint8_t* d0 = h->terminal;
+    float* l0 = h->loss;
     h->s = h->alt_s[slot], h->s2 = h->alt_s2[slot], h->action = h->alt_action[slot], h->reward = h->alt_reward[slot];
     h->terminal = h->alt_terminal[slot];
+    // the K losses of this step are written by the loss kernel STRAIGHT into the slot's entry of the pinned host ring
+    // (mapped memory, posted PCIe writes): no device-to-host copy operation sits between two steps on the compute stream
+    h->loss = h->h_loss_ring + (size_t)slot * h->K;
     h->graph_set = 1 + slot;
     rc = idqn_learn_step_resident(h, u8, nullptr);
     h->graph_set = 0;
-    h->s = s0, h->s2 = s20, h->action = a0, h->reward = r0, h->terminal = d0;
+    h->s = s0, h->s2 = s20, h->action = a0, h->reward = r0, h->terminal = d0, h->loss = l0;
   }
   if (rc) return rc;
   CK(cudaEventRecord(h->ev_consumed[slot], h->stream));
-  CK(cudaMemcpyAsync(h->h_loss_ring + (size_t)slot * h->K, h->loss, sizeof(float) * h->K, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev_done[slot], h->stream));
   *ticket = t;
   h->next_ticket = t + 1;
