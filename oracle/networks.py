@@ -3,7 +3,11 @@
 **Parity unpinned** – jax/flax/optax cannot be imported in this environment and the
 reference ships no golden vectors for ``learn_on_batch``; this file restates the
 documented semantics of the pinned third-party versions (flax 0.10.2, optax 0.2.4,
-``setup.cfg:18,27`` of the reference) at the reference's own call sites:
+``setup.cfg:18,27`` of the reference) at the reference's own call sites.  It is
+cross-checked against a second restatement that shares nothing with it
+(``oracle/networks_np.py``: NumPy float64, hand-derived backward) and against the
+committed float64 fixtures ``tests/golden/network_*.npz`` — which pins the two
+restatements and the CUDA path to each other, not to JAX:
 
 * ``slimdqn/networks/architectures/dqn.py:37-70``  -> :func:`apply`
 * ``slimdqn/networks/idqn.py:13-24``               -> :func:`shift_params`, :func:`sync_target_params`
