@@ -12,6 +12,7 @@ ARCH_FC, ARCH_CNN = 0, 1
 ONLINE, TARGET, MU, NU, GRAD = 0, 1, 2, 3, 4
 F_NO_GRAPH, F_SIMT_ONLY, F_KEEP_GRADS, F_NO_IMG, F_NO_PDL, F_PARTITION, F_OLD_WGRAD, F_NO_FORK, F_NO_DEFER, F_SLOW_APPLY = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 F_TIMELINE = 1024
+F_CHAIN = 2048
 MAX_FEATURES = 8
 MAX_ACTIONS = 32  # HEAD_MAXA of csrc/net.cu
 

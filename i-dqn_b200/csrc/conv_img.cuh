@@ -480,6 +480,312 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------
+// conv1 -> conv2 FORWARD CHAIN: one CTA takes a (net, image) unit through BOTH layers; the intermediate activation
+// (11 x 11 x 64, as the pitched 13 x 15 space-to-depth image conv2 reads) never leaves the SM: the epilogue of stage A
+// writes its bf16 hi / lo planes straight into shared memory in the SWIZZLE_128B layout the stage-B MMAs read.  One
+// launch and one pass over the units instead of two kernels with a grid-wide boundary between them (each paid ~3 us
+// to its first MMA, ~2 us for its last epilogue and the tail imbalance of the layer before).
+//   shared memory: image A (conv1 input, both planes, single buffer: it is free again while stage B runs) | image B
+//   (conv2 input, both planes) | weight ring shared by both stages (stage A: one tap per slot, stage B: two)
+//   TMEM: stage A accumulators (2 tiles x 2N) in columns [0, 256), stage B in [256, 512): the epilogue of B(u) overlaps
+//   the MMAs of A(u+1)
+// Both stages are two-tile passes of conv_taps_kernel<0, 2>; the arithmetic (tap order, split products, epilogue) is the
+// same instruction sequence, so the results are bit-identical to the two-kernel path.
+struct ChainArgs {
+  TapsArgs a, b;   // conv1 / conv2 forward as set up for conv_taps_kernel (geometry, taps, TMA coordinates, epilogue)
+  int bP, b_off_y, b_off_x;  // where stage A's output pixel (y, x) lands in image B: row (y + off_y) * bP + (x + off_x)
+  int b_tap_group;           // taps of stage B per ring slot
+  int ring;
+};
+struct ChainSmem {
+  uint32_t a_plane, a_bytes, b_plane, b_bytes, ring_off, slot_bytes, bar_off, total;
+};
+__host__ __device__ inline ChainSmem chain_smem(const ChainArgs& c) {
+  ChainSmem s;
+  s.a_plane = (uint32_t)c.a.a_halves * c.a.a_buf_rows * 128;
+  s.a_bytes = 2 * s.a_plane;
+  s.b_plane = round_up((uint32_t)c.b.a_halves * c.b.a_buf_rows * 128, 1024);
+  s.b_bytes = 2 * s.b_plane;
+  s.ring_off = s.a_bytes + s.b_bytes;
+  const uint32_t sa = 2 * c.a.b_box_bytes, sb = 2 * c.b.b_box_bytes * c.b_tap_group;
+  s.slot_bytes = round_up(sa > sb ? sa : sb, 1024);
+  s.bar_off = s.ring_off + c.ring * s.slot_bytes;
+  s.total = s.bar_off + 256 + 1024;
+  return s;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_chain_fwd_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                      const __grid_constant__ CUtensorMap mapWa_hi, const __grid_constant__ CUtensorMap mapWa_lo,
+                      const __grid_constant__ CUtensorMap mapWb_hi, const __grid_constant__ CUtensorMap mapWb_lo,
+                      const ChainArgs c) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const ChainSmem L = chain_smem(c);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* x_full = bars;          // image A landed
+  uint64_t* x_empty = bars + 1;     // stage-A MMAs reading it complete
+  uint64_t* bimg_full = bars + 2;   // image B written by the stage-A epilogue (8 warps)
+  uint64_t* bimg_empty = bars + 3;  // stage-B MMAs reading it complete
+  uint64_t* accA_full = bars + 4;
+  uint64_t* accA_empty = bars + 5;  // 8 warps
+  uint64_t* accB_full = bars + 6;
+  uint64_t* accB_empty = bars + 7;  // 8 warps
+  uint64_t* w_full = bars + 8;      // [ring]
+  uint64_t* w_empty = bars + 16;    // [ring]
+  __shared__ uint32_t tmem_base_s;
+
+  const TapsArgs& pa = c.a;
+  const TapsArgs& pb = c.b;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = pa.N, N2 = 2 * N;  // 64 / 128 in both stages
+  const int u0 = (int)((int64_t)blockIdx.x * pa.n_units / gridDim.x), u1 = (int)((int64_t)(blockIdx.x + 1) * pa.n_units / gridDim.x);
+  const int ngA = pa.n_taps, ngB = (pb.n_taps + c.b_tap_group - 1) / c.b_tap_group;
+
+  // image B: the zero border of the padded conv2 input is written once here and never touched again
+  for (uint32_t i = tid; i < L.b_bytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + L.a_bytes)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(x_full, 1), mbar_init(x_empty, 1), mbar_init(bimg_full, 8), mbar_init(bimg_empty, 1);
+    mbar_init(accA_full, 1), mbar_init(accA_empty, 8), mbar_init(accB_full, 1), mbar_init(accB_empty, 8);
+    for (int i = 0; i < c.ring; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  ktl_begin(pa.tl_id);
+
+  if (warp == 0) {
+    // ===== image A producer =====
+    if (elect_one()) {
+      pdl_wait();
+      for (int u = u0, i = 0; u < u1; ++u, ++i) {
+        mbar_wait(x_empty, (i & 1) ^ 1);
+        const uint32_t bytes = 2u * pa.a_halves * pa.a_chunks * pa.a_chunk_rows * 128;
+        tma::expect_tx(x_full, bytes);
+        const int row0 = u * pa.a_rows_alloc;  // unit = (net, image) linear, as the X2 planes of conv1 are laid out
+        for (int pl = 0; pl < 2; ++pl)
+          for (int hf = 0; hf < pa.a_halves; ++hf)
+            for (int ch = 0; ch < pa.a_chunks; ++ch)
+              tma::load_3d(base + pl * L.a_plane + (uint32_t)hf * pa.a_buf_rows * 128 + (uint32_t)ch * pa.a_chunk_rows * 128,
+                           pl ? &mapA_lo : &mapA_hi, x_full, 0, hf, row0 + ch * pa.a_chunk_rows);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== weight producer: stage A groups (one tap each), then stage B groups, through one ring =====
+    if (elect_one()) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      for (int u = u0; u < u1; ++u) {
+        const int net = u / pa.imgs;
+        for (int t = 0; t < ngA; ++t) {
+          mbar_wait(&w_empty[ws], wphase ^ 1);
+          tma::expect_tx(&w_full[ws], 2u * pa.b_box_bytes);
+          const uint32_t slot = base + L.ring_off + ws * L.slot_bytes;
+          tma::load_4d(slot, &mapWa_hi, &w_full[ws], 0, pa.w_c1[t], pa.w_c2[t], net);
+          tma::load_4d(slot + pa.b_box_bytes, &mapWa_lo, &w_full[ws], 0, pa.w_c1[t], pa.w_c2[t], net);
+          if (++ws == c.ring) ws = 0, wphase ^= 1;
+        }
+        for (int grp = 0; grp < ngB; ++grp) {
+          mbar_wait(&w_empty[ws], wphase ^ 1);
+          const int tg0 = grp * c.b_tap_group, tg1 = min(pb.n_taps, tg0 + c.b_tap_group);
+          tma::expect_tx(&w_full[ws], 2u * pb.b_box_bytes * (tg1 - tg0));
+          for (int t = tg0; t < tg1; ++t) {
+            const uint32_t slot = base + L.ring_off + ws * L.slot_bytes + (uint32_t)(t - tg0) * 2u * pb.b_box_bytes;
+            tma::load_4d(slot, &mapWb_hi, &w_full[ws], 0, pb.w_c1[t], pb.w_c2[t], net);
+            tma::load_4d(slot + pb.b_box_bytes, &mapWb_lo, &w_full[ws], 0, pb.w_c1[t], pb.w_c2[t], net);
+          }
+          if (++ws == c.ring) ws = 0, wphase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer =====
+    if (elect_one() && u0 < u1) {
+      const uint32_t idesc2 = make_idesc_bf16(128, N2, false, true), idesc1 = make_idesc_bf16(128, N, false, true);
+      const uint32_t a_hi32 = tma::desc_hi32(1024, tma::LT_SW128);
+      const uint32_t wa_hi32 = tma::desc_hi32(8 * pa.b_row_bytes, pa.b_row_bytes == 128 ? tma::LT_SW128 : tma::LT_SW64);
+      const uint32_t wb_hi32 = tma::desc_hi32(8 * pb.b_row_bytes, pb.b_row_bytes == 128 ? tma::LT_SW128 : tma::LT_SW64);
+      const uint32_t imgA_hi = base, imgA_lo = base + L.a_plane, imgB_hi = base + L.a_bytes, imgB_lo = imgB_hi + L.b_plane;
+      int ws = 0;
+      uint32_t wphase = 0;
+      for (int u = u0, i = 0; u < u1; ++u, ++i) {
+        // ---- stage A: conv1, both tiles per tap ----
+        mbar_wait(accA_empty, (i & 1) ^ 1);
+        mbar_wait(x_full, i & 1);
+        for (int t = 0; t < ngA; ++t) {
+          mbar_wait(&w_full[ws], wphase);
+          tcgen05_after_sync();
+          const uint32_t wslot = base + L.ring_off + ws * L.slot_bytes;
+          for (int ti = 0; ti < 2; ++ti) {
+            const uint32_t d = tmem + (uint32_t)ti * N2;
+            uint32_t bh = tma::desc_lo32(wslot, pa.b_box_bytes);
+            uint32_t ah = tma::desc_lo32(imgA_hi, 16) + (uint32_t)pa.a_shift[t] * 8 + (uint32_t)ti * 1024;
+            uint32_t al = tma::desc_lo32(imgA_lo, 16) + (uint32_t)pa.a_shift[t] * 8 + (uint32_t)ti * 1024;
+            for (int j4 = 0; j4 < pa.kt; j4 += 4) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                if (t == 0 && j4 == 0 && jj == 0) tma::mma_bf16_split<false>(d, ah, a_hi32, bh, wa_hi32, idesc2);
+                else tma::mma_bf16_split<true>(d, ah + 2 * jj, a_hi32, bh + jj * pa.b_row_bytes, wa_hi32, idesc2);
+                tma::mma_bf16_split<true>(d, al + 2 * jj, a_hi32, bh + jj * pa.b_row_bytes, wa_hi32, idesc1);
+              }
+              ah += (uint32_t)pa.a_buf_rows * 8, al += (uint32_t)pa.a_buf_rows * 8, bh += 4 * pa.b_row_bytes;
+            }
+          }
+          mma_commit(&w_empty[ws]);
+          if (++ws == c.ring) ws = 0, wphase ^= 1;
+        }
+        mma_commit(accA_full);
+        mma_commit(x_empty);
+        // ---- stage B: conv2 on the image the stage-A epilogue is writing into shared memory ----
+        mbar_wait(accB_empty, (i & 1) ^ 1);
+        mbar_wait(bimg_full, i & 1);
+        for (int grp = 0; grp < ngB; ++grp) {
+          mbar_wait(&w_full[ws], wphase);
+          tcgen05_after_sync();
+          const int tg0 = grp * c.b_tap_group, tg1 = min(pb.n_taps, tg0 + c.b_tap_group);
+          for (int ti = 0; ti < 2; ++ti) {
+            const uint32_t d = tmem + 256u + (uint32_t)ti * N2;
+            for (int t = tg0; t < tg1; ++t) {
+              const uint32_t wslot = base + L.ring_off + ws * L.slot_bytes + (uint32_t)(t - tg0) * 2u * pb.b_box_bytes;
+              uint32_t bh = tma::desc_lo32(wslot, pb.b_box_bytes);
+              uint32_t ah = tma::desc_lo32(imgB_hi, 16) + (uint32_t)pb.a_shift[t] * 8 + (uint32_t)ti * 1024;
+              uint32_t al = tma::desc_lo32(imgB_lo, 16) + (uint32_t)pb.a_shift[t] * 8 + (uint32_t)ti * 1024;
+              for (int j4 = 0; j4 < pb.kt; j4 += 4) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  if (t == 0 && j4 == 0 && jj == 0) tma::mma_bf16_split<false>(d, ah, a_hi32, bh, wb_hi32, idesc2);
+                  else tma::mma_bf16_split<true>(d, ah + 2 * jj, a_hi32, bh + jj * pb.b_row_bytes, wb_hi32, idesc2);
+                  tma::mma_bf16_split<true>(d, al + 2 * jj, a_hi32, bh + jj * pb.b_row_bytes, wb_hi32, idesc1);
+                }
+                ah += (uint32_t)pb.a_buf_rows * 8, al += (uint32_t)pb.a_buf_rows * 8, bh += 4 * pb.b_row_bytes;
+              }
+            }
+          }
+          mma_commit(&w_empty[ws]);
+          if (++ws == c.ring) ws = 0, wphase ^= 1;
+        }
+        mma_commit(accB_full);
+        mma_commit(bimg_empty);
+      }
+    }
+    __syncwarp();
+    pdl_trigger();
+  } else {
+    // ===== epilogue warps 3..10: TMEM lane quadrant = warp % 4, 32-column chunk (warp - 3) / 4 of the 64 channels =====
+    const int q = warp & 3, chalf = (warp - 3) >> 2;
+    const int r = q * 32 + lane;
+    const int c0 = chalf * 32;
+    uint8_t* imgB = smem + L.a_bytes;
+    pdl_wait();
+    for (int u = u0, i = 0; u < u1; ++u, ++i) {
+      const int net = u / pa.imgs, im = u - net * pa.imgs;
+      // biases of both layers for this thread's 32 channels: requested before the first accumulator wait
+      float4 ba[8], bb[8];
+      {
+        const float4* pa_bias = reinterpret_cast<const float4*>(pa.w.get<float>(net) + pa.b_off + c0);
+        const float4* pb_bias = reinterpret_cast<const float4*>(pb.w.get<float>(net) + pb.b_off + c0);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) ba[k4] = __ldg(pa_bias + k4), bb[k4] = __ldg(pb_bias + k4);
+      }
+      // ---- stage A epilogue: relu(conv1) -> bf16 hi / lo planes of image B in shared memory ----
+      mbar_wait(bimg_empty, (i & 1) ^ 1);  // the previous unit's stage-B MMAs have read image B
+      mbar_wait(accA_full, i & 1);
+      tcgen05_after_sync();
+      for (int ti = 0; ti < 2; ++ti) {
+        const int m = ti * 128 + r;
+        const int my = m / pa.P, mx = m - my * pa.P;
+        const bool rowok = m < pa.M_valid && mx < pa.W_valid;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ti * N2;
+        float v[32], v2[32];
+        tmem_ld16_nowait(taddr + c0, v);
+        tmem_ld16_nowait(taddr + c0 + 16, v + 16);
+        tmem_ld16_nowait(taddr + N + c0, v2);
+        tmem_ld16_nowait(taddr + N + c0 + 16, v2 + 16);
+        tmem_ld_wait();
+        if (!rowok) continue;
+        float o[32];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          o[4 * k4] = fmaxf(fmaf(v[4 * k4] + v2[4 * k4], pa.scale, ba[k4].x), 0.f);
+          o[4 * k4 + 1] = fmaxf(fmaf(v[4 * k4 + 1] + v2[4 * k4 + 1], pa.scale, ba[k4].y), 0.f);
+          o[4 * k4 + 2] = fmaxf(fmaf(v[4 * k4 + 2] + v2[4 * k4 + 2], pa.scale, ba[k4].z), 0.f);
+          o[4 * k4 + 3] = fmaxf(fmaf(v[4 * k4 + 3] + v2[4 * k4 + 3], pa.scale, ba[k4].w), 0.f);
+        }
+        // image B row of output pixel (my, mx); 128-byte rows, 16-byte chunk j stored at j ^ (row & 7) (SWIZZLE_128B)
+        const int row = (my + c.b_off_y) * c.bP + mx + c.b_off_x;
+        uint8_t* rowp = imgB + (uint32_t)row * 128;
+#pragma unroll
+        for (int h8 = 0; h8 < 4; ++h8) {
+          uint4 hh, ll;
+          split8(o + 8 * h8, hh, ll);
+          const uint32_t chunk = (uint32_t)(((c0 >> 3) + h8) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(rowp + chunk) = hh;
+          *reinterpret_cast<uint4*>(rowp + L.b_plane + chunk) = ll;
+          if (net < pa.w.zsplit) {
+            // online heads: the backward pass reads this activation (relu' mask of conv2's data gradient, operand of its
+            // weight gradient) from the conv2 input planes in global memory; target nets never need it again
+            const int64_t pi = (int64_t)net * pa.dst.net_stride + plane_index(pa.dst, 0, im, my, mx) + c0;
+            reinterpret_cast<uint4*>(pa.dst.hi + pi)[h8] = hh;
+            reinterpret_cast<uint4*>(pa.dst.lo + pi)[h8] = ll;
+          }
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes of image B -> visible to the stage-B MMAs
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        tma::arrive(accA_empty);
+        tma::arrive(bimg_full);
+      }
+      // ---- stage B epilogue: relu(conv2) -> planes of the Dense_0 input in global memory ----
+      mbar_wait(accB_full, i & 1);
+      tcgen05_after_sync();
+      for (int ti = 0; ti < 2; ++ti) {
+        const int m = ti * 128 + r;
+        const int my = m / pb.P, mx = m - my * pb.P;
+        const bool rowok = m < pb.M_valid && mx < pb.W_valid;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)ti * N2;
+        float v[32], v2[32];
+        tmem_ld16_nowait(taddr + c0, v);
+        tmem_ld16_nowait(taddr + c0 + 16, v + 16);
+        tmem_ld16_nowait(taddr + N + c0, v2);
+        tmem_ld16_nowait(taddr + N + c0 + 16, v2 + 16);
+        tmem_ld_wait();
+        if (!rowok) continue;
+        float o[32];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          o[4 * k4] = fmaxf(fmaf(v[4 * k4] + v2[4 * k4], pb.scale, bb[k4].x), 0.f);
+          o[4 * k4 + 1] = fmaxf(fmaf(v[4 * k4 + 1] + v2[4 * k4 + 1], pb.scale, bb[k4].y), 0.f);
+          o[4 * k4 + 2] = fmaxf(fmaf(v[4 * k4 + 2] + v2[4 * k4 + 2], pb.scale, bb[k4].z), 0.f);
+          o[4 * k4 + 3] = fmaxf(fmaf(v[4 * k4 + 3] + v2[4 * k4 + 3], pb.scale, bb[k4].w), 0.f);
+        }
+        const int64_t pi = (int64_t)net * pb.dst.net_stride + plane_index(pb.dst, 0, im, my, mx) + c0;
+#pragma unroll
+        for (int h8 = 0; h8 < 4; ++h8) {
+          uint4 hh, ll;
+          split8(o + 8 * h8, hh, ll);
+          reinterpret_cast<uint4*>(pb.dst.hi + pi)[h8] = hh;
+          reinterpret_cast<uint4*>(pb.dst.lo + pi)[h8] = ll;
+        }
+      }
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) tma::arrive(accB_empty);
+    }
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  ktl_end(pa.tl_id);
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // weight gradient.  CTA = (head z, image range); accumulators of all M tiles live in TMEM across the images.
 struct WgradArgs {
   int heads, groups, imgs;          // grid = heads * groups * tsplit; CTA handles images [gidx*ipg, min(imgs, +ipg))

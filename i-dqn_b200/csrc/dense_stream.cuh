@@ -112,15 +112,32 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapW_on, const __grid_co
 
   if (warp == 0) {
     if (elect_one()) {
-      pdl_wait();
-      int st = 0, ui = 0;
+      // The weights do not depend on the kernels before this one in the step (only the batch operand does): the weight
+      // boxes of the first `stages` K blocks are requested BEFORE griddepcontrol.wait, i.e. while the preceding kernel
+      // (conv2 / the loss kernels) is still running -- the HBM stream starts a few microseconds early.
+      int st = 0, ui = 0, blk = 0;
       uint32_t ph = 0;
+      bool waited = false;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ui) {
         const int uu = u + p.unit0;
         const int sp = uu % p.splits, nt = uu / p.splits, tile = nt % p.tiles, net = nt / p.tiles;
         const CUtensorMap* mapW = net < p.heads ? &mapW_on : &mapW_tg;
         const int head = net < p.heads ? net : net - p.heads;
-        for (int kb = 0; kb < p.kb_per_unit; ++kb) {
+        for (int kb = 0; kb < p.kb_per_unit; ++kb, ++blk) {
+          if (!waited && blk >= p.stages) {
+            // every stage holds its weight tile: now the batch operands of those stages, then the ordinary pipeline
+            pdl_wait();
+            waited = true;
+            int u2 = blockIdx.x, kb2 = 0;
+            for (int b2 = 0; b2 < blk; ++b2) {
+              const int uu2 = u2 + p.unit0, sp2 = uu2 % p.splits, net2 = (uu2 / p.splits) / p.tiles;
+              const int k02 = (sp2 * p.kb_per_unit + kb2) * BKD;
+              const uint32_t s2 = base + b2 * STAGE_BYTES;
+              tma::load_3d(s2 + W_BYTES, &mapB_hi, &full[b2], k02, 0, net2);
+              tma::load_3d(s2 + W_BYTES + B_BYTES, &mapB_lo, &full[b2], k02, 0, net2);
+              if (++kb2 == p.kb_per_unit) kb2 = 0, u2 += gridDim.x;
+            }
+          }
           mbar_wait(&empty[st], ph ^ 1);
           tl_stamp(p.debug, 2000 + ui * 16 + kb);
           tma::expect_tx(&full[st], STAGE_BYTES);
@@ -129,9 +146,23 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapW_on, const __grid_co
           const uint64_t pol = net < p.keep_heads ? tma::L2_EVICT_LAST : tma::L2_EVICT_FIRST;
           if (MODE == 0) tma::load_3d_hint(s0, mapW, &full[st], tile * 128, k0, head, pol);  // [64 i][128 o] fp32
           else tma::load_3d_hint(s0, mapW, &full[st], k0, tile * 128, head, pol);            // [128 i][64 o] fp32
-          tma::load_3d(s0 + W_BYTES, &mapB_hi, &full[st], k0, 0, net);
-          tma::load_3d(s0 + W_BYTES + B_BYTES, &mapB_lo, &full[st], k0, 0, net);
+          if (waited) {
+            tma::load_3d(s0 + W_BYTES, &mapB_hi, &full[st], k0, 0, net);
+            tma::load_3d(s0 + W_BYTES + B_BYTES, &mapB_lo, &full[st], k0, 0, net);
+          }
           if (++st == p.stages) st = 0, ph ^= 1;
+        }
+      }
+      if (!waited) {  // fewer K blocks than stages in this CTA: the batch operands of all of them
+        pdl_wait();
+        int u2 = blockIdx.x, kb2 = 0;
+        for (int b2 = 0; b2 < blk; ++b2) {
+          const int uu2 = u2 + p.unit0, sp2 = uu2 % p.splits, net2 = (uu2 / p.splits) / p.tiles;
+          const int k02 = (sp2 * p.kb_per_unit + kb2) * BKD;
+          const uint32_t s2 = base + b2 * STAGE_BYTES;
+          tma::load_3d(s2 + W_BYTES, &mapB_hi, &full[b2], k02, 0, net2);
+          tma::load_3d(s2 + W_BYTES + B_BYTES, &mapB_lo, &full[b2], k02, 0, net2);
+          if (++kb2 == p.kb_per_unit) kb2 = 0, u2 += gridDim.x;
         }
       }
     }

@@ -10,6 +10,8 @@ struct ImgHost {
   img::TapsArgs fwd[IDQN_IMG_LAYERS], dg[IDQN_IMG_LAYERS];
   img::WgradArgs wg[IDQN_IMG_LAYERS];
   img::S2dArgs s2d;
+  img::ChainArgs chain;   // conv1 -> conv2 forward in one kernel (conv_chain_fwd_kernel)
+  int chain_on;
   // weight-streaming kernels of the big Dense layer (dense_stream.cuh)
   int dense_on;
   alignas(64) CUtensorMap fmapWf[2], fmapWd, dmapX[2], dmapDy[2];  // fp32 Dense_0 kernel: fwd boxes {128 o, 64 i} of the online / target arena, dgrad boxes {64 o, 128 i} (online)
@@ -301,6 +303,22 @@ static int img_setup(idqn_handle* h) {
       a.part = h->wpart, a.span = h->wspan, a.w_off = l.w_off, a.b_off = l.b_off;
     }
   }
+  // ---- conv1 -> conv2 forward chain (conv_chain_fwd_kernel): both layers two-tile, 64 output channels, 128-byte weight rows ----
+  {
+    const img::TapsArgs &a = H->fwd[1], &b = H->fwd[2];
+    img::ChainArgs& c = H->chain;
+    c.a = a, c.b = b;
+    const img::Geom& n = H->g[2];
+    c.bP = n.P, c.b_off_y = n.ph, c.b_off_x = n.pw;
+    c.b_tap_group = std::max(1, (int)((2 * a.b_box_bytes) / (2 * b.b_box_bytes)));  // as many conv2 taps as fill a conv1 slot
+    c.ring = 2;
+    const img::ChainSmem L = img::chain_smem(c);
+    H->chain_on = IDQN_IMG_LAYERS == 3 && a.tiles == 2 && b.tiles == 2 && a.N == 64 && b.N == 64 && a.hpg == 1 && b.hpg == 1 &&
+                  a.n_units == b.n_units && n.s == 1 && b.a_halves == 1 && a.kt % 4 == 0 && b.kt % 4 == 0 &&
+                  (a.n_taps + (b.n_taps + c.b_tap_group - 1) / c.b_tap_group) >= c.ring && L.total <= IMG_SMEM_OPTIN &&
+                  // an M tile may read rows past its image: they must stay inside the allocation
+                  (uint32_t)(256 + b.a_shift[b.n_taps - 1]) * 128 <= L.b_bytes + c.ring * L.slot_bytes;
+  }
   // ---- input space-to-depth ----
   {
     const img::Geom& g = H->g[0];
@@ -505,6 +523,22 @@ static int img_launch_taps(idqn_handle* h, int li, bool dgrad, int a_planes, int
 #undef IMG_TAPS_LAUNCH
   CK(cudaGetLastError());
   mark(h, dgrad ? "img_dgrad_L%d" : "img_fwd_L%d", li);
+  return IDQN_OK;
+}
+
+// conv1 + conv2 forward of every net as one launch
+static int img_launch_chain_fwd(idqn_handle* h) {
+  ImgHost* H = (ImgHost*)h->img_host;
+  img::ChainArgs c = H->chain;
+  c.a.tl_id = tl_next(h);
+  const img::ChainSmem L = img::chain_smem(c);
+  const int per = (c.a.n_units + h->sm_avail - 1) / h->sm_avail;  // units of the busiest CTA
+  const int grid = (c.a.n_units + per - 1) / per;                  // the fewest CTAs with that maximum
+  CK(img_set_smem(img::conv_chain_fwd_kernel, L.total));
+  CK(launch_pdl(h->pdl, img::conv_chain_fwd_kernel, dim3(grid), dim3(img::NTHREADS), L.total, h->stream, h->il[1].mapX[0],
+                h->il[1].mapX[1], h->il[1].mapW[0], h->il[1].mapW[1], h->il[2].mapW[0], h->il[2].mapW[1], c));
+  CK(cudaGetLastError());
+  mark(h, "img_fwd_chain_L%d", 1);
   return IDQN_OK;
 }
 

@@ -941,8 +941,17 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   if (use_img) {
     int rc = img_launch_s2d(h, x_u8);
     if (rc) return rc;
+    // opt-in (IDQN_F_CHAIN): measured 49.5 us for the chain against 26 + 25 us for the two launches at K = 5 (0.3025 vs
+    // 0.3005 ms per step) and 18.8 vs 19.5 us at K = 1: a (net, image) unit is then ONE serial MMA stream of both layers on
+    // one SM (320 units on 107 CTAs at K = 5), whereas the two launches split every unit's M tiles over two CTAs
+    const bool chain = ((ImgHost*)h->img_host)->chain_on && (h->cfg.flags & IDQN_F_CHAIN);
     for (int li = 0; li < n_img; ++li) {
-      rc = img_launch_taps(h, li, false, li == 0 ? 1 : 2);
+      if (chain && li == 1) {
+        rc = img_launch_chain_fwd(h);  // conv1 and conv2 of a (net, image) in one CTA, the intermediate image in shared memory
+        li = 2;
+      } else {
+        rc = img_launch_taps(h, li, false, li == 0 ? 1 : 2);
+      }
       if (rc) return rc;
     }
   } else if (in_planes && !dry) {
@@ -1457,6 +1466,8 @@ extern "C" int idqn_download_activation(idqn_handle* h, int net, int layer, floa
   REQUIRE(n >= 0 && n <= h->layers[layer].act_size, "too many elements");
   CK(cudaSetDevice(h->cfg.device));
   if (h->img_on && h->img_last && layer < IDQN_IMG_LAYERS) {  // the image path keeps conv activations as planes
+    REQUIRE(!(layer == 1 && net >= h->K && ((ImgHost*)h->img_host)->chain_on && (h->cfg.flags & IDQN_F_CHAIN)),
+            "the conv1 activation of a target net is not materialised by the forward chain (IDQN_F_CHAIN)");
     int rc = img_rebuild_activation(h, net, layer);
     if (rc) return rc;
   }

@@ -69,6 +69,7 @@ typedef struct idqn_config {
 #define IDQN_F_SLOW_APPLY 512 /* best_action through the generic batch-1 kernels instead of the step's own kernels */
 #define IDQN_F_NO_DEFER 256 /* Dense_0 wgrad+Adam right after its data gradient instead of at the end of the backward pass */
 #define IDQN_F_NO_FORK 128  /* keep the conv weight-gradient kernels on the main stream (no second graph branch) */
+#define IDQN_F_CHAIN 2048 /* conv1 and conv2 forward as ONE kernel (conv_chain_fwd_kernel: a (net, image) unit goes through both layers in one CTA, the intermediate image stays in shared memory).  Bit-identical; measured not faster than the two launches: off by default */
 #define IDQN_F_TIMELINE 1024 /* kernels stamp the global timer at first-CTA start / last-CTA end: idqn_kernel_timeline reads the true in-graph schedule */
 #define IDQN_F_OLD_WGRAD 64 /* Dense_0 wgrad+Adam on the generic tcgen05 kernel (Adam in its epilogue) instead of the TMA pipeline */
 

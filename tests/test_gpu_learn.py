@@ -511,3 +511,27 @@ def test_training_loop_mirror_runs_the_reference_schedule():
     assert [d["epoch"] for d in logs if "epoch" in d] == [0, 1]
     sched = linear_schedule(1.0, 0.1, 150)
     assert sched(0) == 1.0 and abs(sched(75) - 0.55) < 1e-12 and sched(150) == sched(10 ** 6) == 0.1
+
+
+def test_forward_chain_is_bit_identical_to_the_two_kernel_path():
+    """conv1 -> conv2 in one kernel (IDQN_F_CHAIN: the intermediate image in shared memory) issues the same MMAs in the same
+    order as the two conv_taps launches: losses and every arena stay bit-identical over 5 steps with a D-sync."""
+    from idqn_b200 import _lib as L
+    from idqn_b200.networks.idqn import iDQN
+    obs, feats, A, K, B = (84, 84, 4), [32, 64, 64, 512], 6, 3, 32
+    rng = np.random.default_rng(61)
+    params = O.init_params(rng, obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    target = O.init_params(np.random.default_rng(1061), obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    batches = [make_batch(rng, B, obs, A, True) for _ in range(5)]
+    runs = []
+    for flags in (0, L.F_CHAIN):
+        agent = iDQN(0, obs, A, K, feats, "cnn", 3e-4, 0.99, 1, 1, 8, 4, 1.5e-4, flags=flags)
+        agent.params, agent.target_params = params, target
+        losses = []
+        for step, b in enumerate(batches, start=1):
+            losses.append(agent._engine.learn_host(b, want_losses=True))
+            agent.update_target_params(step)
+        runs.append((np.stack(losses), [agent._engine.download_arena(w) for w in (L.ONLINE, L.TARGET, L.MU, L.NU)]))
+    np.testing.assert_array_equal(runs[0][0], runs[1][0])
+    for a, b in zip(runs[0][1], runs[1][1]):
+        np.testing.assert_array_equal(a, b)
