@@ -131,6 +131,7 @@ struct Layer {
 // X2 (input of the layer), zero-embedded output-gradient planes dyZ, and the TMA tensor maps over them
 struct ImgLayerState {
   alignas(64) CUtensorMap mapX[2], mapW[2], mapZ[2];  // hi, lo
+  alignas(64) CUtensorMap mapXw[2], mapZw[2];         // the same X2 / dyZ planes with the part boxes of conv_wgrad_kernel
   __nv_bfloat16 *x2_hi, *x2_lo;   // [nets][B][XRa][C2]  (layer 0: nets = 2 inputs; else 2K nets)
   __nv_bfloat16 *dz_hi, *dz_lo;   // [K][B][ZRa][OC]
   int64_t x2_net_stride, dz_net_stride;  // elements

@@ -798,6 +798,10 @@ struct WgradArgs {
   uint32_t z_row_bytes;             // 128 (OC = 64) or 64 (OC = 32)
   int z_start;                      // (T-1)(P+1): row of dyZ that pairs with X2 row 0
   int k16;                          // K = 16 steps per image (ceil(OH*P / 16))
+  // PARTS: an image is streamed as n_parts consecutive ranges [pj[i], pj[i+1]) of its K = 16 steps through TWO buffers
+  // (part i+1 loads while part i multiplies; the step order -- hence every rounding -- is that of one whole image).  The
+  // x_* / z_* box fields above then describe the box of ONE part: X rows [16 pj, 16 pj + x_buf_rows), dyZ rows from z_start + 16 pj
+  int n_parts, pj[4];
   // M tiles: tile i covers two 64-row groups; group 0 at row shift sh0[i] (+ half h0[i]), group 1 at sh1 / h1
   int n_tiles;
   int sh0[MAX_TAPS], sh1[MAX_TAPS], hf0[MAX_TAPS], hf1[MAX_TAPS];
@@ -812,7 +816,7 @@ struct WgradArgs {
   int tl_id;
 };
 struct WgradSmem {
-  uint32_t x_plane_bytes, x_bytes, z_plane_bytes, z_bytes, ones_off, bar_off, total;
+  uint32_t x_plane_bytes, x_bytes, z_plane_bytes, z_bytes, buf_bytes, ones_off, bar_off, total;
 };
 __host__ __device__ inline WgradSmem wgrad_smem(const WgradArgs& p, int a_planes) {
   WgradSmem s;
@@ -820,7 +824,8 @@ __host__ __device__ inline WgradSmem wgrad_smem(const WgradArgs& p, int a_planes
   s.x_bytes = a_planes * s.x_plane_bytes;
   s.z_plane_bytes = round_up((uint32_t)p.z_buf_rows * p.z_row_bytes, 1024);
   s.z_bytes = 2 * s.z_plane_bytes;
-  s.ones_off = s.x_bytes + s.z_bytes;
+  s.buf_bytes = s.x_bytes + s.z_bytes;  // one buffer = the X planes and the dyZ planes of one part
+  s.ones_off = 2 * s.buf_bytes;
   s.bar_off = s.ones_off + 2048;
   s.total = s.bar_off + 64 + 1024;
   return s;
@@ -832,12 +837,14 @@ struct WgradIssue {
   uint32_t x0, x1, x2;   // the first three of them by value (registers) for the specialised loops
   uint32_t xpl16, x_hi32, zh0, z_hi32, tmem, N2, idesc2, idesc1, dbias, ones_lo, z_row_bytes;
   bool has_bias;
+  uint32_t boff;         // 16-byte units added to every X / dyZ descriptor: the buffer of the current part
+  int j0;                // first K = 16 step of the current part (descriptor offsets are relative to the part)
 };
 // generic step (any tile count; ACC = false: the very first step of the CTA, which initialises the accumulators)
 template <int A_PLANES, bool ACC>
 __device__ __forceinline__ void wgrad_issue_step(const WgradIssue& w, int nt, int j) {
-  const uint32_t zh = w.zh0 + (uint32_t)j * w.z_row_bytes;  // 16 rows = row_bytes 16-byte units
-  const uint32_t xk = (uint32_t)j * 128;                    // 16 rows of 128 bytes
+  const uint32_t zh = w.zh0 + w.boff + (uint32_t)(j - w.j0) * w.z_row_bytes;  // 16 rows = row_bytes 16-byte units
+  const uint32_t xk = w.boff + (uint32_t)(j - w.j0) * 128;                    // 16 rows of 128 bytes
   for (int t = 0; t < nt; ++t) {
     const uint32_t d = w.tmem + (uint32_t)t * w.N2;
     tma::mma_bf16_split<ACC>(d, w.xlo[t] + xk, w.x_hi32, zh, w.z_hi32, w.idesc2);
@@ -848,8 +855,8 @@ __device__ __forceinline__ void wgrad_issue_step(const WgradIssue& w, int nt, in
 // accumulating step with a compile-time tile count: straight-line code
 template <int A_PLANES, int NT>
 __device__ __forceinline__ void wgrad_issue_tiles(const WgradIssue& w, int j) {
-  const uint32_t zh = w.zh0 + (uint32_t)j * w.z_row_bytes;
-  const uint32_t xk = (uint32_t)j * 128;
+  const uint32_t zh = w.zh0 + w.boff + (uint32_t)(j - w.j0) * w.z_row_bytes;
+  const uint32_t xk = w.boff + (uint32_t)(j - w.j0) * 128;
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
     const uint32_t d = w.tmem + (uint32_t)t * w.N2;
@@ -873,9 +880,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const WgradSmem L = wgrad_smem(p, A_PLANES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* full = bars;       // image pair landed
-  uint64_t* empty = bars + 1;  // MMAs reading the buffers complete
-  uint64_t* done = bars + 2;   // all MMAs of the CTA complete
+  uint64_t* full = bars;       // [2] part landed in buffer b
+  uint64_t* empty = bars + 2;  // [2] MMAs reading buffer b complete
+  uint64_t* done = bars + 4;   // all MMAs of the CTA complete
   __shared__ uint32_t tmem_base_s;
 
   pdl_trigger();
@@ -901,7 +908,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
     row[0] = __float2bfloat16(1.0f);
   }
   if (tid == 0) {
-    mbar_init(full, 1), mbar_init(empty, 1), mbar_init(done, 1);
+    mbar_init(&full[0], 1), mbar_init(&full[1], 1), mbar_init(&empty[0], 1), mbar_init(&empty[1], 1), mbar_init(done, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
@@ -915,25 +922,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
 
   if (warp == 0) {
     pdl_wait();
-    for (int im = im0, i = 0; im < im1; ++im, ++i) {
-      mbar_wait(empty, (i & 1) ^ 1);
-      if (elect_one()) {
-        tl_stamp(p.debug, 1000 + i);
-        const uint32_t bytes = (uint32_t)A_PLANES * p.x_halves * p.x_chunks * p.x_chunk_rows * 128 +
-                               2u * p.z_chunks * p.z_chunk_rows * p.z_row_bytes;
-        tma::expect_tx(full, bytes);
-        const int xrow = ((p.x_shared ? 0 : z) * p.imgs + im) * p.x_rows_alloc, zrow = (z * p.imgs + im) * p.z_rows_alloc;
-        for (int pl = 0; pl < A_PLANES; ++pl)
-          for (int hf = 0; hf < p.x_halves; ++hf)
-            for (int ch = 0; ch < p.x_chunks; ++ch)
-              tma::load_3d(xs + pl * L.x_plane_bytes + (uint32_t)hf * p.x_buf_rows * 128 + (uint32_t)ch * p.x_chunk_rows * 128,
-                           pl ? &mapX_lo : &mapX_hi, full, 0, hf, xrow + ch * p.x_chunk_rows);
-        for (int pl = 0; pl < 2; ++pl)
-          for (int ch = 0; ch < p.z_chunks; ++ch)
-            tma::load_3d(zs + pl * L.z_plane_bytes + (uint32_t)ch * p.z_chunk_rows * p.z_row_bytes, pl ? &mapZ_lo : &mapZ_hi,
-                         full, 0, 0, zrow + ch * p.z_chunk_rows);
+    int i = 0;
+    for (int im = im0; im < im1; ++im) {
+      for (int part = 0; part < p.n_parts; ++part, ++i) {
+        const int b = i & 1;
+        mbar_wait(&empty[b], ((i >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          tl_stamp(p.debug, 1000 + i);
+          const uint32_t bytes = (uint32_t)A_PLANES * p.x_halves * p.x_chunks * p.x_chunk_rows * 128 +
+                                 2u * p.z_chunks * p.z_chunk_rows * p.z_row_bytes;
+          tma::expect_tx(&full[b], bytes);
+          const int xrow = ((p.x_shared ? 0 : z) * p.imgs + im) * p.x_rows_alloc + 16 * p.pj[part];
+          const int zrow = (z * p.imgs + im) * p.z_rows_alloc + p.z_start + 16 * p.pj[part];
+          const uint32_t xb = xs + b * L.buf_bytes, zb = zs + b * L.buf_bytes;
+          for (int pl = 0; pl < A_PLANES; ++pl)
+            for (int hf = 0; hf < p.x_halves; ++hf)
+              for (int ch = 0; ch < p.x_chunks; ++ch)
+                tma::load_3d(xb + pl * L.x_plane_bytes + (uint32_t)hf * p.x_buf_rows * 128 + (uint32_t)ch * p.x_chunk_rows * 128,
+                             pl ? &mapX_lo : &mapX_hi, &full[b], 0, hf, xrow + ch * p.x_chunk_rows);
+          for (int pl = 0; pl < 2; ++pl)
+            for (int ch = 0; ch < p.z_chunks; ++ch)
+              tma::load_3d(zb + pl * L.z_plane_bytes + (uint32_t)ch * p.z_chunk_rows * p.z_row_bytes, pl ? &mapZ_lo : &mapZ_hi,
+                           &full[b], 0, 0, zrow + ch * p.z_chunk_rows);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     {
@@ -953,31 +966,36 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
       }
       const uint32_t xpl16 = L.x_plane_bytes >> 4, ones_lo = tma::desc_lo32(base + L.ones_off, 16);
       // B = [dy_hi | dy_lo]: the lo plane is the second N group, LBO = plane bytes
-      const uint32_t zh0 = tma::desc_lo32(zs + (uint32_t)p.z_start * p.z_row_bytes, L.z_plane_bytes);
+      const uint32_t zh0 = tma::desc_lo32(zs, L.z_plane_bytes);  // the part's box starts at dyZ row z_start + 16 pj
       const uint32_t dbias = tmem + (uint32_t)nt * N2;
-      for (int im = im0, i = 0; im < im1; ++im, ++i) {
-        mbar_wait(full, i & 1);
+      int i = 0;
+      for (int im = im0; im < im1; ++im)
+      for (int part = 0; part < p.n_parts; ++part, ++i) {
+        const int b = i & 1;
+        mbar_wait(&full[b], (i >> 1) & 1);
         tcgen05_after_sync();
         if (elect_one()) {
         tl_stamp(p.debug, 3000 + 2 * i);
         // The issuing thread is ONE instruction stream: the loop is specialised on the number of accumulator tiles of this
         // CTA (a 16-way predicated unroll cost ~300 cycles per K = 16 step for the one or two MMAs it contained -- 5x the
         // tensor time, tools/mma_rate.cu) and the non-accumulating first step is peeled off.
-        const WgradIssue w{xlo, xlo[0], nt > 1 ? xlo[1] : 0u, nt > 2 ? xlo[2] : 0u, xpl16, x_hi32, zh0, z_hi32, tmem, (uint32_t)N2, idesc2, idesc1, dbias, ones_lo, p.z_row_bytes, has_bias};
-        int j = 0;
+        const WgradIssue w{xlo, xlo[0], nt > 1 ? xlo[1] : 0u, nt > 2 ? xlo[2] : 0u, xpl16, x_hi32, zh0, z_hi32, tmem, (uint32_t)N2, idesc2, idesc1, dbias, ones_lo, p.z_row_bytes, has_bias,
+                           (uint32_t)b * (L.buf_bytes >> 4), p.pj[part]};
+        int j = p.pj[part];
+        const int jend = p.pj[part + 1];
         if (i == 0) {
-          wgrad_issue_step<A_PLANES, false>(w, nt, 0);
-          j = 1;
+          wgrad_issue_step<A_PLANES, false>(w, nt, j);
+          ++j;
         }
         switch (nt) {
-          case 1: for (; j < p.k16; ++j) wgrad_issue_tiles<A_PLANES, 1>(w, j); break;
-          case 2: for (; j < p.k16; ++j) wgrad_issue_tiles<A_PLANES, 2>(w, j); break;
-          case 3: for (; j < p.k16; ++j) wgrad_issue_tiles<A_PLANES, 3>(w, j); break;
-          default: for (; j < p.k16; ++j) wgrad_issue_step<A_PLANES, true>(w, nt, j); break;
+          case 1: for (; j < jend; ++j) wgrad_issue_tiles<A_PLANES, 1>(w, j); break;
+          case 2: for (; j < jend; ++j) wgrad_issue_tiles<A_PLANES, 2>(w, j); break;
+          case 3: for (; j < jend; ++j) wgrad_issue_tiles<A_PLANES, 3>(w, j); break;
+          default: for (; j < jend; ++j) wgrad_issue_step<A_PLANES, true>(w, nt, j); break;
         }
-        mma_commit(empty);
+        mma_commit(&empty[b]);
         tl_stamp(p.debug, 3001 + 2 * i);
-        if (im == im1 - 1) mma_commit(done);
+        if (im == im1 - 1 && part == p.n_parts - 1) mma_commit(done);
         }
         __syncwarp();
       }

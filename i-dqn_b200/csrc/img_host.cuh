@@ -262,11 +262,34 @@ static int img_setup(idqn_handle* h) {
       a.k16 = (g.OH * g.P + 15) / 16;
       a.z_start = (g.T - 1) * (g.P + 1);
       const int shmax = (g.T - 1) * g.P + (g.T - 1);
-      a.x_rows_alloc = g.XRa, a.x_chunks = g.x_chunks, a.x_chunk_rows = g.x_chunk_rows, a.x_halves = g.halves;
-      a.x_buf_rows = (std::max(g.XRa, shmax + 16 * a.k16) + 7) / 8 * 8;
-      a.z_rows_alloc = g.ZRa, a.z_chunks = g.z_chunks, a.z_chunk_rows = g.z_chunk_rows;
-      a.z_buf_rows = (std::max(g.ZRa, a.z_start + 16 * a.k16) + 7) / 8 * 8;
+      a.x_rows_alloc = g.XRa, a.x_halves = g.halves;
+      a.z_rows_alloc = g.ZRa;
       a.z_row_bytes = (uint32_t)g.OC * 2;
+      {
+        // parts: the K = 16 steps of an image in two halves, each with its own box of X2 rows (+ the tap-shift halo) and
+        // of dyZ rows, double-buffered in shared memory
+        a.n_parts = a.k16 >= 4 ? 2 : 1;
+        const int smax = (a.k16 + a.n_parts - 1) / a.n_parts;
+        a.pj[0] = 0, a.pj[1] = a.n_parts == 2 ? smax : a.k16, a.pj[2] = a.k16, a.pj[3] = a.k16;
+        const int xrows = 16 * smax + shmax, zrows = 16 * smax;
+        a.x_chunks = (xrows + 255) / 256, a.x_chunk_rows = ((xrows + a.x_chunks - 1) / a.x_chunks + 7) / 8 * 8;
+        a.x_buf_rows = a.x_chunks * a.x_chunk_rows;
+        a.z_chunks = (zrows + 255) / 256, a.z_chunk_rows = ((zrows + a.z_chunks - 1) / a.z_chunks + 7) / 8 * 8;
+        a.z_buf_rows = a.z_chunks * a.z_chunk_rows;
+        ImgLayerState& S = h->il[li];
+        const int xnets = li == 0 ? 2 : 2 * K;
+        for (int pl = 0; pl < 2; ++pl) {
+          const uint64_t xdims[3] = {64, (uint64_t)g.halves, (uint64_t)xnets * B * g.XRa};
+          const uint64_t xstr[2] = {128, (uint64_t)g.C2 * 2};
+          const uint32_t xbox[3] = {64, 1, (uint32_t)a.x_chunk_rows};
+          REQUIRE(tma::encode_bf16(&S.mapXw[pl], pl ? S.x2_lo : S.x2_hi, 3, xdims, xstr, xbox, 128), "tensor map X2 (wgrad parts) L%d", li);
+          const uint64_t zdims[3] = {(uint64_t)g.OC, 1, (uint64_t)K * B * g.ZRa};
+          const uint64_t zstr[2] = {(uint64_t)g.OC * 2, (uint64_t)g.OC * 2};
+          const uint32_t zbox[3] = {(uint32_t)g.OC, 1, (uint32_t)a.z_chunk_rows};
+          REQUIRE(tma::encode_bf16(&S.mapZw[pl], pl ? S.dz_lo : S.dz_hi, 3, zdims, zstr, zbox, g.OC * 2), "tensor map dyZ (wgrad parts) L%d", li);
+        }
+        REQUIRE(img::wgrad_smem(a, li == 0 ? 1 : 2).total <= IMG_SMEM_OPTIN, "internal: wgrad L%d does not fit shared memory", li);
+      }
       // 64-row groups: (tap, c2 / 64), paired into 128-row tiles
       const int run = g.s * g.IC, ry_per_grp = 64 / run;
       int ng = 0, gsh[2 * img::MAX_TAPS], ghf[2 * img::MAX_TAPS], grow[2 * img::MAX_TAPS];
@@ -552,12 +575,12 @@ static int img_launch_wgrad(idqn_handle* h, int li, int a_planes) {
   const int grid = a.heads * a.groups * a.tsplit;
   if (a_planes == 1) {
     CK(img_set_smem(img::conv_wgrad_kernel<1>, L.total));
-    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<1>, dim3(grid), dim3(img::WG_THREADS), L.total, h->stream, S.mapX[0], S.mapX[1],
-                  S.mapZ[0], S.mapZ[1], a));
+    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<1>, dim3(grid), dim3(img::WG_THREADS), L.total, h->stream, S.mapXw[0], S.mapXw[1],
+                  S.mapZw[0], S.mapZw[1], a));
   } else {
     CK(img_set_smem(img::conv_wgrad_kernel<2>, L.total));
-    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<2>, dim3(grid), dim3(img::WG_THREADS), L.total, h->stream, S.mapX[0], S.mapX[1],
-                  S.mapZ[0], S.mapZ[1], a));
+    CK(launch_pdl(h->pdl, img::conv_wgrad_kernel<2>, dim3(grid), dim3(img::WG_THREADS), L.total, h->stream, S.mapXw[0], S.mapXw[1],
+                  S.mapZw[0], S.mapZw[1], a));
   }
   CK(cudaGetLastError());
   mark(h, "img_wgrad_L%d", li);
