@@ -161,7 +161,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, N2 = 2 * p.N;   // accumulator columns per tile: [0,N) hi*hi + lo*hi, [N,2N) hi*lo
-  const bool pair = KIND == 0 && p.pair;
+  const bool pair = p.pair != 0;  // forward conv1 / conv2 and the conv2 data gradient (N = 64: two tiles x 2N columns, twice)
   const int ACCW = (pair ? 2 : 1) * N2;  // columns of one accumulator buffer (one pass)
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * ACCW) tmem_cols <<= 1;
@@ -346,16 +346,17 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       const int nb = min(p.hpg, p.nets_per_g - hg * p.hpg);
       const int ab = ai & 1;
       j += npt;
-      // dgrad (never paired): the relu' masks of this thread's (at most two) 32-column chunks do not depend on the
-      // accumulator: they are requested BEFORE the wait for the MMAs, so their L2 latency hides behind the MMA phase
+      // dgrad: the relu' masks of this thread's 32-column chunks do not depend on the accumulator: they are requested BEFORE
+      // the wait for the MMAs, so their L2 latency hides behind the MMA phase.  Two slots: the two chunks (c0, c0 + 64) of a
+      // single-tile pass at N = 128, or the one chunk of each tile of a two-tile pass (N = 64)
       uint4 xa[2][4];
       if (KIND == 1) {
-        const int m = tile0 * 128 + r;
-        const int my = m / p.P, mx = m - my * p.P;
-        const bool rowok = m < p.M_valid && mx < p.W_valid;
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
-          const int c0 = chalf * 32 + kk * 64;
+          const int m = (tile0 + (pair ? kk : 0)) * 128 + r;
+          const int my = m / p.P, mx = m - my * p.P;
+          const bool rowok = m < p.M_valid && mx < p.W_valid && (!pair || kk < npt);
+          const int c0 = chalf * 32 + (pair ? 0 : kk * 64);
           const int blk = c0 / p.OC, ry = blk / p.s, rx = blk - ry * p.s;
           const int iy = my * p.s + ry - p.ph, ix = mx * p.s + rx - p.pw;
           const bool ok = c0 < N && rowok && (unsigned)iy < (unsigned)p.IH && (unsigned)ix < (unsigned)p.IW;
@@ -434,7 +435,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           const int iy = my * p.s + ry - p.ph, ix = mx * p.s + rx - p.pw;
           const bool ok = rowok && (unsigned)iy < (unsigned)p.IH && (unsigned)ix < (unsigned)p.IW;
           // relu' mask: the layer input is this very row of the X2 hi plane (hi > 0 <=> x > 0), 32 contiguous bf16
-          const int kk = c0 >> 6;  // this thread's chunk index (N <= 128: at most two chunks per thread)
+          const int kk = pair ? ti : c0 >> 6;  // mask slot: the tile of a two-tile pass, else this thread's chunk index (N <= 128)
           tmem_ld_wait();
           if (!ok) continue;
           float o[32];
@@ -1022,18 +1023,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_cons
         arow = p.b_off, sc = 1.f;
       }
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)t * N2;
-      for (int c0 = chalf * 16; c0 < N; c0 += 32) {
-        float v[16], v2[16];
-        tmem_ld16_nowait(taddr + c0, v);
-        tmem_ld16_nowait(taddr + N + c0, v2);
-        tmem_ld_wait();
-        if (arow < 0) continue;
+      // this thread's 16-column chunks (one at N = 32, two at N = 64): every TMEM load of the tile is in flight before the
+      // one wait (warp-uniform trip counts: the loads are .sync.aligned)
+      float v[2][16], v2[2][16];
+      const int c00 = chalf * 16, nc = c00 + 32 < N ? 2 : (c00 < N ? 1 : 0);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          reinterpret_cast<float4*>(part + arow + c0)[k4] =
-              make_float4((v[4 * k4] + v2[4 * k4]) * sc, (v[4 * k4 + 1] + v2[4 * k4 + 1]) * sc,
-                          (v[4 * k4 + 2] + v2[4 * k4 + 2]) * sc, (v[4 * k4 + 3] + v2[4 * k4 + 3]) * sc);
-      }
+      for (int cc = 0; cc < 2; ++cc)
+        if (cc < nc) {
+          tmem_ld16_nowait(taddr + c00 + 32 * cc, v[cc]);
+          tmem_ld16_nowait(taddr + N + c00 + 32 * cc, v2[cc]);
+        }
+      tmem_ld_wait();
+      if (arow < 0) continue;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc)
+        if (cc < nc) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            reinterpret_cast<float4*>(part + arow + c00 + 32 * cc)[k4] =
+                make_float4((v[cc][4 * k4] + v2[cc][4 * k4]) * sc, (v[cc][4 * k4 + 1] + v2[cc][4 * k4 + 1]) * sc,
+                            (v[cc][4 * k4 + 2] + v2[cc][4 * k4 + 2]) * sc, (v[cc][4 * k4 + 3] + v2[cc][4 * k4 + 3]) * sc);
+        }
     }
   }
   if (warp == 2 && lane == 0) tl_stamp(p.debug, 1201);

@@ -219,6 +219,7 @@ static int img_setup(idqn_handle* h) {
       a.N = g.C2;  // <= 128 (img_geom): the epilogue prefetches the relu' masks of at most two 32-column chunks per thread
       a.tpp = std::max(1, std::min(a.tiles, 128 / a.N));
       a.n_taps = g.T * g.T, a.kt = g.OC / 16;
+      a.pair = a.tiles == 2 && 8 * a.N <= 512 && !getenv("IDQN_NO_PAIR");  // conv2: N = 64
       int shmax = 0;
       for (int ty = 0; ty < g.T; ++ty)
         for (int tx = 0; tx < g.T; ++tx) {
