@@ -604,7 +604,17 @@ static int dense_launch(idqn_handle* h, bool dgrad, bool z_dst, int unit0 = -1, 
   }
   a.keep_heads = l2_keep_heads(h);
   const dense::Smem L = dense::smem_layout(a);
-  const int grid = std::min(a.n_units, h->sm_count);
+  int grid = std::min(a.n_units, h->sm_count);
+  {
+    // whole rounds: with u units on g CTAs the kernel takes ceil(u / g) units of time whatever g is; the fewest CTAs with
+    // that maximum leave the partial last round (305 data-gradient units on 148 CTAs: nine CTAs with a third unit) no
+    // idle bandwidth to wait for -- every CTA streams all the time and shares HBM with fewer others
+    static const bool rounds_env = !getenv("IDQN_NO_ROUNDS");
+    if (rounds_env && unit0 < 0) {
+      const int per = (a.n_units + grid - 1) / grid;
+      grid = (a.n_units + per - 1) / per;
+    }
+  }
   if (dgrad) {
     CK(img_set_smem(dense::dense_stream_kernel<1>, L.total));
     CK(launch_pdl(h->pdl, dense::dense_stream_kernel<1>, dim3(grid), dim3(dense::NTHREADS), L.total, h->stream,
