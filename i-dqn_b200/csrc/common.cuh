@@ -63,6 +63,15 @@ __device__ __forceinline__ void ktl_end(int id) {
   }
 }
 
+// per-CTA stamps of ONE kernel of the step (the one whose timeline slot equals g_ctl_sel): [cta][0] entry, [1] first operand
+// landed, [2] last MMA committed, [3] exit -- where inside a kernel's span its CTAs spend their time (tools/cta_timeline.py)
+#define IDQN_CTL_MAX 160
+static __device__ unsigned long long g_ctl[IDQN_CTL_MAX * 4];
+static __device__ int g_ctl_sel = -1;
+__device__ __forceinline__ void ctl_stamp(int id, int k) {
+  if (id >= 0 && id == g_ctl_sel && blockIdx.x < IDQN_CTL_MAX) g_ctl[blockIdx.x * 4 + k] = ktl_now();
+}
+
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args&&... args) {

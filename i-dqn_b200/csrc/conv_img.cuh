@@ -191,6 +191,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   const uint32_t tmem = tmem_base_s;
   if (tid == 0) tl_stamp(p.debug, 1);
   ktl_begin(p.tl_id);
+  if (tid == 0) ctl_stamp(p.tl_id, 0);
 
   if (warp == 0) {
     // ===== image producer: one load per unit this CTA touches =====
@@ -293,6 +294,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           if (p.resident) ws = grp;
           if (reload) mbar_wait(&w_full[ws], wphase);
           tcgen05_after_sync();
+          if (ai == 0 && grp == 0) ctl_stamp(p.tl_id, 1);
           tl_stamp(p.debug, 3000 + ai * 32 + grp);
           const int tg0 = grp * p.tap_group, tg1 = min(p.n_taps, tg0 + p.tap_group);
           for (int ti = 0; ti < npt; ++ti) {
@@ -319,6 +321,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           if (last_grp) {
             mma_commit(&acc_full[ab]);
             if (unit_ends) mma_commit(&x_empty[xb]);
+            if (last_job) ctl_stamp(p.tl_id, 2);
           }
           tl_stamp(p.debug, 3000 + ai * 32 + 16 + grp);
           if (!p.resident && ++ws == p.ring) ws = 0, wphase ^= 1;
@@ -476,6 +479,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 #undef PASS_TILES
   tcgen05_before_sync();
   __syncthreads();
+  if (tid == 0) ctl_stamp(p.tl_id, 3);
   ktl_end(p.tl_id);
   if (warp == 2) tmem_dealloc(tmem, tmem_cols);
 }

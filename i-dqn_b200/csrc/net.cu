@@ -1056,7 +1056,10 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
       int rc = li > 0 ? img_launch_taps(h, li, true, 2) : IDQN_OK;
       if (rc) return rc;
       cudaStream_t main_stream = h->stream;
-      if (fork_conv) h->stream = h->side;
+      // conv0's weight gradient stays on the main stream (unless IDQN_WGRAD0_SIDE): it depends on conv1's data gradient only, and
+      // as the side branch's third kernel it would also wait for conv1's weight gradient
+      static const bool wgrad0_side = getenv("IDQN_WGRAD0_SIDE") != nullptr;
+      if (fork_conv && (li > 0 || wgrad0_side)) h->stream = h->side;
       rc = img_launch_wgrad(h, li, li == 0 ? 1 : 2);
       h->stream = main_stream;
       if (rc) return rc;
@@ -1066,6 +1069,10 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
         if (deferred_li >= 0) {
           // main: the HBM kernel (after the last conv weight gradient, so it does not take the SMs from it);
           // side: the final Adam next to it; join
+          if (!wgrad0_side) {  // the final Adam (side) also reads conv0's partial gradients, computed on the main stream
+            CK(cudaEventRecord(h->ev_fork, h->stream));
+            CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+          }
           rc = launch_wgrad_layer(h, deferred_li, x_u8, dry, ws_part, ws_tick);
           if (rc) return rc;
           h->stream = h->side;
@@ -1932,4 +1939,23 @@ extern "C" int idqn_select_action(idqn_handle* h, const void* state, int u8, uin
     return IDQN_OK;  // no device work at all on an exploring step
   }
   return idqn_best_action(h, IDQN_ONLINE, head, state, u8, action);
+}
+
+// IDQN_F_TIMELINE: per-CTA stamps (entry, first operand landed, last MMA committed, exit; ns) of the kernel in timeline slot
+// `slot` during the steps run since the selection; slot < 0 turns the recording off.  out: [4 * n_ctas]
+extern "C" int idqn_cta_timeline(idqn_handle* h, int slot, unsigned long long* out, int max_ctas, int* n_out) {
+  REQUIRE(h, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (out && n_out) {
+    const int n = std::min(max_ctas, IDQN_CTL_MAX);
+    static unsigned long long buf[IDQN_CTL_MAX * 4];
+    CK(cudaMemcpyFromSymbol(buf, g_ctl, sizeof(buf)));
+    memcpy(out, buf, sizeof(unsigned long long) * 4 * n);
+    *n_out = n;
+  }
+  static unsigned long long zeros[IDQN_CTL_MAX * 4];
+  CK(cudaMemcpyToSymbol(g_ctl, zeros, sizeof(zeros)));
+  CK(cudaMemcpyToSymbol(g_ctl_sel, &slot, sizeof(int)));
+  return IDQN_OK;
 }

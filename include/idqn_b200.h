@@ -143,6 +143,10 @@ int idqn_profile_step(idqn_handle* h, int state_is_u8, int max_entries, float* m
 /* IDQN_F_TIMELINE handles: global-timer stamps (ns) of the kernels of the most recent step in launch order, out[2*i] =
  * start of the first CTA, out[2*i+1] = end of the last CTA, names[32*i..] the kernel tag; resets the slots */
 int idqn_kernel_timeline(idqn_handle* h, unsigned long long* out, char* names, int max_entries, int* n_out);
+/* IDQN_F_TIMELINE: per-CTA global-timer stamps {entry, first operand landed, last MMA committed, exit} of the conv kernel in
+ * timeline slot `slot` (launch index inside the step), recorded by the steps that follow; reads back what was recorded since
+ * the previous call (out may be NULL) */
+int idqn_cta_timeline(idqn_handle* h, int slot, unsigned long long* out, int max_ctas, int* n_out);
 /* pipeline timeline of CTA 0 of the kernel named by the IDQN_TL environment variable (fwd0..2, dgrad1..2, wgrad0..2,
  * dfwd3, ddgrad3) during the most recent step: entries (clock64 << 16 | tag), 0 = unused; returns the entry count */
 int idqn_debug_timeline(unsigned long long* out, int max_entries);

@@ -23,8 +23,13 @@ struct Cfg {
   uint32_t b_start, b_lbo, b_sbo, b_lt, b_kstep;
   int ksteps;            // K = 16 steps per "tile" (descriptor offsets wrap after this many)
   int a2;                // 1: a second MMA per step with N/2 columns (the A_lo * B_hi term)
+  int alt;               // accumulators the stream of MMAs rotates over (1: every MMA accumulates into the same columns)
 };
 
+// KS / A2 / ALT are compile-time so that the timed loop is straight-line code with every descriptor in a register: the
+// issuing thread must not be what is measured (a first version with run-time loop bounds and a division per MMA
+// measured ~100-170 cycles of ITS OWN overhead per iteration)
+template <int KS, int A2, int ALT>
 __global__ void __launch_bounds__(128) rate_kernel(const Cfg c, int iters, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -54,10 +59,19 @@ __global__ void __launch_bounds__(128) rate_kernel(const Cfg c, int iters, long 
     mbar_wait(&bar, 0);
     tcgen05_after_sync();
     const long long t0 = clock64();
+    uint32_t ad[KS], bd[KS];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) ad[j] = a0 + j * (c.a_kstep >> 4), bd[j] = b0 + j * (c.b_kstep >> 4);
     for (int it = 0; it < iters; ++it) {
-      for (int j = 0; j < c.ksteps; ++j) {
-        tma::mma_bf16_split<true>(tmem, a0 + j * (c.a_kstep >> 4), a_hi32, b0 + j * (c.b_kstep >> 4), b_hi32, idesc);
-        if (c.a2) tma::mma_bf16_split<true>(tmem, a0 + j * (c.a_kstep >> 4) + 64, a_hi32, b0 + j * (c.b_kstep >> 4), b_hi32, idesc_half);
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        // ALT > 1: the same step for ALT independent accumulators back to back (M tiles sharing a weight tile)
+#pragma unroll
+        for (int q = 0; q < ALT; ++q) tma::mma_bf16_split<true>(tmem + q * (512 / ALT), ad[j] + q * 1024, a_hi32, bd[j], b_hi32, idesc);
+        if (A2) {
+#pragma unroll
+          for (int q = 0; q < ALT; ++q) tma::mma_bf16_split<true>(tmem + q * (512 / ALT), ad[j] + 64 + q * 1024, a_hi32, bd[j], b_hi32, idesc_half);
+        }
       }
     }
     mma_commit(&bar);
@@ -92,16 +106,29 @@ int main() {
       {"A MN-major LBO 8 KB, B MN-major SW64, N=64", 1, 1, 64, 0, 8192, 1024, SW128, 2048, 0, 4096, 512, SW64, 1024, 8, 0},
       {"A MN-major LBO 8 KB, B K-major, N=128", 1, 0, 128, 0, 8192, 1024, SW128, 2048, 0, 16, 1024, SW128, 32, 4, 0},
       {"A MN-major LBO 8 KB, B MN-major, N=256", 1, 1, 256, 0, 8192, 1024, SW128, 2048, 0, 8192, 1024, SW128, 2048, 8, 0},
+      {"2 accumulators alternating: A K-major, B K-major, N=64 (per MMA)", 0, 0, 64, 0, 16, 1024, SW128, 32, 0, 16, 1024, SW128, 32, 4, 0, 2},
+      {"2 accumulators alternating: A K-major, B K-major, N=128 (per MMA)", 0, 0, 128, 0, 16, 1024, SW128, 32, 0, 16, 1024, SW128, 32, 4, 0, 2},
+      {"2 accumulators alternating: A K-major, B K-major, N=256 (per MMA)", 0, 0, 256, 0, 16, 1024, SW128, 32, 0, 16, 1024, SW128, 32, 4, 0, 2},
+      {"4 accumulators alternating: N=128 (per MMA)", 0, 0, 128, 0, 16, 1024, SW128, 32, 0, 16, 1024, SW128, 32, 4, 0, 4},
+      {"4 accumulators alternating: N=64 (per MMA)", 0, 0, 64, 0, 16, 1024, SW128, 32, 0, 16, 1024, SW128, 32, 4, 0, 4},
+      {"2 accumulators alternating, conv fwd pair (N=128 then N=64) [per step and tile]", 0, 1, 128, 0, 16, 1024, SW128, 32, 0, 8192, 1024, SW128, 2048, 4, 1, 2},
+      {"2 accumulators alternating, conv dgrad pair (N=256 then N=128) [per step and tile]", 0, 0, 256, 0, 16, 1024, SW128, 32, 0, 16, 1024, SW128, 32, 4, 1, 2},
   };
   long long* d_out;
   cudaMalloc(&d_out, sizeof(long long) * 4);
-  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024);
   const int iters = 64;
   printf("%-78s  clk/MMA-step   (ideal tensor time M128 x N x K16: N/2 clk)\n", "configuration");
   for (const Cfg& c : cfgs) {
     long long h = 0;
     for (int rep = 0; rep < 2; ++rep) {
-      rate_kernel<<<1, 128, 201 * 1024 + 1024>>>(c, iters, d_out);
+      const int alt = c.alt > 0 ? c.alt : 1;
+#define RUN(KS, A2, ALT)                                                                                         \
+  if (c.ksteps == KS && c.a2 == A2 && alt == ALT) {                                                              \
+    cudaFuncSetAttribute(rate_kernel<KS, A2, ALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024); \
+    rate_kernel<KS, A2, ALT><<<1, 128, 201 * 1024 + 1024>>>(c, iters, d_out);                                     \
+  }
+      RUN(4, 0, 1) RUN(4, 1, 1) RUN(8, 0, 1) RUN(8, 1, 1) RUN(4, 0, 2) RUN(4, 1, 2) RUN(4, 0, 4) RUN(8, 0, 2)
+#undef RUN
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
         printf("%-78s  FAILED: %s\n", c.name, cudaGetErrorString(e));
@@ -109,7 +136,7 @@ int main() {
       }
       cudaMemcpy(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
     }
-    const double per = (double)h / (iters * c.ksteps);
+    const double per = (double)h / (iters * c.ksteps * (c.alt > 0 ? c.alt : 1));
     printf("%-78s  %8.1f       (%d%s)\n", c.name, per, c.N / 2, c.a2 ? " + half" : "");
   }
   return 0;
