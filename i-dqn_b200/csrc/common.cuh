@@ -158,7 +158,8 @@ struct idqn_handle {
   void* partition;      // smpart::Partition, null when green contexts are unavailable or disabled
   cudaEvent_t ev_fork, ev_join[2];
   // second branch of the step graph: the conv weight-gradient kernels run next to the conv data-gradient chain
-  cudaStream_t side;
+  cudaStream_t side, side2;
+  cudaEvent_t ev_fork2;
   cudaEvent_t ev_conv[IDQN_IMG_LAYERS], ev_side_done;
   float part_frac;      // share of the Dense_0 wgrad+Adam tiles that run inside the partition
   int wg_tile0, wg_tiles;  // tile range of the next Dense wgrad+Adam launch (wg_tiles == 0: all)

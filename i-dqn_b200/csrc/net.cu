@@ -1043,6 +1043,15 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   // the END of the backward pass: the conv chain (main: dgrads, side: wgrads) runs first, then the final Adam launch
   // -- small CTAs that fit next to the persistent ones -- hides under the 97 us of the HBM kernel.
   int deferred_li = -1;
+  bool overlapped = false;
+  int deferred_t0 = 0;
+  static const float overlap_frac = getenv("IDQN_WG_FRAC") ? (float)atof(getenv("IDQN_WG_FRAC")) : 1.0f;
+  static const int overlap_env = getenv("IDQN_WG_OVERLAP") ? atoi(getenv("IDQN_WG_OVERLAP")) : -1;
+  // CTAs of the Dense_0 update when it runs next to the conv backward chain instead of after it (0: after).  Measured on
+  // B200 (tools/r2l.sh, ms per step, deferred -> overlapped): K=1 0.122 -> 0.113 at 64-80 CTAs, K=2 0.173 -> 0.168 at 72,
+  // K=3 0.213 -> 0.208 at 80-88, K=5 0.298 -> 0.291 at 88-96, K=8 0.418 -> 0.416 at 112; fewer CTAs starve the update
+  // (~41 GB/s per SM), more starve the chain.  IDQN_WG_OVERLAP=<n> overrides, 0 restores the deferred order.
+  const int overlap_ctas = overlap_env >= 0 ? overlap_env : (K <= 10 ? std::min(h->sm_count, (64 + 6 * K) * h->sm_count / 148) : 0);
   for (int li = L - 2; li >= 0; --li) {
     // the dgrad of this layer reads the weights the fused wgrad+Adam kernel overwrites: dgrad first
     if (li < n_img) {
@@ -1073,7 +1082,9 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
             CK(cudaEventRecord(h->ev_fork, h->stream));
             CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
           }
+          if (deferred_t0 > 0) h->wg_tile0 = deferred_t0, h->wg_tiles = h->layers[deferred_li].g.Kd / dwt::TM - deferred_t0;
           rc = launch_wgrad_layer(h, deferred_li, x_u8, dry, ws_part, ws_tick);
+          h->wg_tile0 = h->wg_tiles = 0;
           if (rc) return rc;
           h->stream = h->side;
           const int64_t hi = (fused_hi + 3) / 4 * 4;
@@ -1082,6 +1093,7 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
           if (rc) return rc;
           CK(cudaEventRecord(h->ev_join[0], h->side));
           CK(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+          if (overlapped) CK(cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
           return IDQN_OK;
         }
       }
@@ -1130,6 +1142,26 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
       break;
     }
     if (fused && fork_conv && li == n_img && dense_wgrad_tma_ok(h, li) && !(h->cfg.flags & IDQN_F_NO_DEFER)) {
+      if (overlap_ctas > 0) {
+        // few heads: the conv backward kernels leave SMs idle, so the HBM-bound update runs NEXT TO them on a third
+        // branch, on overlap_ctas persistent CTAs (it must follow the data gradient, which reads the weights it rewrites)
+        CK(cudaEventRecord(h->ev_fork2, h->stream));
+        CK(cudaStreamWaitEvent(h->side2, h->ev_fork2, 0));
+        cudaStream_t main_stream = h->stream;
+        const int sm = h->sm_avail;
+        h->stream = h->side2, h->sm_avail = std::min(sm, overlap_ctas);
+        const int mt = h->layers[li].g.Kd / dwt::TM;
+        const int t1 = std::max(1, std::min(mt, (int)(mt * overlap_frac + 0.5f)));
+        h->wg_tile0 = 0, h->wg_tiles = t1;
+        int rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
+        h->stream = main_stream, h->sm_avail = sm;
+        h->wg_tile0 = h->wg_tiles = 0;
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_join[1], h->side2));
+        overlapped = true;
+        if (t1 < mt) deferred_li = li, deferred_t0 = t1;  // the rest of the tiles after the chain, on the whole machine
+        continue;
+      }
       deferred_li = li;
       continue;
     }
@@ -1140,7 +1172,9 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   // Adam over the rest of the arena of every head
   if (fused_lo < 0) return launch_adam_ranges(h, 0, h->stride, false, 0, 0);
   const int64_t hi = (fused_hi + 3) / 4 * 4;  // layer starts are 128-byte aligned, so this stays inside the gap
-  return launch_adam_ranges(h, 0, fused_lo, use_img && fused_lo == h->wspan, hi, h->stride - hi);
+  int rc = launch_adam_ranges(h, 0, fused_lo, use_img && fused_lo == h->wspan, hi, h->stride - hi);
+  if (!rc && overlapped) CK(cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
+  return rc;
 }
 
 int idqn_learn_step_resident(idqn_handle* h, int x_u8, float* losses_host) {
@@ -1237,9 +1271,11 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
     const bool prio = !getenv("IDQN_NO_PRIORITY");
     CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio ? hi : 0));
     CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio ? lo : 0));
+    CK(cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, prio ? lo : 0));
   }
   h->sm_avail = h->sm_count;
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_side_done, cudaEventDisableTiming));
@@ -1396,6 +1432,8 @@ extern "C" int idqn_destroy(idqn_handle* h) {
   for (int i = 0; i < IDQN_IMG_LAYERS; ++i)
     if (h->ev_conv[i]) cudaEventDestroy(h->ev_conv[i]);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
+  if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
   if (h->partition) {
     smpart::destroy((smpart::Partition*)h->partition);
     delete (smpart::Partition*)h->partition;
