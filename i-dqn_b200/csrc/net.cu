@@ -927,6 +927,11 @@ static int launch_adam_ranges(idqn_handle* h, int64_t off_a, int64_t len_a, bool
 }
 
 // enqueue one whole learning step on h->stream (batch already staged in h->s/s2/action/reward/terminal);
+static int dense_update_ctas(const idqn_handle* h) {
+  static const int env = getenv("IDQN_WG_OVERLAP") ? atoi(getenv("IDQN_WG_OVERLAP")) : -1;
+  return env >= 0 ? env : (h->K <= 10 ? std::min(h->sm_count, (64 + 6 * h->K) * h->sm_count / 148) : 0);
+}
+
 // dry = only size the split-K workspace
 static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_t* ws_part = nullptr,
                               int* ws_tick = nullptr) {
@@ -1046,12 +1051,11 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   bool overlapped = false;
   int deferred_t0 = 0;
   static const float overlap_frac = getenv("IDQN_WG_FRAC") ? (float)atof(getenv("IDQN_WG_FRAC")) : 1.0f;
-  static const int overlap_env = getenv("IDQN_WG_OVERLAP") ? atoi(getenv("IDQN_WG_OVERLAP")) : -1;
   // CTAs of the Dense_0 update when it runs next to the conv backward chain instead of after it (0: after).  Measured on
   // B200 (tools/r2l.sh, ms per step, deferred -> overlapped): K=1 0.122 -> 0.113 at 64-80 CTAs, K=2 0.173 -> 0.168 at 72,
   // K=3 0.213 -> 0.208 at 80-88, K=5 0.298 -> 0.291 at 88-96, K=8 0.418 -> 0.416 at 112; fewer CTAs starve the update
   // (~41 GB/s per SM), more starve the chain.  IDQN_WG_OVERLAP=<n> overrides, 0 restores the deferred order.
-  const int overlap_ctas = overlap_env >= 0 ? overlap_env : (K <= 10 ? std::min(h->sm_count, (64 + 6 * K) * h->sm_count / 148) : 0);
+  const int overlap_ctas = dense_update_ctas(h);
   for (int li = L - 2; li >= 0; --li) {
     // the dgrad of this layer reads the weights the fused wgrad+Adam kernel overwrites: dgrad first
     if (li < n_img) {
@@ -1062,7 +1066,13 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
         CK(cudaEventRecord(h->ev_conv[li], h->stream));
         CK(cudaStreamWaitEvent(h->side, h->ev_conv[li], 0));
       }
+      // next to the Dense_0 update the data-gradient kernels are persistent over the SMs it leaves (they would otherwise sit on
+      // all of them, waiting, when it becomes ready)
+      static const int bwd_sms_env = getenv("IDQN_CONV_BWD_SMS") ? atoi(getenv("IDQN_CONV_BWD_SMS")) : -1;
+      const int sm_all = h->sm_avail;
+      if (overlapped) h->sm_avail = std::max(8, std::min(sm_all, bwd_sms_env > 0 ? bwd_sms_env : (bwd_sms_env == 0 ? sm_all : sm_all - overlap_ctas)));
       int rc = li > 0 ? img_launch_taps(h, li, true, 2) : IDQN_OK;
+      h->sm_avail = sm_all;
       if (rc) return rc;
       cudaStream_t main_stream = h->stream;
       // conv0's weight gradient stays on the main stream (unless IDQN_WGRAD0_SIDE): it depends on conv1's data gradient only, and
@@ -1997,3 +2007,7 @@ extern "C" int idqn_cta_timeline(idqn_handle* h, int slot, unsigned long long* o
   CK(cudaMemcpyToSymbol(g_ctl_sel, &slot, sizeof(int)));
   return IDQN_OK;
 }
+
+// CTAs the graph-replayed step gives the Dense_0 weight-gradient + Adam kernel next to the conv backward chain
+// (0: the kernel runs after the chain on the whole machine)
+extern "C" int idqn_dense_update_ctas(idqn_handle* h) { return h ? dense_update_ctas(h) : 0; }
