@@ -367,8 +367,20 @@ def run_ours(args):
         pass
     rl["kernel"] = top
     rl["peak_source"] = pk["src"]
-    rl["how"] = ("the kernel launched alone on every SM, timed with CUDA events around each launch (idqn_profile_step, un-graphed): "
-                 "its own operating point")
+    ctas = int(eng.lib.idqn_dense_update_ctas(eng.h))
+    rl["how"] = ("CUDA events around every launch of an un-graphed step (idqn_profile_step), same grids as the graph-replayed step: "
+                 + (f"this kernel on {ctas} CTAs, the share of the machine the step gives it" if ctas > 0 else "this kernel on every SM"))
+    if ctas > 0 and rl.get("achieved"):
+        # the same kernel given the whole machine (how the step ran it before the overlap): its own ceiling
+        try:
+            ag2 = make_agent(k_total, flags=args.flags)
+            L.check(ag2._engine.lib.idqn_set_dense_update_ctas(ag2._engine.h, 0))
+            acc2 = profile_kernels(ag2._engine, L)
+            rl["whole_machine"] = {"ctas": "all", "us": round(acc2[top] * 1e3, 2), "achieved": rl["achieved"] * acc[top] / acc2[top],
+                                   "frac": rl["frac"] * acc[top] / acc2[top]}
+            del ag2
+        except Exception as e:
+            rl["whole_machine"] = {"error": str(e)}
     # ... and what the same kernel does INSIDE the graph-replayed step, where it is given a capped grid and runs next to
     # the conv backward chain (global-timer stamps of its first CTA start / last CTA end, IDQN_F_TIMELINE)
     try:
@@ -458,8 +470,8 @@ def in_step_leg(make_agent, k_total, rb, L, top, rl, alone_ms):
     if rl.get("achieved"):
         ach = rl["achieved"] * alone_ms * 1e3 / us
         out.update({"achieved": ach, "frac": ach / rl["peak"],
-                    "note": "concurrent with the conv backward kernels by design (DESIGN.md section 3): the step is faster "
-                            "with this kernel on part of the machine than with it alone on all of it"})
+                    "note": "first CTA start to last CTA end inside the graph, where the conv backward kernels run on the other SMs "
+                            "(DESIGN.md section 3): the step is faster with this kernel on part of the machine than alone on all of it"})
     del ag
     return out
 

@@ -62,6 +62,7 @@ SYMBOLS = {
     "idqn_kernel_timeline": (_I, [_P, _P, _P, _I, C.POINTER(_I)]),
     "idqn_cta_timeline": (_I, [_P, _I, _P, _I, C.POINTER(_I)]),
     "idqn_dense_update_ctas": (_I, [_P]),
+    "idqn_set_dense_update_ctas": (_I, [_P, _I]),
     "idqn_shift_params": (_I, [_P]),
     "idqn_sync_target": (_I, [_P]),
     "idqn_copy_online_to_target": (_I, [_P]),

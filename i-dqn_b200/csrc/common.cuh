@@ -163,6 +163,7 @@ struct idqn_handle {
   cudaEvent_t ev_conv[IDQN_IMG_LAYERS], ev_side_done;
   float part_frac;      // share of the Dense_0 wgrad+Adam tiles that run inside the partition
   int wg_tile0, wg_tiles;  // tile range of the next Dense wgrad+Adam launch (wg_tiles == 0: all)
+  int update_ctas_set;     // idqn_set_dense_update_ctas: 0 = automatic, n + 1 = n CTAs (n = 0: after the conv chain, every SM)
   int sm_avail;         // SMs of the stream the next launches go to
   // arenas [K][stride]
   float *online, *target, *mu, *nu, *grad;

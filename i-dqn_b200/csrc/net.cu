@@ -929,6 +929,7 @@ static int launch_adam_ranges(idqn_handle* h, int64_t off_a, int64_t len_a, bool
 // enqueue one whole learning step on h->stream (batch already staged in h->s/s2/action/reward/terminal);
 static int dense_update_ctas(const idqn_handle* h) {
   static const int env = getenv("IDQN_WG_OVERLAP") ? atoi(getenv("IDQN_WG_OVERLAP")) : -1;
+  if (h->update_ctas_set > 0) return std::min(h->sm_count, h->update_ctas_set - 1);
   return env >= 0 ? env : (h->K <= 10 ? std::min(h->sm_count, (64 + 6 * h->K) * h->sm_count / 148) : 0);
 }
 
@@ -1056,6 +1057,9 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
   // K=3 0.213 -> 0.208 at 80-88, K=5 0.298 -> 0.291 at 88-96, K=8 0.418 -> 0.416 at 112; fewer CTAs starve the update
   // (~41 GB/s per SM), more starve the chain.  IDQN_WG_OVERLAP=<n> overrides, 0 restores the deferred order.
   const int overlap_ctas = dense_update_ctas(h);
+  // idqn_profile_step times the kernels one by one on one stream: same grids as in the graph, so that its per-kernel times
+  // (bench.py: kernel_ms, roofline) describe the launches the timed step makes
+  const bool same_grids = h->prof_on && overlap_ctas > 0 && use_img && use_dense && n_img == L - 2 && !(h->cfg.flags & (IDQN_F_NO_FORK | IDQN_F_NO_DEFER));
   for (int li = L - 2; li >= 0; --li) {
     // the dgrad of this layer reads the weights the fused wgrad+Adam kernel overwrites: dgrad first
     if (li < n_img) {
@@ -1070,7 +1074,7 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
       // all of them, waiting, when it becomes ready)
       static const int bwd_sms_env = getenv("IDQN_CONV_BWD_SMS") ? atoi(getenv("IDQN_CONV_BWD_SMS")) : -1;
       const int sm_all = h->sm_avail;
-      if (overlapped) h->sm_avail = std::max(8, std::min(sm_all, bwd_sms_env > 0 ? bwd_sms_env : (bwd_sms_env == 0 ? sm_all : sm_all - overlap_ctas)));
+      if (overlapped || same_grids) h->sm_avail = std::max(8, std::min(sm_all, bwd_sms_env > 0 ? bwd_sms_env : (bwd_sms_env == 0 ? sm_all : sm_all - overlap_ctas)));
       int rc = li > 0 ? img_launch_taps(h, li, true, 2) : IDQN_OK;
       h->sm_avail = sm_all;
       if (rc) return rc;
@@ -1175,7 +1179,10 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
       deferred_li = li;
       continue;
     }
+    const int sm_all = h->sm_avail;
+    if (same_grids && fused && li == n_img && dense_wgrad_tma_ok(h, li)) h->sm_avail = std::min(sm_all, overlap_ctas);
     int rc = launch_wgrad_layer(h, li, x_u8, dry, ws_part, ws_tick);
+    h->sm_avail = sm_all;
     if (rc) return rc;
   }
   if (dry) return IDQN_OK;
@@ -2011,3 +2018,11 @@ extern "C" int idqn_cta_timeline(idqn_handle* h, int slot, unsigned long long* o
 // CTAs the graph-replayed step gives the Dense_0 weight-gradient + Adam kernel next to the conv backward chain
 // (0: the kernel runs after the chain on the whole machine)
 extern "C" int idqn_dense_update_ctas(idqn_handle* h) { return h ? dense_update_ctas(h) : 0; }
+
+// n > 0: the Dense_0 update runs on n CTAs next to the conv backward chain; 0: after the chain on every SM; < 0: automatic
+// (64 + 6 K).  Call before the first learning step: captured graphs keep the schedule they were captured with.
+extern "C" int idqn_set_dense_update_ctas(idqn_handle* h, int n) {
+  REQUIRE(h, "null handle");
+  h->update_ctas_set = n < 0 ? 0 : n + 1;
+  return IDQN_OK;
+}

@@ -535,3 +535,48 @@ def test_forward_chain_is_bit_identical_to_the_two_kernel_path():
     np.testing.assert_array_equal(runs[0][0], runs[1][0])
     for a, b in zip(runs[0][1], runs[1][1]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_backward_schedule_does_not_change_the_numbers():
+    """The Dense_0 update runs either after the conv backward chain on every SM (idqn_set_dense_update_ctas 0), next to it on
+    the automatic 64 + 6 K CTAs, or on an arbitrary cap: three graphs with different branches and grids, the same kernels on
+    the same operands -- losses and every arena bit-identical over 5 steps with a D-sync.  The per-CTA timeline of the
+    instrumented build reports the capped grid."""
+    import ctypes as C
+    from idqn_b200 import _lib as L
+    from idqn_b200.networks.idqn import iDQN
+    obs, feats, A, K, B = (84, 84, 4), [32, 64, 64, 512], 6, 3, 32
+    rng = np.random.default_rng(67)
+    params = O.init_params(rng, obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    target = O.init_params(np.random.default_rng(1067), obs, feats, "cnn", A, n_networks=K, bias_scale=0.01)
+    batches = [make_batch(rng, B, obs, A, True) for _ in range(5)]
+    runs = []
+    for ctas in (0, -1, 40):
+        agent = iDQN(0, obs, A, K, feats, "cnn", 3e-4, 0.99, 1, 1, 8, 4, 1.5e-4)
+        eng = agent._engine
+        L.check(eng.lib.idqn_set_dense_update_ctas(eng.h, ctas))
+        got = int(eng.lib.idqn_dense_update_ctas(eng.h))
+        assert got == (ctas if ctas >= 0 else 64 + 6 * K) or got == (64 + 6 * K) * torch.cuda.get_device_properties(0).multi_processor_count // 148
+        agent.params, agent.target_params = params, target
+        losses = []
+        for step, b in enumerate(batches, start=1):
+            losses.append(eng.learn_host(b, want_losses=True))
+            agent.update_target_params(step)
+        runs.append((np.stack(losses), [eng.download_arena(w) for w in (L.ONLINE, L.TARGET, L.MU, L.NU)]))
+    for other in runs[1:]:
+        np.testing.assert_array_equal(runs[0][0], other[0])
+        for a, b in zip(runs[0][1], other[1]):
+            np.testing.assert_array_equal(a, b)
+    # instrumented build: the update kernel's launch (slot 8 of the step) ran on the capped grid
+    agent = iDQN(0, obs, A, K, feats, "cnn", 3e-4, 0.99, 1, 1, 8, 4, 1.5e-4, flags=L.F_TIMELINE)
+    eng = agent._engine
+    kt, names, n = np.zeros(128, np.uint64), np.zeros(64 * 32, np.uint8), C.c_int(0)
+    for b in batches[:3]:
+        eng.learn_host(b, want_losses=True)
+        L.check(eng.lib.idqn_kernel_timeline(eng.h, L.ptr(kt), L.ptr(names), 64, C.byref(n)))  # reads and clears: the last step's stamps
+    got = [bytes(names[32 * i:32 * i + 32]).split(b"\0")[0].decode() for i in range(n.value)]
+    assert n.value == 15 and "dense_wgrad_adam_L3" in got and got[0] == "s2d_input_L0"
+    t = kt[:2 * n.value].astype(np.int64).reshape(-1, 2)
+    assert (t[:, 1] > t[:, 0]).all()
+    upd, chain_end = got.index("dense_wgrad_adam_L3"), t[got.index("img_wgrad_L0"), 1]
+    assert t[upd, 0] < chain_end, "the update must start before the conv backward chain has finished"
