@@ -27,7 +27,7 @@ namespace dwt {
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
-constexpr int NTHREADS = 576;   // warp 0: TMA, warp 1: MMA, warps 2..17: epilogue
+constexpr int NTHREADS = 608;   // warp 0: TMA loads, warp 1: MMA, warps 2..17: epilogue, warp 18: TMA stores
 constexpr int STAGES = 3;
 constexpr int TM = 8;           // rows (i) per tile
 constexpr int TN = 32;          // N of the MMAs (rows i, the first TM are the tile's)
@@ -81,12 +81,13 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
   uint64_t* acc_empty = bars + 10;   // [2]
   uint64_t* a_full = bars + 12;      // dy^T operand of the current head
   uint64_t* a_empty = bars + 13;
+  uint64_t* ready = bars + 14;       // [STAGES] Adam results written into the stage (epilogue -> store warp)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   ktl_begin(p.tl_id);
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1), mbar_init(&ready[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 16);
     mbar_init(a_full, 1), mbar_init(a_empty, 1);
     fence_mbar_init();
@@ -166,11 +167,33 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
         if (++st == STAGES) st = 0, ph ^= 1;
       }
     }
+  } else if (warp == 18) {
+    // ===== store warp: a stage goes back to the loader as soon as ITS OWN bulk stores have read it.  (Bulk groups are
+    // per thread: when an epilogue thread issued the stores it could only wait for the previous tile's group without
+    // stalling the next tile's Adam, so every stage was held one tile period longer: 3 stages, ~1 load in flight.)
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = i0; it < i1; ++it) {
+        const int z = it / p.ntiles, row0 = (p.tile0 + it % p.ntiles) * TM;
+        mbar_wait(&ready[st], ph);
+        const uint32_t src = base + st * STAGE_BYTES;
+        for (int hb = 0; hb < 2; ++hb) {
+          tma::store_3d_hint(&mapW, src + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
+          tma::store_3d_hint(&mapM, src + TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
+          tma::store_3d_hint(&mapV, src + 2 * TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();
+        tma::arrive(&empty[st]);
+        if (++st == STAGES) st = 0, ph ^= 1;
+      }
+      bulk_wait_all();
+    }
   } else {
     // ===== epilogue: warps 2..17; TMEM lane quadrant = warp % 4 (column o), column block = (warp - 2) / 4 =====
     const int q = warp & 3, o = q * 32 + lane, cbk = (warp - 2) >> 2;
-    const bool storer = tid == 64;
-    int st = 0, ti = 0, prev_st = -1, last_z = -1;
+    int st = 0, ti = 0, last_z = -1;
     uint32_t ph = 0;
     AdamCoef ac;
     for (int it = i0; it < i1; ++it, ++ti) {
@@ -211,27 +234,13 @@ dense_wgrad_adam_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
       }
       fence_proxy_async_smem();  // generic-proxy writes of this thread -> visible to the bulk stores
       epi_bar_sync();
-      if (storer) {
-        const uint32_t src = base + st * STAGE_BYTES;
-        for (int hb = 0; hb < 2; ++hb) {
-          tma::store_3d_hint(&mapW, src + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
-          tma::store_3d_hint(&mapM, src + TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
-          tma::store_3d_hint(&mapV, src + 2 * TILE_F32 + hb * (TILE_F32 / 2), hb * 256, row0, z, p.stream_policy);
-        }
-        bulk_commit();
-        if (prev_st >= 0) {
-          bulk_wait_read<1>();  // the stores of the previous tile have read their stage
-          tma::arrive(&empty[prev_st]);
-        }
-        prev_st = st;
-      }
+      if (tid == 64) tma::arrive(&ready[st]);
       if (p.grad) {  // the optional gradient after the barrier: off the stores' critical path
 #pragma unroll
         for (int e = 0; e < TM; ++e) p.grad[gb + (int64_t)e * p.O] = g[e];
       }
       if (++st == STAGES) st = 0, ph ^= 1;
     }
-    if (storer) bulk_wait_all();
   }
   tcgen05_before_sync();
   __syncthreads();
