@@ -8,7 +8,7 @@ import threading
 PKG = os.path.dirname(os.path.abspath(__file__))
 
 OK, EINVAL, ECUDA, ERANGE, EASSERT, ENOMEM = 0, -1, -2, -3, -4, -5
-ARCH_FC, ARCH_CNN = 0, 1
+ARCH_FC, ARCH_CNN, ARCH_IMPALA = 0, 1, 2
 ONLINE, TARGET, MU, NU, GRAD = 0, 1, 2, 3, 4
 F_NO_GRAPH, F_SIMT_ONLY, F_KEEP_GRADS, F_NO_IMG, F_NO_PDL, F_PARTITION, F_OLD_WGRAD, F_NO_FORK, F_NO_DEFER, F_SLOW_APPLY = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 F_TIMELINE = 1024

@@ -123,16 +123,22 @@ struct ConvGeom {
   FastDiv d_ohow, d_ow, d_kwic, d_ic, d_oc;
 };
 
+#define IDQN_LAYER_GEMM 0  /* conv / dense: has a kernel and a bias */
+#define IDQN_LAYER_POOL 1  /* max-pool (impala, architectures/dqn.py:20): no parameters */
 struct Layer {
   ConvGeom g;           // with g.B == cfg.batch_size
   int is_conv;
+  int kind;             // IDQN_LAYER_*
+  // y = [relu_out] (conv([relu_in] x) + b) [+ output of layer skip_from].  cnn / fc: relu_out on every hidden layer; impala's
+  // pre-activation residual blocks (architectures/dqn.py:22-27) use all three
+  int relu_in, relu_out, skip_from;
   int64_t w_off, b_off; // float offsets inside a head's arena (b_off == w_off + Kd*OC)
   int64_t act_off;      // float offset of this layer's output inside one net's activation block (per sample count B)
   int64_t act_size;     // B*OH*OW*OC
   char name[16];
 };
 
-#define IDQN_MAX_LAYERS (IDQN_MAX_FEATURES + 1)
+#define IDQN_MAX_LAYERS 32  /* impala: 3 x (5 convs + pool) + dense trunk */
 #define IDQN_PROF_MAX 64
 #define IDQN_IMG_LAYERS 3
 
@@ -150,6 +156,7 @@ struct idqn_handle {
   idqn_config cfg;
   int n_layers;
   Layer layers[IDQN_MAX_LAYERS];
+  int n_param_layers, param_layer[IDQN_MAX_LAYERS];  // layers that own a (kernel, bias) leaf pair, in flax creation order
   int64_t stride;       // floats per head in every arena
   int64_t in_elems;     // elements of one input sample
   int K, B, A;

@@ -33,6 +33,8 @@ struct FwdProb {
   int64_t ystride;
   float scale;
   int relu;
+  int relu_in;        // the conv reads relu(x) (impala's pre-activation blocks)
+  const float* skip;  // optional residual input, same layout / net stride as y: y += skip (after the activation)
   int nz, S;  // nets, split-K factor
   int M, N, K, kchunk;
 
@@ -42,6 +44,7 @@ struct FwdProb {
     const float* xf;
     const float* wk;
     const float* bias;
+    const float* skip;
     float* y;
     __nv_bfloat16 *yh, *yl;
     int M, kbeg, kend, z;
@@ -56,7 +59,8 @@ struct FwdProb {
       int iy = (int)(oy * g.S + ky) - g.PH, ix = (int)(ox * g.S + kx) - g.PW;
       if ((unsigned)iy >= (unsigned)g.IH || (unsigned)ix >= (unsigned)g.IW) return 0.f;
       int64_t idx = (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + c;
-      return xu ? (float)__ldg(xu + idx) : __ldg(xf + idx);
+      const float v = xu ? (float)__ldg(xu + idx) : __ldg(xf + idx);
+      return p->relu_in ? fmaxf(v, 0.f) : v;
     }
     __device__ __forceinline__ float loadB(int k, int n) const {
       if (k >= kend || n >= p->N) return 0.f;
@@ -66,6 +70,7 @@ struct FwdProb {
       if (m >= M || n >= p->N) return;
       float v = acc * p->scale + __ldg(bias + n);
       if (p->relu) v = fmaxf(v, 0.f);
+      if (skip) v += __ldg(skip + (int64_t)m * p->N + n);
       y[(int64_t)m * p->N + n] = v;
       if (yh) tc::st1_planes(yh + (int64_t)m * p->N + n, yl + (int64_t)m * p->N + n, v);
     }
@@ -81,6 +86,7 @@ struct FwdProb {
     c.xu = x_u8 ? x.get<uint8_t>(z) : nullptr;
     c.xf = x_u8 ? nullptr : x.get<float>(z);
     c.y = y + (int64_t)z * ystride;
+    c.skip = skip ? skip + (int64_t)z * ystride : nullptr;
     c.yh = yh ? yh + (int64_t)z * ystride : nullptr;
     c.yl = yl ? yl + (int64_t)z * ystride : nullptr;
     c.M = M;
@@ -100,6 +106,7 @@ struct WgradProb {
   float* gout;      // grad arena base; row m of the [Kd+1, OC] result goes to gout[z*gstride + w_off + m*OC + n]
   int64_t gstride, w_off;
   float scale;      // 1/255 for the u8/255 first layer (applied to kernel rows only)
+  int relu_in;      // the layer read relu(x)
   int nz, S;
   int M, N, K, kchunk;
 
@@ -122,7 +129,8 @@ struct WgradProb {
       int iy = (int)(oy * g.S + ky) - g.PH, ix = (int)(ox * g.S + kx) - g.PW;
       if ((unsigned)iy >= (unsigned)g.IH || (unsigned)ix >= (unsigned)g.IW) return 0.f;
       int64_t idx = (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + c;
-      return xu ? (float)__ldg(xu + idx) : __ldg(xf + idx);
+      const float v = xu ? (float)__ldg(xu + idx) : __ldg(xf + idx);
+      return p->relu_in ? fmaxf(v, 0.f) : v;
     }
     __device__ __forceinline__ float loadB(int k, int n) const {
       if (k >= kend || n >= p->N) return 0.f;
@@ -158,6 +166,8 @@ struct DgradProb {
   NetPtr w;         // head arena base (online)
   int64_t w_off;
   const float* xact;  // layer input activations (relu outputs) [nz][B*IH*IW*IC] for the mask
+  int mask;           // 1: dx *= (xact > 0) (the input went through a relu on its way into this layer); 0: linear input
+  const float* add;   // optional [nz][..] gradient that reaches the same activation through a residual connection: dx += add
   float* dx;          // same shape
   __nv_bfloat16 *dxh, *dxl;  // optional planes of dx
   int64_t xstride;
@@ -174,6 +184,7 @@ struct DgradProb {
     const float* dy;
     const float* wk;
     const float* xact;
+    const float* add;
     float* dx;
     __nv_bfloat16 *dxh, *dxl;
     int M, kbeg, kend, z;
@@ -219,7 +230,8 @@ struct DgradProb {
       int iy, ix;
       rowdec(m, b, iy, ix);
       int64_t idx = (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + n;
-      const float o = xact[idx] > 0.f ? acc : 0.f;  // relu'(0) = 0 as in jax
+      float o = (!p->mask || xact[idx] > 0.f) ? acc : 0.f;  // relu'(0) = 0 as in jax
+      if (add) o += add[idx];
       dx[idx] = o;
       if (dxh) tc::st1_planes(dxh + idx, dxl + idx, o);
     }
@@ -239,6 +251,7 @@ struct DgradProb {
     c.dy = dy + (int64_t)z * dystride;
     c.wk = w.get<float>(z) + w_off;
     c.xact = xact + (int64_t)z * xstride;
+    c.add = add ? add + (int64_t)z * xstride : nullptr;
     c.dx = dx + (int64_t)z * xstride;
     c.dxh = dxh ? dxh + (int64_t)z * xstride : nullptr;
     c.dxl = dxl ? dxl + (int64_t)z * xstride : nullptr;
@@ -375,4 +388,70 @@ static inline cudaError_t launch_gemm_simt(const P& p, int gridz, float* part, i
     gemm_simt_kernel<64, 64, A_KFAST, B_KFAST, P><<<grid, 256, 0, st>>>(p, part, tickets);
   }
   return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------
+// max-pool k x k / s, SAME (-inf) padding (flax nn.max_pool, architectures/dqn.py:20), NHWC fp32, nz nets.
+// The backward pass routes dy to the FIRST maximum of its window in (ky, kx) row-major order (what a strict > scan finds).
+struct PoolArgs {
+  int nz, B, IH, IW, C, OH, OW, PH, PW, K, S;
+  const float* x;   // [nz][B][IH][IW][C]
+  float* y;         // [nz][B][OH][OW][C]   (forward)
+  const float* dy;  // backward
+  float* dx;
+  int64_t xstride, ystride;  // floats between nets
+};
+__device__ __forceinline__ int pool_argmax(const PoolArgs& a, const float* xb, int oy, int ox, int c, float* best_out) {
+  float best = -INFINITY;
+  int arg = -1;
+  for (int ky = 0; ky < a.K; ++ky) {
+    const int iy = oy * a.S + ky - a.PH;
+    if ((unsigned)iy >= (unsigned)a.IH) continue;
+    for (int kx = 0; kx < a.K; ++kx) {
+      const int ix = ox * a.S + kx - a.PW;
+      if ((unsigned)ix >= (unsigned)a.IW) continue;
+      const float v = __ldg(xb + ((int64_t)iy * a.IW + ix) * a.C + c);
+      if (arg < 0 || v > best) best = v, arg = iy * a.IW + ix;
+    }
+  }
+  if (best_out) *best_out = best;
+  return arg;
+}
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const PoolArgs a) {
+  const int64_t per = (int64_t)a.B * a.OH * a.OW * a.C, total = per * a.nz;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i / per);
+    int64_t r = i - (int64_t)z * per;
+    const int c = (int)(r % a.C);
+    r /= a.C;
+    const int ox = (int)(r % a.OW);
+    r /= a.OW;
+    const int oy = (int)(r % a.OH), b = (int)(r / a.OH);
+    float best;
+    pool_argmax(a, a.x + (int64_t)z * a.xstride + (int64_t)b * a.IH * a.IW * a.C, oy, ox, c, &best);
+    a.y[(int64_t)z * a.ystride + (i - (int64_t)z * per)] = best;
+  }
+}
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const PoolArgs a) {
+  // one thread per INPUT element: the (at most ceil(K/S)^2) windows that contain it, gathered -- no atomics, fixed order
+  const int64_t per = (int64_t)a.B * a.IH * a.IW * a.C, total = per * a.nz;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i / per);
+    int64_t r = i - (int64_t)z * per;
+    const int c = (int)(r % a.C);
+    r /= a.C;
+    const int ix = (int)(r % a.IW);
+    r /= a.IW;
+    const int iy = (int)(r % a.IH), b = (int)(r / a.IH);
+    const float* xb = a.x + (int64_t)z * a.xstride + (int64_t)b * a.IH * a.IW * a.C;
+    const float* dyb = a.dy + (int64_t)z * a.ystride + (int64_t)b * a.OH * a.OW * a.C;
+    // windows oy with oy*S - PH <= iy <= oy*S - PH + K - 1
+    const int oy_lo = max(0, (iy + a.PH - a.K + a.S) / a.S), oy_hi = min(a.OH - 1, (iy + a.PH) / a.S);
+    const int ox_lo = max(0, (ix + a.PW - a.K + a.S) / a.S), ox_hi = min(a.OW - 1, (ix + a.PW) / a.S);
+    float g = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy)
+      for (int ox = ox_lo; ox <= ox_hi; ++ox)
+        if (pool_argmax(a, xb, oy, ox, c, nullptr) == iy * a.IW + ix) g += __ldg(dyb + ((int64_t)oy * a.OW + ox) * a.C + c);
+    a.dx[(int64_t)z * a.xstride + (i - (int64_t)z * per)] = g;
+  }
 }

@@ -50,7 +50,7 @@ static int build_layers(idqn_handle* h) {
     for (int i = 0; i < 3; ++i) {
       Layer& l = h->layers[L++];
       memset(&l, 0, sizeof(l));
-      l.is_conv = 1;
+      l.is_conv = 1, l.relu_out = 1, l.skip_from = -1;
       ConvGeom& g = l.g;
       g.B = c.batch_size;
       g.IH = ih, g.IW = iw, g.IC = ic;
@@ -62,6 +62,40 @@ static int build_layers(idqn_handle* h) {
       finish_geom(g);
       snprintf(l.name, sizeof(l.name), "Conv_%d", i);
       ih = g.OH, iw = g.OW, ic = g.OC;
+    }
+    start = 3;
+    h->in_elems = (int64_t)c.obs[0] * c.obs[1] * c.obs[2];
+  } else if (c.arch == IDQN_ARCH_IMPALA) {
+    // architectures/dqn.py:54-60: Stack(features[0]), Stack(features[1]), relu(Stack(features[2])); a Stack (:7-29) is
+    // Conv_0 3x3 (no activation), max-pool 3x3 / 2 SAME, then twice x -> x + Conv(relu(Conv(relu(x))))
+    REQUIRE(c.n_features >= 3, "impala needs >= 3 features (architectures/dqn.py:56-58)");
+    ih = c.obs[0], iw = c.obs[1], ic = c.obs[2];
+    for (int st = 0; st < 3; ++st) {
+      for (int j = 0; j < 6; ++j) {  // j: 0 = Conv_0, 1 = pool, 2..5 = Conv_1..Conv_4
+        REQUIRE(L < IDQN_MAX_LAYERS, "too many layers");
+        Layer& l = h->layers[L++];
+        memset(&l, 0, sizeof(l));
+        l.is_conv = 1, l.skip_from = -1;
+        ConvGeom& g = l.g;
+        g.B = c.batch_size;
+        g.IH = ih, g.IW = iw, g.IC = ic;
+        g.KH = g.KW = 3;
+        if (j == 1) {
+          l.kind = IDQN_LAYER_POOL;
+          g.S = 2, g.OC = ic;
+          snprintf(l.name, sizeof(l.name), "Stack_%d/pool", st);
+        } else {
+          g.S = 1, g.OC = c.features[st];
+          const int cj = j == 0 ? 0 : j - 1;
+          snprintf(l.name, sizeof(l.name), "Stack_%d/Conv_%d", st, cj);
+          if (cj == 1 || cj == 3) l.relu_in = 1, l.relu_out = 1;   // first conv of a block: relu(Conv(relu(x)))
+          if (cj == 2 || cj == 4) l.skip_from = L - 3;             // second conv of a block: + block input
+        }
+        same_pad(ih, g.KH, g.S, &g.OH, &g.PH);
+        same_pad(iw, g.KW, g.S, &g.OW, &g.PW);
+        finish_geom(g);
+        ih = g.OH, iw = g.OW, ic = g.OC;
+      }
     }
     start = 3;
     h->in_elems = (int64_t)c.obs[0] * c.obs[1] * c.obs[2];
@@ -77,6 +111,9 @@ static int build_layers(idqn_handle* h) {
     REQUIRE(L < IDQN_MAX_LAYERS, "too many layers");
     Layer& l = h->layers[L++];
     memset(&l, 0, sizeof(l));
+    l.skip_from = -1;
+    l.relu_out = i < c.n_features;                          // every Dense but the last (architectures/dqn.py:67-70)
+    l.relu_in = c.arch == IDQN_ARCH_IMPALA && i == start;   // relu(Stack_2(x)) feeds the trunk (:59)
     ConvGeom& g = l.g;
     g.B = c.batch_size;
     g.IH = g.IW = g.OH = g.OW = 1;
@@ -88,14 +125,18 @@ static int build_layers(idqn_handle* h) {
     fan_in = g.OC;
   }
   h->n_layers = L;
+  h->n_param_layers = 0;
   int64_t off = 0, aoff = 0;
   for (int i = 0; i < L; ++i) {
     Layer& l = h->layers[i];
     REQUIRE(l.g.OC > 0 && l.g.Kd > 0, "layer %d has an empty dimension", i);
-    off = (off + 31) / 32 * 32;  // 128-byte aligned layer start
-    l.w_off = off;
-    l.b_off = off + (int64_t)l.g.Kd * l.g.OC;  // bias directly after the kernel: [Kd+1, OC] block
-    off = l.b_off + l.g.OC;
+    if (l.kind == IDQN_LAYER_GEMM) {
+      h->param_layer[h->n_param_layers++] = i;
+      off = (off + 31) / 32 * 32;  // 128-byte aligned layer start
+      l.w_off = off;
+      l.b_off = off + (int64_t)l.g.Kd * l.g.OC;  // bias directly after the kernel: [Kd+1, OC] block
+      off = l.b_off + l.g.OC;
+    }
     l.act_off = aoff;
     l.act_size = (int64_t)c.batch_size * l.g.OH * l.g.OW * l.g.OC;
     aoff += (l.act_size + 31) / 32 * 32;
@@ -611,7 +652,7 @@ struct FwdIO {
 static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples, const FwdIO& io, int x_u8, int relu,
                             bool dry, int64_t* ws_part, int* ws_tick) {
   const Layer& l = h->layers[li];
-  const float scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;  // architectures/dqn.py:44
+  const float scale = (li == 0 && h->cfg.arch != IDQN_ARCH_FC) ? (1.0f / 255.0f) : 1.0f;  // architectures/dqn.py:44,57
   if (use_tc(h) && tc_conv_ok(l) && nsamples * l.g.OH * l.g.OW >= 64) {
     tcg::TcFwdConv p;
     p.g = l.g, p.g.B = nsamples;
@@ -672,6 +713,9 @@ static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples
   p.ystride = io.ystride;
   p.scale = scale;
   p.relu = relu;
+  p.relu_in = l.relu_in;
+  // the residual input lives in the same activation block as y (same base, same net stride)
+  p.skip = (l.skip_from >= 0 && io.y) ? io.y - l.act_off + h->layers[l.skip_from].act_off : nullptr;
   p.nz = nz;
   p.M = nsamples * l.g.OH * l.g.OW;
   p.N = l.g.OC;
@@ -687,6 +731,36 @@ static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples
   if (rc) return rc;
   CK((launch_gemm_simt<true, false>(p, nz * p.S, h->part, h->tickets, h->stream)));
   mark(h, "fwd_L%d", li);
+  return IDQN_OK;
+}
+
+// ---- max-pool (impala) ---------------------------------------------------------------------------------------------
+static PoolArgs pool_args(const Layer& l, int nz, int nsamples) {
+  PoolArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nz = nz, a.B = nsamples, a.IH = l.g.IH, a.IW = l.g.IW, a.C = l.g.IC, a.OH = l.g.OH, a.OW = l.g.OW;
+  a.PH = l.g.PH, a.PW = l.g.PW, a.K = l.g.KH, a.S = l.g.S;
+  return a;
+}
+static int launch_pool_fwd(idqn_handle* h, int li, int nz, int nsamples, const float* x, float* y, int64_t stride) {
+  PoolArgs a = pool_args(h->layers[li], nz, nsamples);
+  a.x = x, a.y = y, a.xstride = a.ystride = stride;
+  const int64_t total = (int64_t)nz * nsamples * a.OH * a.OW * a.C;
+  maxpool_fwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
+  CK(cudaGetLastError());
+  mark(h, "pool_fwd_L%d", li);
+  return IDQN_OK;
+}
+// dact of layer li-1 from dact of the pool layer li (online nets)
+static int launch_pool_bwd(idqn_handle* h, int li) {
+  const Layer &l = h->layers[li], &prev = h->layers[li - 1];
+  PoolArgs a = pool_args(l, h->K, h->B);
+  a.x = h->act + prev.act_off, a.dy = h->dact + l.act_off, a.dx = h->dact + prev.act_off;
+  a.xstride = a.ystride = h->act_stride;
+  const int64_t total = (int64_t)h->K * h->B * a.IH * a.IW * a.C;
+  maxpool_bwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
+  CK(cudaGetLastError());
+  mark(h, "pool_bwd_L%d", li);
   return IDQN_OK;
 }
 
@@ -706,7 +780,7 @@ static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_
     xl = NetPtr{h->act_lo + o, h->act_lo + o, h->act_stride, h->act_stride, K};
   }
   const int xu = (li == 0) ? x_u8 : 0;
-  const float scale = (li == 0 && h->cfg.arch == IDQN_ARCH_CNN) ? (1.0f / 255.0f) : 1.0f;
+  const float scale = (li == 0 && h->cfg.arch != IDQN_ARCH_FC) ? (1.0f / 255.0f) : 1.0f;
   const bool keep = (h->cfg.flags & IDQN_F_KEEP_GRADS) != 0;
   if (dense_wgrad_tma_ok(h, li)) {
     if (dry) return IDQN_OK;
@@ -786,6 +860,7 @@ static int launch_wgrad_layer(idqn_handle* h, int li, int x_u8, bool dry, int64_
   p.gstride = h->stride;
   p.w_off = l.w_off;
   p.scale = scale;
+  p.relu_in = l.relu_in;
   p.nz = K;
   p.M = l.g.Kd + 1;
   p.N = l.g.OC;
@@ -874,6 +949,11 @@ static int launch_dgrad_layer(idqn_handle* h, int li, bool img_dst = false) {
   p.w = NetPtr{h->online, h->online, h->stride, h->stride, K};
   p.w_off = l.w_off;
   p.xact = h->act + prev.act_off;
+  // relu' of the input: it was the previous layer's relu output, or this layer applied the relu itself (impala blocks)
+  p.mask = (l.relu_in || prev.relu_out) ? 1 : 0;
+  p.add = nullptr;
+  for (int j = li + 1; j < h->n_layers; ++j)  // a later layer that adds this activation to its output (residual)
+    if (h->layers[j].skip_from == li - 1) p.add = h->dact + h->layers[j].act_off;
   p.dx = h->dact + prev.act_off;
   p.dxh = h->dact_hi + prev.act_off, p.dxl = h->dact_lo + prev.act_off;
   p.xstride = h->act_stride;
@@ -991,7 +1071,13 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     io.wl = NetPtr{h->won_lo, h->wtg_lo, h->stride, h->stride, K};
     const int64_t o = h->layers[li].act_off;
     io.y = h->act + o, io.yh = h->act_hi + o, io.yl = h->act_lo + o, io.ystride = h->act_stride;
-    int rc = launch_fwd_layer(h, li, 2 * K, nh, B, io, li == 0 ? x_u8 : 0, 1, dry, ws_part, ws_tick);
+    if (h->layers[li].kind == IDQN_LAYER_POOL) {
+      if (dry) continue;
+      int rc = launch_pool_fwd(h, li, 2 * K, B, h->act + h->layers[li - 1].act_off, h->act + o, h->act_stride);
+      if (rc) return rc;
+      continue;
+    }
+    int rc = launch_fwd_layer(h, li, 2 * K, nh, B, io, li == 0 ? x_u8 : 0, h->layers[li].relu_out, dry, ws_part, ws_tick);
     if (rc) return rc;
   }
   // final layer + loss + its backward
@@ -1110,6 +1196,13 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
           if (overlapped) CK(cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
           return IDQN_OK;
         }
+      }
+      continue;
+    }
+    if (h->layers[li].kind == IDQN_LAYER_POOL) {  // no parameters: only the data gradient
+      if (!dry) {
+        int rc = launch_pool_bwd(h, li);
+        if (rc) return rc;
       }
       continue;
     }
@@ -1268,6 +1361,9 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   idqn_handle* h = new idqn_handle();
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
+  // impala runs on the fp32 CUDA-core implicit-GEMM kernels (gemm_simt.cuh) + the pool kernels: its pre-activation residual
+  // blocks and 3x3 / 1 convolutions over 1..64 channels are not what the tcgen05 paths were built for
+  if (cfg->arch == IDQN_ARCH_IMPALA) h->cfg.flags |= IDQN_F_SIMT_ONLY;
   h->K = cfg->n_heads, h->B = cfg->batch_size, h->A = cfg->n_actions;
   int rc = build_layers(h);
   if (rc) {
@@ -1380,6 +1476,7 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
     FwdIO nul;
     memset(&nul, 0, sizeof(nul));
     for (int li = 0; li < h->n_layers; ++li) {
+      if (h->layers[li].kind == IDQN_LAYER_POOL) continue;
       rc = launch_fwd_layer(h, li, 1, 1, B, nul, 0, 0, true, &part, &tickets);
       if (rc) return rc;
     }
@@ -1461,11 +1558,11 @@ extern "C" int idqn_destroy(idqn_handle* h) {
 }
 
 extern "C" int64_t idqn_arena_stride(const idqn_handle* h) { return h ? h->stride : 0; }
-extern "C" int idqn_leaf_count(const idqn_handle* h) { return h ? 2 * h->n_layers : 0; }
+extern "C" int idqn_leaf_count(const idqn_handle* h) { return h ? 2 * h->n_param_layers : 0; }
 extern "C" int idqn_leaf_info(const idqn_handle* h, int leaf, int64_t* offset, int64_t* size, int32_t shape[4],
                               int32_t* ndim, char name[16]) {
-  REQUIRE(h && leaf >= 0 && leaf < 2 * h->n_layers, "bad leaf index");
-  const Layer& l = h->layers[leaf / 2];
+  REQUIRE(h && leaf >= 0 && leaf < 2 * h->n_param_layers, "bad leaf index");
+  const Layer& l = h->layers[h->param_layer[leaf / 2]];
   if (leaf % 2 == 0) {
     *offset = l.w_off;
     *size = (int64_t)l.g.Kd * l.g.OC;
@@ -1789,7 +1886,10 @@ static int enqueue_apply(idqn_handle* h, int which, int head, int u8, int n) {
     io.yh = last ? nullptr : h->act_hi + o;
     io.yl = last ? nullptr : h->act_lo + o;
     io.ystride = 0;
-    rc = launch_fwd_layer(h, li, 1, 1, n, io, li == 0 ? u8 : 0, last ? 0 : 1, false, nullptr, nullptr);
+    if (h->layers[li].kind == IDQN_LAYER_POOL)
+      rc = launch_pool_fwd(h, li, 1, n, h->act + h->layers[li - 1].act_off, h->act + o, 0);
+    else
+      rc = launch_fwd_layer(h, li, 1, 1, n, io, li == 0 ? u8 : 0, last ? 0 : h->layers[li].relu_out, false, nullptr, nullptr);
     if (rc) return rc;
   }
   return IDQN_OK;

@@ -47,6 +47,20 @@ class Leaf:
         return f"Leaf(device, which={self._which}, shape={self.shape})"
 
 
+def _module(inner: Dict[str, Any], name: str, create: bool = False) -> Dict[str, Any]:
+    """The {"kernel", "bias"} dict of module ``name``; "Stack_0/Conv_1" is flax's nested ``inner["Stack_0"]["Conv_1"]``."""
+    node = inner
+    for part in name.split("/"):
+        node = node.setdefault(part, {}) if create else node[part]
+    return node
+
+
+def _map_leaves(fn, tree):
+    if isinstance(tree, dict):
+        return {k: _map_leaves(fn, v) for k, v in tree.items()}
+    return fn(tree)
+
+
 class Tree(dict):
     """``{"params": {"Conv_0": {"kernel": Leaf, "bias": Leaf}, ...}}`` backed by an engine arena.
 
@@ -54,9 +68,9 @@ class Tree(dict):
     owning agent's methods and no data moves; ``np.asarray(leaf)`` / ``to_host()`` copy out."""
 
     def __init__(self, engine: "Engine", which: int, squeeze: bool):
-        inner: Dict[str, Dict[str, Leaf]] = {}
+        inner: Dict[str, Any] = {}
         for i, info in enumerate(engine.leaves):
-            inner.setdefault(info["module"], {})[info["kind"]] = Leaf(engine, which, i, squeeze)
+            _module(inner, info["module"], create=True)[info["kind"]] = Leaf(engine, which, i, squeeze)
         super().__init__(params=inner)
         self._engine_ref = weakref.ref(engine)
         self._which = which
@@ -66,7 +80,7 @@ class Tree(dict):
         return self
 
     def to_host(self) -> Dict[str, Any]:
-        return {"params": {m: {k: np.asarray(v) for k, v in d.items()} for m, d in self["params"].items()}}
+        return {"params": _map_leaves(np.asarray, self["params"])}
 
     def is_view_of(self, engine: "Engine", which: int) -> bool:
         return self._engine_ref() is engine and self._which == which
@@ -97,10 +111,8 @@ class Engine:
                  learning_rate: float, gamma: float, update_horizon: int, adam_eps: float, batch_size: int = 32,
                  device: int = 0, flags: int = 0):
         self.lib = L.lib()
-        if architecture_type not in ("cnn", "fc"):
-            raise NotImplementedError(
-                f"architecture_type={architecture_type!r}: only 'cnn' and 'fc' have sm_100a kernels "
-                "('impala' is out of the hot-path scope, SURVEY §2 row 3)")
+        if architecture_type not in ("cnn", "fc", "impala"):
+            raise ValueError(f"architecture_type={architecture_type!r}: expected 'cnn', 'impala' or 'fc'")
         features = [int(f) for f in features]
         if int(n_actions) > L.MAX_ACTIONS:
             raise ValueError(f"n_actions={n_actions}: the fused final-layer kernels hold at most {L.MAX_ACTIONS} actions")
@@ -108,10 +120,10 @@ class Engine:
             raise ValueError("too many feature layers")
         obs = tuple(int(d) for d in np.atleast_1d(observation_dim))
         cfg = L.Config()
-        cfg.arch = L.ARCH_CNN if architecture_type == "cnn" else L.ARCH_FC
-        if architecture_type == "cnn":
+        cfg.arch = {"cnn": L.ARCH_CNN, "impala": L.ARCH_IMPALA, "fc": L.ARCH_FC}[architecture_type]
+        if architecture_type in ("cnn", "impala"):
             if len(obs) != 3:
-                raise ValueError("cnn needs observation_dim=(H, W, C)")
+                raise ValueError(f"{architecture_type} needs observation_dim=(H, W, C)")
             cfg.obs[:] = obs
         else:
             cfg.obs[:] = (int(np.prod(obs)), 1, 1)
@@ -167,7 +179,7 @@ class Engine:
     def upload_tree(self, which: int, tree, squeezed: bool = False) -> None:
         inner = tree["params"] if "params" in tree else tree
         for i, info in enumerate(self.leaves):
-            v = np.asarray(inner[info["module"]][info["kind"]], dtype=np.float32)
+            v = np.asarray(_module(inner, info["module"])[info["kind"]], dtype=np.float32)
             if squeezed:
                 v = v[None]
             if v.shape != (self.K,) + info["shape"]:
@@ -175,10 +187,10 @@ class Engine:
             self.upload_leaf(which, i, v)
 
     def download_tree(self, which: int, squeezed: bool = False) -> Dict[str, Any]:
-        inner: Dict[str, Dict[str, np.ndarray]] = {}
+        inner: Dict[str, Any] = {}
         for i, info in enumerate(self.leaves):
             a = self.download_leaf(which, i)
-            inner.setdefault(info["module"], {})[info["kind"]] = a[0] if squeezed else a
+            _module(inner, info["module"], create=True)[info["kind"]] = a[0] if squeezed else a
         return {"params": inner}
 
     def download_arena(self, which: int) -> np.ndarray:
@@ -192,6 +204,8 @@ class Engine:
         """[(B, OH, OW, OC)] of every hidden layer (the final Dense is fused into the loss kernel)."""
         from .architectures._shapes import CNN_SPECS, same_out
         shapes = []
+        if self.architecture_type == "impala":
+            raise NotImplementedError("download_activation is a cnn / fc parity aid")
         if self.architecture_type == "cnn":
             h, w, _ = self.obs_shape
             for i, (_, s) in enumerate(CNN_SPECS):

@@ -1,6 +1,6 @@
 """``DQNNet`` — the Q-network description and its stand-alone ``init`` / ``apply``
-(mirrors slimdqn/networks/architectures/dqn.py:32-70; 'cnn' :39-53 and 'fc' :61-63 have sm_100a kernels,
-'impala' :54-60 is outside the hot-path scope)."""
+(mirrors slimdqn/networks/architectures/dqn.py:32-70; 'cnn' :39-53 and 'fc' :61-63 run on the tcgen05 kernels,
+'impala' :7-29,54-60 on the fp32 CUDA-core kernels of the same engine)."""
 from __future__ import annotations
 
 import math
@@ -28,17 +28,25 @@ class DQNNet:
 
         obs = tuple(np.asarray(x).shape)
         rng = np.random.default_rng([int(v) for v in _prng.as_key(key)])
-        tree = {}
+        tree: Dict = {}
         for name, kshape, bshape in layer_shapes(obs, self.features, self.architecture_type, self.n_actions):
             rf = int(np.prod(kshape[:-2]))
             fan_in, fan_out = rf * kshape[-2], rf * kshape[-1]
-            if self.architecture_type == "cnn":
+            # impala: xavier-uniform for a Stack's first conv (:14-19) and the dense trunk (:55,68,70); the convs of the
+            # residual blocks (:25-26) pass no kernel_init = flax's lecun-normal
+            xavier = self.architecture_type == "cnn" or (
+                self.architecture_type == "impala" and (name.endswith("/Conv_0") or name.startswith("Dense_")))
+            if xavier:
                 bound = math.sqrt(6.0 / (fan_in + fan_out))
                 kernel = rng.uniform(-bound, bound, kshape)
             else:
                 std = math.sqrt(1.0 / fan_in) / 0.87962566103423978
                 kernel = _truncated_normal(rng, kshape) * std
-            tree[name] = {"kernel": kernel.astype(np.float32), "bias": np.zeros(bshape, np.float32)}
+            node = tree
+            parts = name.split("/")
+            for part in parts[:-1]:  # flax sub-module nesting: "Stack_0/Conv_1" -> tree["Stack_0"]["Conv_1"]
+                node = node.setdefault(part, {})
+            node[parts[-1]] = {"kernel": kernel.astype(np.float32), "bias": np.zeros(bshape, np.float32)}
         return {"params": tree}
 
     # -- stand-alone forward (tests, compute_target/loss helpers) -------------------------------------

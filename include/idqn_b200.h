@@ -36,6 +36,7 @@ extern "C" {
 
 #define IDQN_ARCH_FC 0     /* architectures/dqn.py:61-63 */
 #define IDQN_ARCH_CNN 1    /* architectures/dqn.py:39-53 */
+#define IDQN_ARCH_IMPALA 2 /* architectures/dqn.py:7-29,54-60: three residual stacks (fp32 CUDA-core kernels; not a benchmark config) */
 #define IDQN_MAX_FEATURES 8
 
 /* which per-head arena a transfer addresses */

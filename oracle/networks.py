@@ -9,7 +9,7 @@ cross-checked against a second restatement that shares nothing with it
 committed float64 fixtures ``tests/golden/network_*.npz`` — which pins the two
 restatements and the CUDA path to each other, not to JAX:
 
-* ``slimdqn/networks/architectures/dqn.py:37-70``  -> :func:`apply`
+* ``slimdqn/networks/architectures/dqn.py:37-70``  -> :func:`apply` ('cnn', 'fc' and -- ``:7-29,54-60`` -- 'impala')
 * ``slimdqn/networks/idqn.py:13-24``               -> :func:`shift_params`, :func:`sync_target_params`
 * ``slimdqn/networks/idqn.py:96-124``              -> :func:`learn_on_batch`, :func:`loss_on_batch`,
                                                       :func:`loss`, :func:`compute_target`
@@ -17,8 +17,8 @@ restatements and the CUDA path to each other, not to JAX:
 * ``slimdqn/networks/dqn.py:41-92``                -> the same functions with ``K`` axis absent
 
 Parameters are nested dicts of numpy arrays in the Flax layout
-``{"params": {"Conv_0": {"kernel": [kh,kw,in,out], "bias": [out]}, ...}}``; the i-DQN
-functions take leaves with a leading K axis.
+``{"params": {"Conv_0": {"kernel": [kh,kw,in,out], "bias": [out]}, ...}}`` (impala: one more level,
+``{"Stack_0": {"Conv_0": ..., ..., "Conv_4": ...}, ...}``); the i-DQN functions take leaves with a leading K axis.
 """
 from __future__ import annotations
 
@@ -55,6 +55,18 @@ def layer_shapes(observation_dim, features: Sequence[int], architecture_type: st
             h, w, c = same_pad(h, k, s)[0], same_pad(w, k, s)[0], features[i]
         in_dim = h * w * c
         start = 3
+    elif architecture_type == "impala":
+        # architectures/dqn.py:54-60: Stack(features[0..2]); a Stack (:7-29) is Conv_0, max-pool, then two residual blocks of
+        # two convs each (flax auto-names them Conv_1..Conv_4 in creation order); every conv 3x3, stride 1, SAME
+        h, w, c = observation_dim
+        for i in range(3):
+            f = features[i]
+            layers.append((f"Stack_{i}/Conv_0", (3, 3, c, f), (f,)))
+            for j in range(1, 5):
+                layers.append((f"Stack_{i}/Conv_{j}", (3, 3, f, f), (f,)))
+            h, w, c = same_pad(h, 3, 2)[0], same_pad(w, 3, 2)[0], f  # the 3x3 / 2 SAME max-pool (:20)
+        in_dim = h * w * c
+        start = 3
     elif architecture_type == "fc":
         in_dim = int(np.prod(observation_dim))
         start = 0
@@ -80,7 +92,11 @@ def init_params(rng: np.random.Generator, observation_dim, features, architectur
         for name, kshape, bshape in layer_shapes(observation_dim, features, architecture_type, n_actions):
             rf = int(np.prod(kshape[:-2]))
             fan_in, fan_out = rf * kshape[-2], rf * kshape[-1]
-            if architecture_type == "cnn":
+            # impala: xavier-uniform for the first conv of a Stack (:14-19) and the dense trunk (:55,68,70), flax's default
+            # lecun-normal for the convs of the residual blocks (:25-26 pass no kernel_init)
+            xavier = architecture_type == "cnn" or (architecture_type == "impala" and
+                                                    (name.endswith("/Conv_0") or name.startswith("Dense_")))
+            if xavier:
                 a = math.sqrt(6.0 / (fan_in + fan_out))
                 kern = rng.uniform(-a, a, kshape)
             else:
@@ -88,7 +104,7 @@ def init_params(rng: np.random.Generator, observation_dim, features, architectur
                 kern = np.clip(rng.standard_normal(kshape), -2, 2) * std
             bias = rng.standard_normal(bshape) * bias_scale
             tree[name] = {"kernel": kern.astype(np.float32), "bias": bias.astype(np.float32)}
-        return {"params": tree}
+        return {"params": nest_modules(tree)}
     if n_networks is None:
         return one()
     heads = [one() for _ in range(n_networks)]
@@ -98,6 +114,18 @@ def init_params(rng: np.random.Generator, observation_dim, features, architectur
 # ---------------------------------------------------------------------------------------
 # tiny pytree helpers (nested dicts only)
 # ---------------------------------------------------------------------------------------
+
+def nest_modules(flat: dict) -> dict:
+    """{"Stack_0/Conv_0": m, "Dense_0": n} -> {"Stack_0": {"Conv_0": m}, "Dense_0": n} (flax sub-module nesting)."""
+    out: dict = {}
+    for name, mod in flat.items():
+        node = out
+        parts = name.split("/")
+        for part in parts[:-1]:
+            node = node.setdefault(part, {})
+        node[parts[-1]] = mod
+    return out
+
 
 def tree_map(fn, *trees):
     t0 = trees[0]
@@ -134,8 +162,16 @@ def _conv_same(x_nhwc: torch.Tensor, kernel_hwio: torch.Tensor, bias: torch.Tens
     _, wlo, whi = same_pad(x_nhwc.shape[2], kw, stride)
     x = x_nhwc.permute(0, 3, 1, 2)
     x = F.pad(x, (wlo, whi, hlo, hhi))
-    y = F.conv2d(x, kernel_hwio.permute(3, 2, 0, 1), bias, stride=stride)
+    y = F.conv2d(x, kernel_hwio.permute(3, 2, 0, 1).contiguous(), bias, stride=stride)  # (contiguous: torch's 1-channel CPU path insists)
     return y.permute(0, 2, 3, 1)
+
+
+def _max_pool_same(x_nhwc: torch.Tensor, k: int = 3, stride: int = 2) -> torch.Tensor:
+    """flax.linen.max_pool(x, (3, 3), strides=(2, 2), padding="SAME") (architectures/dqn.py:20): -inf padding."""
+    _, hlo, hhi = same_pad(x_nhwc.shape[1], k, stride)
+    _, wlo, whi = same_pad(x_nhwc.shape[2], k, stride)
+    x = F.pad(x_nhwc.permute(0, 3, 1, 2), (wlo, whi, hlo, hhi), value=float("-inf"))
+    return F.max_pool2d(x, k, stride).permute(0, 2, 3, 1)
 
 
 def _to_torch(tree, dtype):
@@ -166,6 +202,20 @@ def apply_t(p: Dict[str, Dict[str, torch.Tensor]], x: torch.Tensor, architecture
         for i, (_, s) in enumerate(CNN_SPECS):
             x = act(_conv_same(x, p[f"Conv_{i}"]["kernel"], p[f"Conv_{i}"]["bias"], s))
         x = x.reshape(x.shape[0], -1)  # (h,w,c) order, architectures/dqn.py:53
+    elif architecture_type == "impala":
+        x = x / 255.0  # architectures/dqn.py:57
+        for i in range(3):
+            s = p[f"Stack_{i}"]
+            x = _conv_same(x, s["Conv_0"]["kernel"], s["Conv_0"]["bias"], 1)  # :14-19 (no activation)
+            x = _max_pool_same(x)  # :20
+            for b in range(2):  # :22-27
+                block_input = x
+                x = act(x)
+                x = act(_conv_same(x, s[f"Conv_{1 + 2 * b}"]["kernel"], s[f"Conv_{1 + 2 * b}"]["bias"], 1))
+                x = _conv_same(x, s[f"Conv_{2 + 2 * b}"]["kernel"], s[f"Conv_{2 + 2 * b}"]["bias"], 1)
+                x = x + block_input
+        x = act(x)  # :59
+        x = x.reshape(x.shape[0], -1)  # :60
     elif architecture_type == "fc":
         x = x.reshape(x.shape[0], -1)  # jnp.squeeze of the trailing stack axis, :65
     else:

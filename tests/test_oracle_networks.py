@@ -196,3 +196,62 @@ def test_numpy_oracle_reproduces_the_committed_fixture(name, steps):
 @pytest.mark.parametrize("name", ["mlp_k3", "cnn_k1"])
 def test_torch_fp32_oracle_free_running_stays_inside_the_stated_envelope(name):
     GN.check(GN.run_chain(name, TorchChain(name)))
+
+
+# ---- impala (§8f N4): the two independent restatements against each other, and the pool / residual rules by hand ----------
+
+def test_impala_layer_table_and_naive_maxpool():
+    """Layer table in flax creation order; the SAME max-pool (architectures/dqn.py:20) against a window-by-window scan with
+    -inf padding, on the three padding cases the 84 -> 42 -> 21 -> 11 chain meets ((0,1), (0,1), (1,1)) and an odd width."""
+    names = [n for n, _, _ in O.layer_shapes((84, 84, 4), [32, 64, 64, 512], "impala", 6)]
+    assert names == [f"Stack_{i}/Conv_{j}" for i in range(3) for j in range(5)] + ["Dense_0", "Dense_1"]
+    shapes = {n: k for n, k, _ in O.layer_shapes((84, 84, 4), [32, 64, 64, 512], "impala", 6)}
+    assert shapes["Stack_0/Conv_0"] == (3, 3, 4, 32) and shapes["Stack_1/Conv_0"] == (3, 3, 32, 64)
+    assert shapes["Stack_2/Conv_4"] == (3, 3, 64, 64) and shapes["Dense_0"] == (11 * 11 * 64, 512)
+    rng = np.random.default_rng(2)
+    for H, W in ((84, 84), (42, 42), (21, 21), (7, 10)):
+        x = rng.standard_normal((2, H, W, 3))
+        got = O._max_pool_same(torch.as_tensor(x)).numpy()
+        OH, lo_h, _ = O.same_pad(H, 3, 2)
+        OW, lo_w, _ = O.same_pad(W, 3, 2)
+        want = np.full((2, OH, OW, 3), -np.inf)
+        for oy in range(OH):
+            for ox in range(OW):
+                ys = [y for y in range(oy * 2 - lo_h, oy * 2 - lo_h + 3) if 0 <= y < H]
+                xs = [v for v in range(ox * 2 - lo_w, ox * 2 - lo_w + 3) if 0 <= v < W]
+                want[:, oy, ox, :] = x[:, ys][:, :, xs].max(axis=(1, 2))
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(N.maxpool_forward(x)[0], want)
+
+
+@pytest.mark.parametrize("obs,feats,A", [((21, 19, 4), [3, 5, 2, 7], 4), ((30, 30, 2), [1, 9, 4, 3], 9)])
+def test_impala_two_independent_oracles_agree_in_float64(obs, feats, A):
+    """torch autograd + F.conv2d / F.max_pool2d vs NumPy patch gathers with a hand-derived backward (pool routing to the first
+    maximum, residual gradient fan-in, pre-activation gates): Q-values, loss and every gradient to 1e-12."""
+    rng = np.random.default_rng(17)
+    p = O.init_params(rng, obs, feats, "impala", A, bias_scale=0.1)
+    t = O.init_params(rng, obs, feats, "impala", A, bias_scale=0.1)
+    B = 5
+    batch = dict(state=rng.uniform(0, 255, (B,) + obs), next_state=rng.uniform(0, 255, (B,) + obs),
+                 action=rng.integers(0, A, B), reward=rng.uniform(-1, 1, B), is_terminal=rng.random(B) < 0.3)
+    np.testing.assert_allclose(O.apply(p, batch["state"], "impala", dtype=torch.float64), N.impala_forward(p, batch["state"]),
+                               rtol=1e-12, atol=1e-13)
+    l1, g1 = O.loss_and_grad(p, t, batch, "impala", 0.94, 1, dtype=torch.float64)
+    l2, g2 = N.impala_loss_and_grad(p, t, batch, 0.94, 1)
+    assert abs(l1 - l2) <= 1e-12 * max(1.0, abs(l1))
+
+    def walk(a, b, path=""):
+        if isinstance(a, dict):
+            assert set(a) == set(b), path
+            for k in a:
+                walk(a[k], b[k], f"{path}/{k}")
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12 * max(1.0, float(np.abs(a).max())), err_msg=path)
+    walk(g1, g2)
+    # one step of the K-vmapped update on the nested tree (tree helpers must recurse through the Stack level)
+    pk, tk = O.tree_stack([p, t]), O.tree_stack([t, p])
+    opt = O.init_optimizer_state(pk)
+    p2, o2, losses = O.learn_on_batch(pk, tk, opt, batch, "impala", 0.94, 1, 1e-3, 1e-5)
+    assert losses.shape == (2,) and o2["count"].tolist() == [1, 1]
+    assert p2["params"]["Stack_2"]["Conv_3"]["kernel"].shape == (2, 3, 3, feats[2], feats[2])
+    assert not np.array_equal(p2["params"]["Stack_0"]["Conv_0"]["kernel"], pk["params"]["Stack_0"]["Conv_0"]["kernel"])
