@@ -612,6 +612,27 @@ def other_configs_leg(iDQN, rb, timed, args, local):
 
     ms, _, _, _ = timed(ag._engine, fn_mlp, steps, 10, 1)
     out["configs[0] Lunar Lander MLP K=3 (host batches)"] = round(ms / steps * 1e3, 2)
+    del ag
+    # the reference's third architecture (architectures/dqn.py:7-29,54-60; only its unit tests use it): IMPALA at the Atari
+    # sizes, K = 1, on the fp32 CUDA-core kernels -- 52 GFLOP per head-step (13x NatureCNN), not a tuned path
+    ag = iDQN(0, OBS, A, 1, FEATS, "impala", LR, GAMMA, 1, 1, T_FREQ, D_FREQ, EPS, device=local)
+    ib = [synthetic_batch(np.random.default_rng(40 + i)) for i in range(2)]
+
+    class IBuf:
+        i = 0
+
+        def sample(self):
+            IBuf.i += 1
+            return ib[IBuf.i % 2]
+
+    ibuf = IBuf()
+
+    def fn_impala(step):
+        ag.update_online_params(step, ibuf)
+        ag.update_target_params(step)
+
+    ms, _, _, _ = timed(ag._engine, fn_impala, 20, 3, 1)
+    out["IMPALA K=1 (fp32 CUDA-core kernels, host batches)"] = round(ms / 20 * 1e3, 2)
     return out
 
 

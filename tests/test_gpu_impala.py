@@ -60,6 +60,12 @@ def test_impala_tree_layout_and_apply():
             got = agent._engine.apply(L.ONLINE, k, x)
             want = O.apply(O.tree_index(params, k), x, "impala")
             np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+    # the model pickle (experiments/base/utils.py:123-134: pickle.dump(agent.get_model())) round-trips through a new agent
+    import pickle
+    model = pickle.loads(pickle.dumps(agent.get_model()))
+    other = iDQN(99, obs, A, K, feats, "impala", 1e-3, 0.94, 1, 1, 1, 1, batch_size=8)
+    other.params = model["params"]
+    np.testing.assert_array_equal(other._engine.apply(L.ONLINE, 1, x), agent._engine.apply(L.ONLINE, 1, x))
 
 
 @pytest.mark.parametrize("u8", [False, True])
