@@ -34,6 +34,7 @@ struct FwdProb {
   float scale;
   int relu;
   int relu_in;        // the conv reads relu(x) (impala's pre-activation blocks)
+  int planes_relu;    // the consumer reads relu(y): the planes hold relu(y), y stays linear
   const float* skip;  // optional residual input, same layout / net stride as y: y += skip (after the activation)
   int nz, S;  // nets, split-K factor
   int M, N, K, kchunk;
@@ -72,7 +73,7 @@ struct FwdProb {
       if (p->relu) v = fmaxf(v, 0.f);
       if (skip) v += __ldg(skip + (int64_t)m * p->N + n);
       y[(int64_t)m * p->N + n] = v;
-      if (yh) tc::st1_planes(yh + (int64_t)m * p->N + n, yl + (int64_t)m * p->N + n, v);
+      if (yh) tc::st1_planes(yh + (int64_t)m * p->N + n, yl + (int64_t)m * p->N + n, p->planes_relu ? fmaxf(v, 0.f) : v);
     }
   };
   __device__ __forceinline__ Ctx ctx(int zz) const {
@@ -399,6 +400,8 @@ struct PoolArgs {
   float* y;         // [nz][B][OH][OW][C]   (forward)
   const float* dy;  // backward
   float* dx;
+  __nv_bfloat16 *ph, *pl;    // optional bf16 hi / lo planes of the output (forward: of y, relu'd if planes_relu; backward: of dx)
+  int planes_relu;
   int64_t xstride, ystride;  // floats between nets
 };
 __device__ __forceinline__ int pool_argmax(const PoolArgs& a, const float* xb, int oy, int ox, int c, float* best_out) {
@@ -429,7 +432,9 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const PoolArgs a) {
     const int oy = (int)(r % a.OH), b = (int)(r / a.OH);
     float best;
     pool_argmax(a, a.x + (int64_t)z * a.xstride + (int64_t)b * a.IH * a.IW * a.C, oy, ox, c, &best);
-    a.y[(int64_t)z * a.ystride + (i - (int64_t)z * per)] = best;
+    const int64_t o = (int64_t)z * a.ystride + (i - (int64_t)z * per);
+    a.y[o] = best;
+    if (a.ph) tc::st1_planes(a.ph + o, a.pl + o, a.planes_relu ? fmaxf(best, 0.f) : best);
   }
 }
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const PoolArgs a) {
@@ -452,6 +457,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const PoolArgs a) {
     for (int oy = oy_lo; oy <= oy_hi; ++oy)
       for (int ox = ox_lo; ox <= ox_hi; ++ox)
         if (pool_argmax(a, xb, oy, ox, c, nullptr) == iy * a.IW + ix) g += __ldg(dyb + ((int64_t)oy * a.OW + ox) * a.C + c);
-    a.dx[(int64_t)z * a.xstride + (i - (int64_t)z * per)] = g;
+    const int64_t o = (int64_t)z * a.xstride + (i - (int64_t)z * per);
+    a.dx[o] = g;
+    if (a.ph) tc::st1_planes(a.ph + o, a.pl + o, g);
   }
 }

@@ -86,6 +86,8 @@ struct TcFwdConv {
   int64_t ystride;
   float scale;
   int relu;
+  const float* skip;  // optional residual input (same indexing as y): y += skip after the activation (impala blocks)
+  int planes_relu;    // the consumer reads relu(y) (pre-activation block / trunk): the PLANES hold relu(y), y stays linear
   int nh;           // heads concatenated along N inside one group (they share the input)
   int hpt;          // heads per N tile
   int M, K, NT;     // NT = UMMA N (multiple of 16)
@@ -161,8 +163,21 @@ struct TcFwdConv {
         for (int i = 0; i < 16; ++i) r[i] = fmaxf(r[i], 0.f);
       }
       const int64_t o = (int64_t)net * ystride + (int64_t)m * g.OC + oc;
+      if (skip) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 sk = __ldg(reinterpret_cast<const float4*>(skip + o) + q);
+          r[4 * q] += sk.x, r[4 * q + 1] += sk.y, r[4 * q + 2] += sk.z, r[4 * q + 3] += sk.w;
+        }
+      }
       st16(y + o, r);
-      if (yh) st16_planes(yh + o, yl + o, r);
+      if (yh) {
+        if (planes_relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = fmaxf(r[i], 0.f);
+        }
+        st16_planes(yh + o, yl + o, r);
+      }
       return;
     }
 #pragma unroll
@@ -173,8 +188,9 @@ struct TcFwdConv {
       float r = v[i] * scale + __ldg(w.get<float>(net) + b_off + oc);
       if (relu) r = fmaxf(r, 0.f);
       const int64_t o = (int64_t)net * ystride + (int64_t)m * g.OC + oc;
+      if (skip) r += __ldg(skip + o);
       y[o] = r;
-      if (yh) st1_planes(yh + o, yl + o, r);
+      if (yh) st1_planes(yh + o, yl + o, planes_relu ? fmaxf(r, 0.f) : r);
     }
   }
 };
@@ -188,6 +204,8 @@ struct TcDgradConv {
   NetPtr wh, wl;          // online weight planes
   int64_t w_off;
   const float* xact;      // layer input (relu output) fp32, for the mask
+  int mask;               // 1: dx *= (xact > 0); 0: the input entered the layer linearly (impala: first conv of a Stack)
+  const float* add;       // optional gradient reaching the same activation through a residual connection: dx += add
   float* dx;
   bf16 *dxh, *dxl;
   int64_t xstride;
@@ -257,9 +275,13 @@ struct TcDgradConv {
       float o[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 xa = __ldg(reinterpret_cast<const float4*>(xact + base + n0) + q);
+        const float4 xa = mask ? __ldg(reinterpret_cast<const float4*>(xact + base + n0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
         o[4 * q] = xa.x > 0.f ? v[4 * q] : 0.f, o[4 * q + 1] = xa.y > 0.f ? v[4 * q + 1] : 0.f;
         o[4 * q + 2] = xa.z > 0.f ? v[4 * q + 2] : 0.f, o[4 * q + 3] = xa.w > 0.f ? v[4 * q + 3] : 0.f;
+        if (add) {
+          const float4 ad = __ldg(reinterpret_cast<const float4*>(add + base + n0) + q);
+          o[4 * q] += ad.x, o[4 * q + 1] += ad.y, o[4 * q + 2] += ad.z, o[4 * q + 3] += ad.w;
+        }
       }
       st16(dx + base + n0, o);
       st16_planes(dxh + base + n0, dxl + base + n0, o);
@@ -269,7 +291,8 @@ struct TcDgradConv {
     for (int i = 0; i < 16; ++i) {
       const int n = n0 + i;
       if (n >= g.IC) break;
-      const float o = xact[base + n] > 0.f ? v[i] : 0.f;  // relu'(0) = 0 as in jax
+      float o = (!mask || xact[base + n] > 0.f) ? v[i] : 0.f;  // relu'(0) = 0 as in jax
+      if (add) o += add[base + n];
       dx[base + n] = o;
       st1_planes(dxh + base + n, dxl + base + n, o);
     }

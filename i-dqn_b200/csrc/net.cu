@@ -649,9 +649,13 @@ struct FwdIO {
   int64_t ystride;
 };
 
+// the consumer of layer li reads relu(output): its planes hold relu(y) while the fp32 activation stays linear (residual input)
+static bool planes_relu_of(const idqn_handle* h, int li) { return li + 1 < h->n_layers && h->layers[li + 1].relu_in; }
+
 static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples, const FwdIO& io, int x_u8, int relu,
                             bool dry, int64_t* ws_part, int* ws_tick) {
   const Layer& l = h->layers[li];
+  const float* skip = (l.skip_from >= 0 && io.y) ? io.y - l.act_off + h->layers[l.skip_from].act_off : nullptr;
   const float scale = (li == 0 && h->cfg.arch != IDQN_ARCH_FC) ? (1.0f / 255.0f) : 1.0f;  // architectures/dqn.py:44,57
   if (use_tc(h) && tc_conv_ok(l) && nsamples * l.g.OH * l.g.OW >= 64) {
     tcg::TcFwdConv p;
@@ -659,6 +663,7 @@ static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples
     p.xh = io.xh, p.xl = io.xl, p.wh = io.wh, p.wl = io.wl, p.w = io.w;
     p.w_off = l.w_off, p.b_off = l.b_off;
     p.y = io.y, p.yh = io.yh, p.yl = io.yl, p.ystride = io.ystride, p.scale = scale, p.relu = relu;
+    p.skip = skip, p.planes_relu = planes_relu_of(h, li);
     p.nh = nh;
     p.hpt = std::max(1, std::min(nh, 256 / l.g.OC));
     p.M = nsamples * l.g.OH * l.g.OW, p.K = l.g.Kd;
@@ -714,8 +719,8 @@ static int launch_fwd_layer(idqn_handle* h, int li, int nz, int nh, int nsamples
   p.scale = scale;
   p.relu = relu;
   p.relu_in = l.relu_in;
-  // the residual input lives in the same activation block as y (same base, same net stride)
-  p.skip = (l.skip_from >= 0 && io.y) ? io.y - l.act_off + h->layers[l.skip_from].act_off : nullptr;
+  p.planes_relu = planes_relu_of(h, li);
+  p.skip = skip;  // the residual input lives in the same activation block as y (same base, same net stride)
   p.nz = nz;
   p.M = nsamples * l.g.OH * l.g.OW;
   p.N = l.g.OC;
@@ -745,6 +750,7 @@ static PoolArgs pool_args(const Layer& l, int nz, int nsamples) {
 static int launch_pool_fwd(idqn_handle* h, int li, int nz, int nsamples, const float* x, float* y, int64_t stride) {
   PoolArgs a = pool_args(h->layers[li], nz, nsamples);
   a.x = x, a.y = y, a.xstride = a.ystride = stride;
+  a.ph = h->act_hi + (y - h->act), a.pl = h->act_lo + (y - h->act), a.planes_relu = planes_relu_of(h, li);
   const int64_t total = (int64_t)nz * nsamples * a.OH * a.OW * a.C;
   maxpool_fwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
   CK(cudaGetLastError());
@@ -756,6 +762,7 @@ static int launch_pool_bwd(idqn_handle* h, int li) {
   const Layer &l = h->layers[li], &prev = h->layers[li - 1];
   PoolArgs a = pool_args(l, h->K, h->B);
   a.x = h->act + prev.act_off, a.dy = h->dact + l.act_off, a.dx = h->dact + prev.act_off;
+  a.ph = h->dact_hi + prev.act_off, a.pl = h->dact_lo + prev.act_off;
   a.xstride = a.ystride = h->act_stride;
   const int64_t total = (int64_t)h->K * h->B * a.IH * a.IW * a.C;
   maxpool_bwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
@@ -890,7 +897,13 @@ static int launch_dgrad_layer(idqn_handle* h, int li, bool img_dst = false) {
     return IDQN_EINVAL;
   }
   const NetPtr wh{h->won_hi, h->won_hi, h->stride, h->stride, K}, wl{h->won_lo, h->won_lo, h->stride, h->stride, K};
+  // relu' of the input: it was the previous layer's relu output, or this layer applied the relu itself (impala blocks)
+  const int mask = (l.relu_in || prev.relu_out) ? 1 : 0;
+  const float* add = nullptr;
+  for (int j = li + 1; j < h->n_layers; ++j)  // a later layer that adds this activation to its output (residual)
+    if (h->layers[j].skip_from == li - 1) add = h->dact + h->layers[j].act_off;
   if (use_tc(h) && tc_dense_ok(h, l)) {
+    REQUIRE(mask && !add, "internal: the dense data-gradient kernel always applies the relu mask");
     tcg::TcDgradDenseT p;
     p.dyh = h->dact_hi + l.act_off, p.dyl = h->dact_lo + l.act_off, p.dystride = h->act_stride;
     p.wh = wh, p.wl = wl;
@@ -926,6 +939,7 @@ static int launch_dgrad_layer(idqn_handle* h, int li, bool img_dst = false) {
     p.wh = wh, p.wl = wl;
     p.w_off = l.w_off;
     p.xact = h->act + prev.act_off, p.dx = h->dact + prev.act_off;
+    p.mask = mask, p.add = add;
     p.dxh = h->dact_hi + prev.act_off, p.dxl = h->dact_lo + prev.act_off, p.xstride = h->act_stride;
     p.ncls = S * S, p.JH = JH, p.JW = JW;
     p.d_jwoc = FastDiv(JW * l.g.OC);
@@ -949,11 +963,7 @@ static int launch_dgrad_layer(idqn_handle* h, int li, bool img_dst = false) {
   p.w = NetPtr{h->online, h->online, h->stride, h->stride, K};
   p.w_off = l.w_off;
   p.xact = h->act + prev.act_off;
-  // relu' of the input: it was the previous layer's relu output, or this layer applied the relu itself (impala blocks)
-  p.mask = (l.relu_in || prev.relu_out) ? 1 : 0;
-  p.add = nullptr;
-  for (int j = li + 1; j < h->n_layers; ++j)  // a later layer that adds this activation to its output (residual)
-    if (h->layers[j].skip_from == li - 1) p.add = h->dact + h->layers[j].act_off;
+  p.mask = mask, p.add = add;
   p.dx = h->dact + prev.act_off;
   p.dxh = h->dact_hi + prev.act_off, p.dxl = h->dact_lo + prev.act_off;
   p.xstride = h->act_stride;
@@ -1361,9 +1371,10 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
   idqn_handle* h = new idqn_handle();
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
-  // impala runs on the fp32 CUDA-core implicit-GEMM kernels (gemm_simt.cuh) + the pool kernels: its pre-activation residual
-  // blocks and 3x3 / 1 convolutions over 1..64 channels are not what the tcgen05 paths were built for
-  if (cfg->arch == IDQN_ARCH_IMPALA) h->cfg.flags |= IDQN_F_SIMT_ONLY;
+  // impala runs on the generic kernels, layer by layer: tcgen05 implicit GEMM (gemm_tc.cuh) where the channel counts allow
+  // vector loads, the fp32 CUDA-core problems (gemm_simt.cuh) elsewhere (first conv: 4 channels x 3 taps; 1..7-channel test
+  // nets), plus the pool kernels.  IDQN_IMPALA_SIMT=1 keeps everything on the CUDA cores.
+  if (cfg->arch == IDQN_ARCH_IMPALA && getenv("IDQN_IMPALA_SIMT")) h->cfg.flags |= IDQN_F_SIMT_ONLY;
   h->K = cfg->n_heads, h->B = cfg->batch_size, h->A = cfg->n_actions;
   int rc = build_layers(h);
   if (rc) {

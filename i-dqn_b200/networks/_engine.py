@@ -205,8 +205,15 @@ class Engine:
         from .architectures._shapes import CNN_SPECS, same_out
         shapes = []
         if self.architecture_type == "impala":
-            raise NotImplementedError("download_activation is a cnn / fc parity aid")
-        if self.architecture_type == "cnn":
+            # engine layer order: per Stack [Conv_0, pool, Conv_1, Conv_2, Conv_3, Conv_4], then the dense trunk
+            h, w, _ = self.obs_shape
+            for i in range(3):
+                f = int(self.cfg.features[i])
+                shapes.append((self.B, h, w, f))
+                h, w = same_out(h, 2), same_out(w, 2)
+                shapes.extend([(self.B, h, w, f)] * 5)
+            start = 3
+        elif self.architecture_type == "cnn":
             h, w, _ = self.obs_shape
             for i, (_, s) in enumerate(CNN_SPECS):
                 h, w = same_out(h, s), same_out(w, s)

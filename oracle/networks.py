@@ -166,12 +166,34 @@ def _conv_same(x_nhwc: torch.Tensor, kernel_hwio: torch.Tensor, bias: torch.Tens
     return y.permute(0, 2, 3, 1)
 
 
-def _max_pool_same(x_nhwc: torch.Tensor, k: int = 3, stride: int = 2) -> torch.Tensor:
+def _max_pool_same(x_nhwc: torch.Tensor, k: int = 3, stride: int = 2, arg=None) -> torch.Tensor:
     """flax.linen.max_pool(x, (3, 3), strides=(2, 2), padding="SAME") (architectures/dqn.py:20): -inf padding."""
     _, hlo, hhi = same_pad(x_nhwc.shape[1], k, stride)
     _, wlo, whi = same_pad(x_nhwc.shape[2], k, stride)
     x = F.pad(x_nhwc.permute(0, 3, 1, 2), (wlo, whi, hlo, hhi), value=float("-inf"))
-    return F.max_pool2d(x, k, stride).permute(0, 2, 3, 1)
+    if arg is None:
+        return F.max_pool2d(x, k, stride).permute(0, 2, 3, 1)
+    # the window element to take is given (ky * k + kx per output, [N, OH, OW, C]): parity tests hand over the decisions of
+    # the implementation under test where two window elements are numerically equal
+    patches = x.unfold(2, k, stride).unfold(3, k, stride)  # [N, C, OH, OW, k, k]
+    patches = patches.reshape(*patches.shape[:4], k * k)
+    a = torch.as_tensor(np.asarray(arg)).to(torch.int64).permute(0, 3, 1, 2).unsqueeze(-1)
+    return torch.gather(patches, 4, a)[..., 0].permute(0, 2, 3, 1)
+
+
+def pool_windows_same(x_nhwc: np.ndarray, k: int = 3, stride: int = 2) -> np.ndarray:
+    """The 3x3 / 2 SAME max-pool windows of x (-inf padding), float64 [N, OH, OW, C, k * k], window elements row-major."""
+    x = torch.as_tensor(np.asarray(x_nhwc, dtype=np.float64))
+    _, hlo, hhi = same_pad(x.shape[1], k, stride)
+    _, wlo, whi = same_pad(x.shape[2], k, stride)
+    xp = F.pad(x.permute(0, 3, 1, 2), (wlo, whi, hlo, hhi), value=float("-inf"))
+    patches = xp.unfold(2, k, stride).unfold(3, k, stride)
+    return patches.reshape(*patches.shape[:4], k * k).permute(0, 2, 3, 1, 4).numpy()
+
+
+def pool_argmax_same(x_nhwc: np.ndarray, k: int = 3, stride: int = 2) -> np.ndarray:
+    """First maximum (row-major over the window) of every max-pool window: [N, OH, OW, C] of ky * k + kx."""
+    return np.argmax(pool_windows_same(x_nhwc, k, stride), axis=4)  # np.argmax returns the first maximum
 
 
 def _to_torch(tree, dtype):
@@ -179,11 +201,14 @@ def _to_torch(tree, dtype):
 
 
 def apply_t(p: Dict[str, Dict[str, torch.Tensor]], x: torch.Tensor, architecture_type: str,
-            collect: list | None = None, gates: list | None = None) -> torch.Tensor:
+            collect: list | None = None, gates: list | None = None, pools: list | None = None,
+            collect_pool: list | None = None) -> torch.Tensor:
     """Torch forward of one head on a batch ``x`` ([N,H,W,C] for cnn, [N,obs] for fc).
     ``p`` is the inner ``params`` dict.  ``collect`` receives the pre-activations (for gate margins).
     ``gates`` (one 0/1 tensor per hidden layer) replaces relu(z) by z*gate: used by the parity tests to give the
-    oracle the gate decisions of the implementation under test where a pre-activation is numerically zero."""
+    oracle the gate decisions of the implementation under test where a pre-activation is numerically zero.
+    ``pools`` (impala: one index array per Stack) does the same for the max-pool's choice inside a window;
+    ``collect_pool`` receives the pool inputs."""
     d = 0
     gi = 0
 
@@ -207,7 +232,9 @@ def apply_t(p: Dict[str, Dict[str, torch.Tensor]], x: torch.Tensor, architecture
         for i in range(3):
             s = p[f"Stack_{i}"]
             x = _conv_same(x, s["Conv_0"]["kernel"], s["Conv_0"]["bias"], 1)  # :14-19 (no activation)
-            x = _max_pool_same(x)  # :20
+            if collect_pool is not None:
+                collect_pool.append(x)
+            x = _max_pool_same(x, arg=None if pools is None else pools[i])  # :20
             for b in range(2):  # :22-27
                 block_input = x
                 x = act(x)
@@ -256,10 +283,10 @@ def compute_target_t(pt, b, arch, gamma, n):
     return b["reward"] + coef * q_next.max(dim=1).values
 
 
-def loss_on_batch_t(p, pt, b, arch, gamma, n, collect=None, gates=None):
+def loss_on_batch_t(p, pt, b, arch, gamma, n, collect=None, gates=None, pools=None, collect_pool=None):
     with torch.no_grad():
         y = compute_target_t(pt, b, arch, gamma, n)  # value_and_grad is w.r.t. arg 0 only (idqn.py:105)
-    q = apply_t(p, b["state"], arch, collect, gates)
+    q = apply_t(p, b["state"], arch, collect, gates, pools, collect_pool)
     q_sa = q.gather(1, b["action"][:, None])[:, 0]  # idqn.py:117
     return torch.square(q_sa - y).mean()  # idqn.py:118,112
 
@@ -278,7 +305,7 @@ def loss_on_batch(params, params_target, batch, arch, gamma, n, dtype=torch.floa
 
 
 def loss_and_grad(params, params_target, batch, arch, gamma, n, dtype=torch.float32, margins=False, gates=None,
-                  preacts=False):
+                  preacts=False, pools=None, pool_inputs=False):
     """(loss, grads pytree[, min |pre-activation| per relu layer]) for ONE head (no K axis)."""
     p = _to_torch(params["params"], dtype)
     for leaf in tree_leaves(p):
@@ -287,9 +314,12 @@ def loss_and_grad(params, params_target, batch, arch, gamma, n, dtype=torch.floa
     b = _batch_t(batch, dtype)
     collect = [] if (margins or preacts) else None
     gates_t = None if gates is None else [torch.as_tensor(np.asarray(g, dtype=np.float32)) for g in gates]
-    loss = loss_on_batch_t(p, pt, b, arch, gamma, n, collect, gates_t)
+    collect_pool = [] if pool_inputs else None
+    loss = loss_on_batch_t(p, pt, b, arch, gamma, n, collect, gates_t, pools, collect_pool)
     loss.backward()
     grads = {"params": tree_map(lambda t: t.grad.detach().numpy().copy(), p)}
+    if pool_inputs:  # (loss, grads, relu pre-activations, max-pool inputs)
+        return float(loss.detach()), grads, [z.detach().numpy() for z in collect], [z.detach().numpy() for z in collect_pool]
     if preacts:
         return float(loss.detach()), grads, [z.detach().numpy() for z in collect]
     if margins:
@@ -332,7 +362,7 @@ def tree_map_tuple(tree, i):
 
 
 def learn_on_batch(params, params_target, opt_state, batch, arch, gamma, n, lr, eps, dtype=torch.float32,
-                   return_grads=False, gates=None):
+                   return_grads=False, gates=None, pools=None):
     """idqn.py:96-109 — vmap over K heads of value_and_grad + adam + apply_updates on a shared batch.
 
     ``opt_state = {"count": int32[K], "mu": tree[K,...], "nu": tree[K,...]}``.
@@ -342,7 +372,8 @@ def learn_on_batch(params, params_target, opt_state, batch, arch, gamma, n, lr, 
     counts = np.asarray(opt_state["count"]).copy()
     for k in range(K):
         pk, tk = tree_index(params, k), tree_index(params_target, k)
-        loss, g = loss_and_grad(pk, tk, batch, arch, gamma, n, dtype, gates=None if gates is None else gates[k])
+        loss, g = loss_and_grad(pk, tk, batch, arch, gamma, n, dtype, gates=None if gates is None else gates[k],
+                                pools=None if pools is None else pools[k])
         p2, m2, v2, c2 = adam_step(pk, g, tree_index(opt_state["mu"], k), tree_index(opt_state["nu"], k),
                                    int(counts[k]), lr, eps, dtype)
         counts[k] = c2
