@@ -632,7 +632,7 @@ def other_configs_leg(iDQN, rb, timed, args, local):
         ag.update_target_params(step)
 
     ms, _, _, _ = timed(ag._engine, fn_impala, 20, 3, 1)
-    out["IMPALA K=1 (fp32 CUDA-core kernels, host batches)"] = round(ms / 20 * 1e3, 2)
+    out["IMPALA K=1 (generic tcgen05 + pool kernels, host batches)"] = round(ms / 20 * 1e3, 2)
     return out
 
 

@@ -139,7 +139,7 @@ struct Layer {
 };
 
 #define IDQN_MAX_LAYERS 32  /* impala: 3 x (5 convs + pool) + dense trunk */
-#define IDQN_PROF_MAX 64
+#define IDQN_PROF_MAX 128
 #define IDQN_IMG_LAYERS 3
 
 // per conv layer state of the image-resident tensor-core path (conv_img.cuh): space-to-depth activation planes

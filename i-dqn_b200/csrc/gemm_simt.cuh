@@ -420,6 +420,89 @@ __device__ __forceinline__ int pool_argmax(const PoolArgs& a, const float* xb, i
   if (best_out) *best_out = best;
   return arg;
 }
+// ---- the pool the reference uses (3 x 3 / 2), four channels per thread ---------------------------------------------------
+// grid = (chunks of 256 threads inside one image, images = nz * B); thread = (row, col, group of 4 channels): 16-byte loads,
+// 32-bit index arithmetic, the nine window loads unrolled.  Same decisions as the generic kernels below (first maximum of a
+// window in row-major order, -inf padding never selected); used when C % 4 == 0 and every pointer / stride is 16-byte aligned.
+__device__ __forceinline__ float4 pool_ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// first maximum of window (oy, ox), per channel of the group: value and position iy * IW + ix
+__device__ __forceinline__ void pool3_window(const PoolArgs& a, const float* xb, int oy, int ox, int c, float4& best, int4& arg) {
+  best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  arg = make_int4(-1, -1, -1, -1);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 + ky - a.PH;
+    if ((unsigned)iy >= (unsigned)a.IH) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 + kx - a.PW;
+      if ((unsigned)ix >= (unsigned)a.IW) continue;
+      const int pos = iy * a.IW + ix;
+      const float4 v = pool_ld4(xb + (uint32_t)pos * a.C + c);
+      if (arg.x < 0 || v.x > best.x) best.x = v.x, arg.x = pos;
+      if (arg.y < 0 || v.y > best.y) best.y = v.y, arg.y = pos;
+      if (arg.z < 0 || v.z > best.z) best.z = v.z, arg.z = pos;
+      if (arg.w < 0 || v.w > best.w) best.w = v.w, arg.w = pos;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) maxpool3_fwd_v4_kernel(const PoolArgs a) {
+  const int C4 = a.C >> 2;
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;  // (oy, ox, c4) inside image blockIdx.y
+  if (i >= (uint32_t)(a.OH * a.OW * C4)) return;
+  const int c = (int)(i % C4) * 4, q = (int)(i / C4), ox = q % a.OW, oy = q / a.OW;
+  const int z = blockIdx.y / a.B, b = blockIdx.y - z * a.B;
+  const float* xb = a.x + (int64_t)z * a.xstride + (int64_t)b * a.IH * a.IW * a.C;
+  float4 best;
+  int4 arg;
+  pool3_window(a, xb, oy, ox, c, best, arg);
+  const int64_t o = (int64_t)z * a.ystride + ((int64_t)b * a.OH * a.OW + q) * a.C + c;
+  *reinterpret_cast<float4*>(a.y + o) = best;
+  if (a.ph) {
+    if (a.planes_relu) best = make_float4(fmaxf(best.x, 0.f), fmaxf(best.y, 0.f), fmaxf(best.z, 0.f), fmaxf(best.w, 0.f));
+    uint2 hi, lo;
+    tc::split4(best, hi, lo);
+    *reinterpret_cast<uint2*>(a.ph + o) = hi, *reinterpret_cast<uint2*>(a.pl + o) = lo;
+  }
+}
+__global__ void __launch_bounds__(256) maxpool3_bwd_v4_kernel(const PoolArgs a) {
+  const int C4 = a.C >> 2;
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;  // (iy, ix, c4) inside image blockIdx.y
+  if (i >= (uint32_t)(a.IH * a.IW * C4)) return;
+  const int c = (int)(i % C4) * 4, pos = (int)(i / C4), ix = pos % a.IW, iy = pos / a.IW;
+  const int z = blockIdx.y / a.B, b = blockIdx.y - z * a.B;
+  const float* xb = a.x + (int64_t)z * a.xstride + (int64_t)b * a.IH * a.IW * a.C;
+  const float* dyb = a.dy + (int64_t)z * a.ystride + (int64_t)b * a.OH * a.OW * a.C;
+  // windows oy with 2 oy - PH <= iy <= 2 oy - PH + 2, ascending (oy, ox): the order the generic kernel sums in
+  const int oy_lo = max(0, (iy + a.PH - 1) / 2), oy_hi = min(a.OH - 1, (iy + a.PH) / 2);
+  const int ox_lo = max(0, (ix + a.PW - 1) / 2), ox_hi = min(a.OW - 1, (ix + a.PW) / 2);
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int oy = oy_lo; oy <= oy_hi; ++oy)
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      float4 best;
+      int4 arg;
+      pool3_window(a, xb, oy, ox, c, best, arg);
+      const float4 d = pool_ld4(dyb + (uint32_t)(oy * a.OW + ox) * a.C + c);
+      if (arg.x == pos) g.x += d.x;
+      if (arg.y == pos) g.y += d.y;
+      if (arg.z == pos) g.z += d.z;
+      if (arg.w == pos) g.w += d.w;
+    }
+  const int64_t o = (int64_t)z * a.xstride + ((int64_t)b * a.IH * a.IW + pos) * a.C + c;
+  *reinterpret_cast<float4*>(a.dx + o) = g;
+  if (a.ph) {
+    uint2 hi, lo;
+    tc::split4(g, hi, lo);
+    *reinterpret_cast<uint2*>(a.ph + o) = hi, *reinterpret_cast<uint2*>(a.pl + o) = lo;
+  }
+}
+// the fast kernels apply: 3 x 3 / 2, channel groups of four, 16-byte aligned tensors, one image within 2^31 elements
+inline bool pool3_v4_ok(const PoolArgs& a, const void* p0, const void* p1, const void* p2) {
+  auto al = [](const void* p, size_t n) { return (reinterpret_cast<uintptr_t>(p) % n) == 0; };
+  return a.K == 3 && a.S == 2 && a.C % 4 == 0 && a.xstride % 4 == 0 && a.ystride % 4 == 0 && al(p0, 16) && al(p1, 16) && al(p2, 16) &&
+         (!a.ph || (al(a.ph, 8) && al(a.pl, 8))) && (int64_t)a.IH * a.IW * a.C < (1ll << 31) && (int64_t)a.nz * a.B <= 65535;
+}
+
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const PoolArgs a) {
   const int64_t per = (int64_t)a.B * a.OH * a.OW * a.C, total = per * a.nz;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {

@@ -752,7 +752,10 @@ static int launch_pool_fwd(idqn_handle* h, int li, int nz, int nsamples, const f
   a.x = x, a.y = y, a.xstride = a.ystride = stride;
   a.ph = h->act_hi + (y - h->act), a.pl = h->act_lo + (y - h->act), a.planes_relu = planes_relu_of(h, li);
   const int64_t total = (int64_t)nz * nsamples * a.OH * a.OW * a.C;
-  maxpool_fwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
+  if (pool3_v4_ok(a, a.x, a.y, a.y))
+    maxpool3_fwd_v4_kernel<<<dim3((unsigned)((a.OH * a.OW * (a.C / 4) + 255) / 256), (unsigned)(nz * nsamples)), 256, 0, h->stream>>>(a);
+  else
+    maxpool_fwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
   CK(cudaGetLastError());
   mark(h, "pool_fwd_L%d", li);
   return IDQN_OK;
@@ -765,7 +768,10 @@ static int launch_pool_bwd(idqn_handle* h, int li) {
   a.ph = h->dact_hi + prev.act_off, a.pl = h->dact_lo + prev.act_off;
   a.xstride = a.ystride = h->act_stride;
   const int64_t total = (int64_t)h->K * h->B * a.IH * a.IW * a.C;
-  maxpool_bwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
+  if (pool3_v4_ok(a, a.x, a.dy, a.dx))
+    maxpool3_bwd_v4_kernel<<<dim3((unsigned)((a.IH * a.IW * (a.C / 4) + 255) / 256), (unsigned)(h->K * h->B)), 256, 0, h->stream>>>(a);
+  else
+    maxpool_bwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
   CK(cudaGetLastError());
   mark(h, "pool_bwd_L%d", li);
   return IDQN_OK;
