@@ -255,3 +255,34 @@ def test_impala_two_independent_oracles_agree_in_float64(obs, feats, A):
     assert losses.shape == (2,) and o2["count"].tolist() == [1, 1]
     assert p2["params"]["Stack_2"]["Conv_3"]["kernel"].shape == (2, 3, 3, feats[2], feats[2])
     assert not np.array_equal(p2["params"]["Stack_0"]["Conv_0"]["kernel"], pk["params"]["Stack_0"]["Conv_0"]["kernel"])
+
+
+def test_impala_forced_pool_choices():
+    """The max-pool decisions the GPU parity test hands to the oracle (`pools=`): with the oracle's own choices nothing changes;
+    `pool_argmax_same` is the first maximum in row-major window order (the NumPy oracle's rule, = the CUDA kernels'); and moving
+    ONE choice to another window element moves gradients of the Conv_0 that feeds that pool."""
+    rng = np.random.default_rng(23)
+    obs, feats, A, B = (13, 12, 4), [4, 6, 5, 8], 3, 3
+    p = O.init_params(rng, obs, feats, "impala", A, bias_scale=0.1)
+    t = O.init_params(rng, obs, feats, "impala", A, bias_scale=0.1)
+    batch = small_batch(rng, B, obs, A)
+    l0, g0, z, pin = O.loss_and_grad(p, t, batch, "impala", 0.9, 1, torch.float64, preacts=True, pool_inputs=True)
+    assert [x.shape[1:3] for x in pin] == [(13, 12), (7, 6), (4, 3)] and len(z) == 14
+    pools = [O.pool_argmax_same(x) for x in pin]
+    for x, a in zip(pin, pools):
+        np.testing.assert_array_equal(a, N.maxpool_forward(x)[1][0])
+        w = O.pool_windows_same(x)
+        np.testing.assert_array_equal(np.take_along_axis(w, a[..., None], 4)[..., 0], N.maxpool_forward(x)[0])
+    # ties: the first of equal elements wins
+    tie = np.zeros((1, 4, 4, 1))
+    assert O.pool_argmax_same(tie)[0, 0, 0, 0] == 0 and O.pool_argmax_same(tie)[0, 1, 1, 0] == 0
+    l1, g1 = O.loss_and_grad(p, t, batch, "impala", 0.9, 1, torch.float64, pools=pools)
+    assert abs(l1 - l0) <= 1e-14
+    for a, b in zip(O.tree_leaves(g0), O.tree_leaves(g1)):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-14)
+    moved = [a.copy() for a in pools]
+    w = O.pool_windows_same(pin[1])[1, 2, 2, 3]
+    moved[1][1, 2, 2, 3] = int(np.argsort(w)[-2])  # the runner-up of an interior window (finite: -inf only pads the border)
+    l2, g2 = O.loss_and_grad(p, t, batch, "impala", 0.9, 1, torch.float64, pools=moved)
+    assert abs(l2 - l0) > 1e-9
+    assert not np.array_equal(g2["params"]["Stack_1"]["Conv_0"]["kernel"], g0["params"]["Stack_1"]["Conv_0"]["kernel"])
