@@ -123,14 +123,15 @@ struct TcFwdConv {
     r.base = (int64_t)b * g.IH * g.IW * g.IC;
     return r;
   }
-  // A unit: row = output pixel, 8 consecutive k = (ky, kx, c..c+7); `half` selects one of the two pixels when IC == 4
+  // A unit: row = output pixel, 8 consecutive k = (ky, kx, c..c+7); when IC == 4 a unit is two taps of four channels and
+  // `half` selects one of them: each is decoded on its own, so the pair may straddle a kernel row (odd KW) or the end of K
   __device__ __forceinline__ Src srcA(const Ctx& c, const Row& r, int k, int half) const {
     uint32_t ky, rem, kx, ch;
-    g.d_kwic.divmod(k < K ? k : 0, ky, rem);
+    const int kk = k + 4 * half;
+    g.d_kwic.divmod(kk < K ? kk : 0, ky, rem);
     g.d_ic.divmod(rem, kx, ch);
-    const int iy = r.iy0 + (int)ky, ix = r.ix0 + (int)kx + half;
-    const bool ok = r.valid && k < c.kend && (unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW &&
-                    (int)kx + half < g.KW;
+    const int iy = r.iy0 + (int)ky, ix = r.ix0 + (int)kx;
+    const bool ok = r.valid && kk < c.kend && (unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW;
     const int64_t idx = ok ? r.base + ((int64_t)iy * g.IW + ix) * g.IC + ch : 0;
     return Src{c.ah + idx, c.al + idx, ok};
   }
@@ -333,16 +334,19 @@ struct TcWgradConv {
   __device__ __forceinline__ Row rowA(const Ctx&, int) const { return Row{}; }
   // A unit (MN-major): one k = output pixel, 8 consecutive m = (ky, kx, c..c+7); row Kd is the ones row whose
   // product with dy is the bias gradient (it lands on the bias slot right behind the kernel in the arena)
+  // (IC == 4: a unit is two 4-channel taps, `half` selects one; each is decoded on its own -- with Kd = 36 (3 x 3 x 4) the ones
+  // row is the second half of the unit that starts at row 32)
   __device__ __forceinline__ Src srcA(const Ctx& c, int k, int m, int half) const {
-    if (m == g.Kd) return Src{ones + 4 * half, ones + 8 + 4 * half, k < c.kend && half == 0};
-    const bool inr = k < c.kend && m < g.Kd;
+    const int mm = m + 4 * half;
+    if (mm == g.Kd) return Src{ones, ones + 8, k < c.kend};
+    const bool inr = k < c.kend && mm < g.Kd;
     uint32_t b, rem, oy, ox, ky, rem2, kx, ch;
     g.d_ohow.divmod(inr ? k : 0, b, rem);
     g.d_ow.divmod(rem, oy, ox);
-    g.d_kwic.divmod(inr ? m : 0, ky, rem2);
+    g.d_kwic.divmod(inr ? mm : 0, ky, rem2);
     g.d_ic.divmod(rem2, kx, ch);
-    const int iy = (int)(oy * g.S + ky) - g.PH, ix = (int)(ox * g.S + kx) + half - g.PW;
-    const bool ok = inr && (unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW && (int)kx + half < g.KW;
+    const int iy = (int)(oy * g.S + ky) - g.PH, ix = (int)(ox * g.S + kx) - g.PW;
+    const bool ok = inr && (unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW;
     const int64_t idx = ok ? (((int64_t)b * g.IH + iy) * g.IW + ix) * g.IC + ch : 0;
     return Src{c.ah + idx, c.al + idx, ok};
   }

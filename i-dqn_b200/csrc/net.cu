@@ -498,7 +498,7 @@ static bool use_tc(const idqn_handle* h) { return !(h->cfg.flags & IDQN_F_SIMT_O
 // which layers the tensor-core kernels cover (vector-load friendly shapes); everything else runs the fp32 SIMT path
 static bool tc_conv_ok(const Layer& l) {
   const ConvGeom& g = l.g;
-  const bool ic_ok = (g.IC % 8 == 0) || (g.IC == 4 && g.KW % 2 == 0);
+  const bool ic_ok = (g.IC % 8 == 0) || g.IC == 4;  // 16-byte operand units, or two 8-byte taps of four channels
   return l.is_conv && ic_ok && g.OC % 8 == 0 && g.OC <= 256 && g.IC <= 256;
 }
 static bool tc_dense_ok(const idqn_handle* h, const Layer& l) {
