@@ -163,6 +163,10 @@ struct idqn_handle {
   cudaStream_t stream;
   // SM partitions of the backward pass (sm_partition.cuh): conv chain | HBM-bound Dense_0 wgrad+Adam
   void* partition;      // smpart::Partition, null when green contexts are unavailable or disabled
+  // impala: the max-pool forward of the learning step records which window element it took (one byte per output element of the
+  // online nets, indexed like act); the backward reads it.  pool_arg_ok[li]: the last step forward of pool layer li recorded it
+  uint8_t* pool_arg;
+  unsigned char pool_arg_ok[IDQN_MAX_LAYERS];
   cudaEvent_t ev_fork, ev_join[2];
   // second branch of the step graph: the conv weight-gradient kernels run next to the conv data-gradient chain
   cudaStream_t side, side2;

@@ -402,6 +402,10 @@ struct PoolArgs {
   float* dx;
   __nv_bfloat16 *ph, *pl;    // optional bf16 hi / lo planes of the output (forward: of y, relu'd if planes_relu; backward: of dx)
   int planes_relu;
+  // optional record of the forward's choices, one byte per output element (ky * 3 + kx), indexed like y for nets < arg_nets:
+  // written by the learning step's forward, read by its backward instead of re-scanning nine inputs per window (3 x 3 / 2 kernels)
+  uint8_t* arg;
+  int arg_nets;
   int64_t xstride, ystride;  // floats between nets
 };
 __device__ __forceinline__ int pool_argmax(const PoolArgs& a, const float* xb, int oy, int ox, int c, float* best_out) {
@@ -425,7 +429,7 @@ __device__ __forceinline__ int pool_argmax(const PoolArgs& a, const float* xb, i
 // 32-bit index arithmetic, the nine window loads unrolled.  Same decisions as the generic kernels below (first maximum of a
 // window in row-major order, -inf padding never selected); used when C % 4 == 0 and every pointer / stride is 16-byte aligned.
 __device__ __forceinline__ float4 pool_ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-// first maximum of window (oy, ox), per channel of the group: value and position iy * IW + ix
+// first maximum of window (oy, ox), per channel of the group: value and window element ky * 3 + kx
 __device__ __forceinline__ void pool3_window(const PoolArgs& a, const float* xb, int oy, int ox, int c, float4& best, int4& arg) {
   best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   arg = make_int4(-1, -1, -1, -1);
@@ -437,12 +441,12 @@ __device__ __forceinline__ void pool3_window(const PoolArgs& a, const float* xb,
     for (int kx = 0; kx < 3; ++kx) {
       const int ix = ox * 2 + kx - a.PW;
       if ((unsigned)ix >= (unsigned)a.IW) continue;
-      const int pos = iy * a.IW + ix;
-      const float4 v = pool_ld4(xb + (uint32_t)pos * a.C + c);
-      if (arg.x < 0 || v.x > best.x) best.x = v.x, arg.x = pos;
-      if (arg.y < 0 || v.y > best.y) best.y = v.y, arg.y = pos;
-      if (arg.z < 0 || v.z > best.z) best.z = v.z, arg.z = pos;
-      if (arg.w < 0 || v.w > best.w) best.w = v.w, arg.w = pos;
+      const int code = ky * 3 + kx;
+      const float4 v = pool_ld4(xb + (uint32_t)(iy * a.IW + ix) * a.C + c);
+      if (arg.x < 0 || v.x > best.x) best.x = v.x, arg.x = code;
+      if (arg.y < 0 || v.y > best.y) best.y = v.y, arg.y = code;
+      if (arg.z < 0 || v.z > best.z) best.z = v.z, arg.z = code;
+      if (arg.w < 0 || v.w > best.w) best.w = v.w, arg.w = code;
     }
   }
 }
@@ -458,6 +462,7 @@ __global__ void __launch_bounds__(256) maxpool3_fwd_v4_kernel(const PoolArgs a) 
   pool3_window(a, xb, oy, ox, c, best, arg);
   const int64_t o = (int64_t)z * a.ystride + ((int64_t)b * a.OH * a.OW + q) * a.C + c;
   *reinterpret_cast<float4*>(a.y + o) = best;
+  if (a.arg && z < a.arg_nets) *reinterpret_cast<uint32_t*>(a.arg + o) = (uint32_t)arg.x | ((uint32_t)arg.y << 8) | ((uint32_t)arg.z << 16) | ((uint32_t)arg.w << 24);
   if (a.ph) {
     if (a.planes_relu) best = make_float4(fmaxf(best.x, 0.f), fmaxf(best.y, 0.f), fmaxf(best.z, 0.f), fmaxf(best.w, 0.f));
     uint2 hi, lo;
@@ -472,21 +477,29 @@ __global__ void __launch_bounds__(256) maxpool3_bwd_v4_kernel(const PoolArgs a) 
   const int c = (int)(i % C4) * 4, pos = (int)(i / C4), ix = pos % a.IW, iy = pos / a.IW;
   const int z = blockIdx.y / a.B, b = blockIdx.y - z * a.B;
   const float* xb = a.x + (int64_t)z * a.xstride + (int64_t)b * a.IH * a.IW * a.C;
-  const float* dyb = a.dy + (int64_t)z * a.ystride + (int64_t)b * a.OH * a.OW * a.C;
+  const int64_t yoff = (int64_t)z * a.ystride + (int64_t)b * a.OH * a.OW * a.C;
+  const float* dyb = a.dy + yoff;
   // windows oy with 2 oy - PH <= iy <= 2 oy - PH + 2, ascending (oy, ox): the order the generic kernel sums in
   const int oy_lo = max(0, (iy + a.PH - 1) / 2), oy_hi = min(a.OH - 1, (iy + a.PH) / 2);
   const int ox_lo = max(0, (ix + a.PW - 1) / 2), ox_hi = min(a.OW - 1, (ix + a.PW) / 2);
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int oy = oy_lo; oy <= oy_hi; ++oy)
     for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-      float4 best;
+      const int me = (iy - (oy * 2 - a.PH)) * 3 + (ix - (ox * 2 - a.PW));  // this input as an element of window (oy, ox)
+      const uint32_t w = (uint32_t)(oy * a.OW + ox) * a.C + c;
       int4 arg;
-      pool3_window(a, xb, oy, ox, c, best, arg);
-      const float4 d = pool_ld4(dyb + (uint32_t)(oy * a.OW + ox) * a.C + c);
-      if (arg.x == pos) g.x += d.x;
-      if (arg.y == pos) g.y += d.y;
-      if (arg.z == pos) g.z += d.z;
-      if (arg.w == pos) g.w += d.w;
+      if (a.arg) {
+        const uint32_t packed = __ldg(reinterpret_cast<const uint32_t*>(a.arg + yoff + w));
+        arg = make_int4(packed & 0xff, (packed >> 8) & 0xff, (packed >> 16) & 0xff, packed >> 24);
+      } else {
+        float4 best;
+        pool3_window(a, xb, oy, ox, c, best, arg);
+      }
+      const float4 d = pool_ld4(dyb + w);
+      if (arg.x == me) g.x += d.x;
+      if (arg.y == me) g.y += d.y;
+      if (arg.z == me) g.z += d.z;
+      if (arg.w == me) g.w += d.w;
     }
   const int64_t o = (int64_t)z * a.xstride + ((int64_t)b * a.IH * a.IW + pos) * a.C + c;
   *reinterpret_cast<float4*>(a.dx + o) = g;

@@ -747,12 +747,18 @@ static PoolArgs pool_args(const Layer& l, int nz, int nsamples) {
   a.PH = l.g.PH, a.PW = l.g.PW, a.K = l.g.KH, a.S = l.g.S;
   return a;
 }
-static int launch_pool_fwd(idqn_handle* h, int li, int nz, int nsamples, const float* x, float* y, int64_t stride) {
+// step = the learning step's forward over [online K | target K]: the choices of the online nets are recorded for the backward
+static int launch_pool_fwd(idqn_handle* h, int li, int nz, int nsamples, const float* x, float* y, int64_t stride, bool step = false) {
   PoolArgs a = pool_args(h->layers[li], nz, nsamples);
   a.x = x, a.y = y, a.xstride = a.ystride = stride;
   a.ph = h->act_hi + (y - h->act), a.pl = h->act_lo + (y - h->act), a.planes_relu = planes_relu_of(h, li);
   const int64_t total = (int64_t)nz * nsamples * a.OH * a.OW * a.C;
-  if (pool3_v4_ok(a, a.x, a.y, a.y))
+  const bool fast = pool3_v4_ok(a, a.x, a.y, a.y);
+  if (step) {
+    h->pool_arg_ok[li] = fast && h->pool_arg != nullptr;
+    if (h->pool_arg_ok[li]) a.arg = h->pool_arg + (y - h->act), a.arg_nets = h->K;
+  }
+  if (fast)
     maxpool3_fwd_v4_kernel<<<dim3((unsigned)((a.OH * a.OW * (a.C / 4) + 255) / 256), (unsigned)(nz * nsamples)), 256, 0, h->stream>>>(a);
   else
     maxpool_fwd_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, h->sm_count * 16), 256, 0, h->stream>>>(a);
@@ -767,6 +773,7 @@ static int launch_pool_bwd(idqn_handle* h, int li) {
   a.x = h->act + prev.act_off, a.dy = h->dact + l.act_off, a.dx = h->dact + prev.act_off;
   a.ph = h->dact_hi + prev.act_off, a.pl = h->dact_lo + prev.act_off;
   a.xstride = a.ystride = h->act_stride;
+  if (h->pool_arg_ok[li]) a.arg = h->pool_arg + l.act_off, a.arg_nets = h->K;  // else the kernel re-scans the windows
   const int64_t total = (int64_t)h->K * h->B * a.IH * a.IW * a.C;
   if (pool3_v4_ok(a, a.x, a.dy, a.dx))
     maxpool3_bwd_v4_kernel<<<dim3((unsigned)((a.IH * a.IW * (a.C / 4) + 255) / 256), (unsigned)(h->K * h->B)), 256, 0, h->stream>>>(a);
@@ -1089,7 +1096,7 @@ static int enqueue_learn_step(idqn_handle* h, int x_u8, bool dry = false, int64_
     io.y = h->act + o, io.yh = h->act_hi + o, io.yl = h->act_lo + o, io.ystride = h->act_stride;
     if (h->layers[li].kind == IDQN_LAYER_POOL) {
       if (dry) continue;
-      int rc = launch_pool_fwd(h, li, 2 * K, B, h->act + h->layers[li - 1].act_off, h->act + o, h->act_stride);
+      int rc = launch_pool_fwd(h, li, 2 * K, B, h->act + h->layers[li - 1].act_off, h->act + o, h->act_stride, true);
       if (rc) return rc;
       continue;
     }
@@ -1475,6 +1482,10 @@ extern "C" int idqn_create(const idqn_config* cfg, idqn_handle** out) {
     CK(cudaMalloc(&h->in_lo, ip));
     CK(cudaMemsetAsync(h->in_hi, 0, ip, h->stream));
     CK(cudaMemsetAsync(h->in_lo, 0, ip, h->stream));
+    if (cfg->arch == IDQN_ARCH_IMPALA && !getenv("IDQN_POOL_RESCAN")) {
+      CK(cudaMalloc(&h->pool_arg, (size_t)h->act_stride * K));
+      CK(cudaMemsetAsync(h->pool_arg, 0, (size_t)h->act_stride * K, h->stream));
+    }
     CK(cudaMalloc(&h->ones, sizeof(__nv_bfloat16) * 16));
     CK(cudaMemsetAsync(h->ones, 0, sizeof(__nv_bfloat16) * 16, h->stream));
     const uint16_t one_bits = 0x3F80;  // bf16(1.0)
@@ -1533,7 +1544,7 @@ extern "C" int idqn_destroy(idqn_handle* h) {
                   h->s2,     h->action, h->reward, h->terminal, h->act,  h->dact,  h->q,    h->part,     h->tickets};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  void* planes[] = {h->wpl_hi, h->wpl_lo, h->act_hi, h->act_lo, h->dact_hi, h->dact_lo, h->in_hi, h->in_lo, h->ones};
+  void* planes[] = {h->wpl_hi, h->wpl_lo, h->act_hi, h->act_lo, h->dact_hi, h->dact_lo, h->in_hi, h->in_lo, h->ones, h->pool_arg};
   img_free(h);
   for (void* p : planes)
     if (p) cudaFree(p);
