@@ -868,11 +868,14 @@ static inline cudaError_t launch_tc(const P& p, dim3 grid, float* part, int* tic
   return launch_pdl(pdl, kern, grid, dim3(NTHR), smem, st, p, part, tickets);
 }
 
-// stages that keep two CTAs resident per SM
+// ring depth: at most 56 KB of stages per CTA, i.e. three or four CTAs resident per SM (impala K = 5 step, shared-memory limit
+// per CTA 100 / 72 / 54 / 40 KB: 8.27 / 7.74 / 7.67 / 7.66 ms -- these kernels hide their gather latency with resident CTAs, not
+// with ring depth; the k-block order, hence every rounding, does not depend on the depth).  IDQN_TC_SMEM_KB overrides.
 static inline int pick_stages(int a_planes, int NT, int kblocks) {
   const size_t stage = (size_t)a_planes * 128 * BK * 2 + 2 * (size_t)NT * BK * 2;
+  static const size_t limit = (getenv("IDQN_TC_SMEM_KB") ? (size_t)atoi(getenv("IDQN_TC_SMEM_KB")) : 56) * 1024;
   int n = NS;
-  while (n > 2 && n * stage > 100 * 1024) --n;
+  while (n > 2 && n * stage > limit) --n;
   return std::max(2, std::min(n, kblocks + 1));  // the ring needs >= 2 stages
 }
 

@@ -23,12 +23,12 @@ class GpuChain:
     def __init__(self, name, flags=0):
         from idqn_b200.networks.idqn import iDQN
         c = G.CONFIGS[name]
-        obs = c["obs"] if c["arch"] == "cnn" else c["obs"][0]
+        obs = c["obs"] if c["arch"] in ("cnn", "impala") else c["obs"][0]
         self.agent = iDQN(0, obs, c["A"], c["K"], c["feats"], c["arch"], c["lr"], G.GAMMA, G.NSTEP, 1, G.T, G.D, c["eps"],
                           batch_size=G.B, flags=flags)
 
     def start(self, params, target):
-        self.agent.params, self.agent.target_params = params, target
+        self.agent.params, self.agent.target_params = GN.N.nest_modules(params), GN.N.nest_modules(target)
 
     def step(self, batch):
         a = self.agent

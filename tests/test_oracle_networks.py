@@ -170,6 +170,7 @@ class TorchChain(NumpyChain):
     fixture -- the calibration of the envelope the CUDA path is held to (tests/golden_network.py)."""
 
     def start(self, params, target):
+        params, target = N.nest_modules(params), N.nest_modules(target)  # flax's nesting (impala: Stack_i / Conv_j)
         self.p, self.t, self.st = params, target, O.init_optimizer_state(params)
 
     def step(self, batch):
@@ -186,14 +187,14 @@ class TorchChain(NumpyChain):
             self.t = O.sync_target_params(self.p, self.t)
 
 
-@pytest.mark.parametrize("name,steps", [("mlp_k3", None), ("cnn_k1", 2)])
+@pytest.mark.parametrize("name,steps", [("mlp_k3", None), ("cnn_k1", 2), ("impala_k2", 2)])
 def test_numpy_oracle_reproduces_the_committed_fixture(name, steps):
     for row in GN.run_chain(name, NumpyChain(name), steps=steps):
         for what in ("loss", "param", "mu", "nu", "final_target", "final_param"):
             assert row.get(what, 0.0) <= 1e-12, (row["step"], what, row[what])
 
 
-@pytest.mark.parametrize("name", ["mlp_k3", "cnn_k1"])
+@pytest.mark.parametrize("name", ["mlp_k3", "cnn_k1", "impala_k2"])
 def test_torch_fp32_oracle_free_running_stays_inside_the_stated_envelope(name):
     GN.check(GN.run_chain(name, TorchChain(name)))
 
