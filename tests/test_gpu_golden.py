@@ -56,15 +56,15 @@ def first_step_gradients(name):
     return (e_loss,) + GN.tensor_errors(name, z, "s1/grad", chain.agent.gradients(), G.CONFIGS[name]["K"])
 
 
-@pytest.mark.parametrize("name", ["mlp_k3", "cnn_k1", "cnn_k3", "cnn_k5", "cnn_k8"])
+@pytest.mark.parametrize("name", ["mlp_k3", "cnn_k1", "cnn_k3", "cnn_k5", "cnn_k8", "impala_k2"])
 def test_free_running_ten_steps_against_the_float64_fixture(name):
-    """BASELINE configs [0], [1], [2], the K=5 benchmark configuration and K=8 (configs[3] on one GPU): 10 un-synchronised
-    steps incl. one D-sync and one T-shift; losses every step, parameters / mu / nu / count at the checkpoint steps,
+    """BASELINE configs [0], [1], [2], the K=5 benchmark configuration, K=8 (configs[3] on one GPU) and the impala
+    architecture: 10 un-synchronised steps incl. one D-sync and one T-shift; losses every step, parameters / mu / nu / count at the checkpoint steps,
     target and online parameters after the last events."""
     GN.check(GN.run_chain(name, GpuChain(name)))
 
 
-@pytest.mark.parametrize("name", ["mlp_k3", "cnn_k1", "cnn_k5", "cnn_k8"])
+@pytest.mark.parametrize("name", ["mlp_k3", "cnn_k1", "cnn_k5", "cnn_k8", "impala_k2"])
 def test_first_step_gradients_against_the_float64_fixture(name):
     e_loss, e_grad, where = first_step_gradients(name)
     assert e_loss <= 1e-4, f"loss off by {e_loss:.2e}"
