@@ -375,6 +375,9 @@ def run_ours(args):
         try:
             ag2 = make_agent(k_total, flags=args.flags)
             L.check(ag2._engine.lib.idqn_set_dense_update_ctas(ag2._engine.h, 0))
+            # idqn_profile_step runs the step on whatever the handle's staging buffers hold: give the fresh handle a valid batch
+            # first (a never-fed handle's action buffer is uninitialised device memory, and the loss kernel indexes Q with it)
+            ag2._engine.learn_host(pool[0], want_losses=True)
             acc2 = profile_kernels(ag2._engine, L)
             rl["whole_machine"] = {"ctas": "all", "us": round(acc2[top] * 1e3, 2), "achieved": rl["achieved"] * acc[top] / acc2[top],
                                    "frac": rl["frac"] * acc[top] / acc2[top]}

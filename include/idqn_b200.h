@@ -138,7 +138,9 @@ int idqn_read_td_abs(idqn_handle* h, float* out_host);
 int idqn_read_cumulated_losses(idqn_handle* h, double* sums_host, int reset);
 
 /* measurement aids (no reference counterpart): kernels one step launches, and one un-graphed step with a CUDA
- * event after every launch -> ms[i] / names[32*i..] per kernel, in launch order (uses the staged batch) */
+ * event after every launch -> ms[i] / names[32*i..] per kernel, in launch order.  It runs on the batch the LAST host-batch
+ * learning call staged: call it only after at least one idqn_learn_on_batch_host (a never-fed handle's staging buffers are
+ * uninitialised device memory, and like idqn_learn_on_batch_dev the step does not validate the action indices it is given) */
 int idqn_kernels_per_step(idqn_handle* h);
 int idqn_profile_step(idqn_handle* h, int state_is_u8, int max_entries, float* ms, char* names, int* n_out);
 /* IDQN_F_TIMELINE handles: global-timer stamps (ns) of the kernels of the most recent step in launch order, out[2*i] =
