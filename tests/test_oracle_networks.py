@@ -287,3 +287,20 @@ def test_impala_forced_pool_choices():
     l2, g2 = O.loss_and_grad(p, t, batch, "impala", 0.9, 1, torch.float64, pools=moved)
     assert abs(l2 - l0) > 1e-9
     assert not np.array_equal(g2["params"]["Stack_1"]["Conv_0"]["kernel"], g0["params"]["Stack_1"]["Conv_0"]["kernel"])
+
+
+def test_module_name_flattening_round_trip():
+    """The fixtures and the NumPy chain functions use two-level trees with dotted module names; flax's nesting comes back
+    unchanged, cnn / fc trees are untouched, K-stacked leaves keep their axis."""
+    rng = np.random.default_rng(1)
+    nested = O.init_params(rng, (20, 18, 4), [4, 3, 5, 6], "impala", 3, n_networks=2)
+    flat = N.flatten_modules(nested)
+    assert sorted(flat["params"])[:3] == ["Dense_0", "Dense_1", "Stack_0.Conv_0"] and len(flat["params"]) == 17
+    assert flat["params"]["Stack_2.Conv_4"]["kernel"].shape == (2, 3, 3, 5, 5)
+    back = N.nest_modules(flat)
+    assert sorted(back["params"]) == sorted(nested["params"])
+    for a, b in zip(O.tree_leaves(back), O.tree_leaves(nested)):
+        assert a is b
+    cnn = O.init_params(rng, (84, 84, 4), [32, 64, 64, 512], "cnn", 6)
+    assert N.flatten_modules(cnn)["params"].keys() == cnn["params"].keys() == N.nest_modules(cnn)["params"].keys()
+    assert N.flatten_modules(flat)["params"].keys() == flat["params"].keys()  # idempotent
